@@ -1,0 +1,222 @@
+// bvh_b200/csrc/build_core.cuh — LBVH construction logic shared by the CUDA kernels and the host
+// emulation used by the CPU tests.
+//
+// What it replaces: DefaultBuilder<Node>::build and the builders behind it (reference
+// default_builder.h:33-62, mini_tree_builder.h, binned_sah_builder.h, sweep_sah_builder.h).  The
+// output keeps the reference's data structure invariants: root at index 0,
+// sibling pairs adjacent with the left child at an odd index (bvh.h:34-54), packed leaf/inner index
+// (index.h:51-53), prim_ids a permutation, parent boxes enclosing child boxes computed with the
+// reference's own extend() order (bbox.h:23-27, bvh.h:213-217), larger-area child on the left
+// (SATO, top_down_sah_builder.h:101-108) and leaves of at most max_leaf_size primitives decided by
+// the reference's SAH leaf-cost model (split_heuristic.h:30-38).
+//
+// Pipeline (lbvh_build.cu):  centre bounds -> Morton keys (quantisation as mini_tree_builder.h:170-183,
+// bit interleave as utils.h:103-120) -> radix sort -> ONE bottom-up pass (this file) that links the
+// hierarchy, unions the boxes, applies the SAH leaf collapse and writes every node directly into its
+// final reference-layout slot.  Node numbering: internal node p is the split between sorted
+// primitives p and p+1 and its two children live at reference indices 2p+1 and 2p+2; the root's own
+// record is index 0.
+#pragma once
+
+#include "core.cuh"
+
+namespace bvhb200 {
+
+// ---- Morton codes ---------------------------------------------------------------------------
+// utils.h:103-120 (split_bits / morton_encode) specialised to 10 bits per axis in 32 bits and
+// 21 bits per axis in 64 bits.
+BVH_HD uint32_t spread_bits_10(uint32_t x) {
+    x &= 0x000003FFu;
+    x = (x | (x << 16)) & 0xFF0000FFu;
+    x = (x | (x << 8))  & 0x0F00F00Fu;
+    x = (x | (x << 4))  & 0xC30C30C3u;
+    x = (x | (x << 2))  & 0x49249249u;
+    return x;
+}
+BVH_HD uint64_t spread_bits_21(uint64_t x) {
+    x &= 0x1FFFFFull;
+    x = (x | (x << 32)) & 0x001F00000000FFFFull;
+    x = (x | (x << 16)) & 0x001F0000FF0000FFull;
+    x = (x | (x << 8))  & 0x100F00F00F00F00Full;
+    x = (x | (x << 4))  & 0x10C30C30C30C30C3ull;
+    x = (x | (x << 2))  & 0x1249249249249249ull;
+    return x;
+}
+
+template <typename K> struct MortonTraits;
+template <> struct MortonTraits<uint32_t> {
+    static constexpr int bits_per_axis = 10;
+    static BVH_HD uint32_t encode(uint32_t x, uint32_t y, uint32_t z) {
+        return spread_bits_10(x) | (spread_bits_10(y) << 1) | (spread_bits_10(z) << 2);
+    }
+};
+template <> struct MortonTraits<uint64_t> {
+    static constexpr int bits_per_axis = 21;
+    static BVH_HD uint64_t encode(uint64_t x, uint64_t y, uint64_t z) {
+        return spread_bits_21(x) | (spread_bits_21(y) << 1) | (spread_bits_21(z) << 2);
+    }
+};
+
+// Grid placement of a centre, as mini_tree_builder.h:170-183 does it: scale = dim * safe_inverse(diag),
+// offset = -min * scale, p = max(fma(c, scale, offset), 0), cell = min(dim - 1, (size_t)p).
+template <typename T> struct GridXform { T scale[3], offset[3]; };
+
+template <typename T> BVH_HD GridXform<T> make_grid_xform(const T cmin[3], const T cmax[3], int bits_per_axis) {
+    using R = Real<T>;
+    GridXform<T> g;
+    const T dim = (T)((uint64_t)1 << bits_per_axis);
+    for (int a = 0; a < 3; ++a) {
+        g.scale[a] = R::mul(dim, safe_inverse(R::sub(cmax[a], cmin[a])));
+        g.offset[a] = R::mul(R::neg(cmin[a]), g.scale[a]);
+    }
+    return g;
+}
+
+template <typename T, typename K> BVH_HD K morton_key(const T c[3], const GridXform<T>& g) {
+    using R = Real<T>;
+    const uint64_t last = ((uint64_t)1 << MortonTraits<K>::bits_per_axis) - 1;
+    uint64_t q[3];
+    for (int a = 0; a < 3; ++a) {
+        T p = robust_max(R::fma(c[a], g.scale[a], g.offset[a]), (T)0);
+        // saturating conversion; p is never negative or NaN here
+        uint64_t cell = p >= (T)last ? last : (uint64_t)p;
+        q[a] = cell;
+    }
+    return MortonTraits<K>::encode((K)q[0], (K)q[1], (K)q[2]);
+}
+
+// ---- Hierarchy ------------------------------------------------------------------------------
+// "Distance" between sorted neighbours k and k+1: XOR of the keys, ties broken by XOR of the
+// positions (a ruler sequence, so runs of identical keys become balanced subtrees).  Smaller means
+// more similar; the bottom-up pass merges across the smaller boundary first, so the boundary with
+// the LARGEST distance ends up at the root.
+template <typename K> struct Delta { K hi; uint32_t lo; };
+template <typename K> BVH_HD bool delta_less(const Delta<K>& a, const Delta<K>& b) {
+    return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo);
+}
+template <typename K> BVH_HD Delta<K> delta_at(const K* __restrict__ keys, uint32_t k) {
+    return Delta<K>{ (K)(keys[k] ^ keys[k + 1]), k ^ (k + 1) };
+}
+
+template <typename T> struct NodeAux;
+template <> struct alignas(8)  NodeAux<float>  { float cost;  uint32_t depth; };
+template <> struct alignas(16) NodeAux<double> { double cost; uint32_t depth; uint32_t pad; };
+
+template <typename T> struct BuildParams {
+    DevNode<T>* nodes;            // 2n device slots (slot = reference index + 1)
+    NodeAux<T>* aux;              // 2n, indexed like nodes
+    int* flags;                   // n-1, initialised to -1
+    uint32_t* info;               // [0] tree depth (max stack entries needed), [1] root split position
+    uint32_t n;
+    uint32_t min_leaf, max_leaf;  // TopDownSahBuilder::Config, top_down_sah_builder.h:27-40
+};
+
+template <typename T> BVH_HD void write_node(DevNode<T>* dst, const T bmin[3], const T bmax[3],
+                                             typename Real<T>::UInt index) {
+    DevNode<T> n;
+    for (int k = 0; k < 3; ++k) { n.bounds[2 * k] = bmin[k]; n.bounds[2 * k + 1] = bmax[k]; }
+    n.index = index; n.pad = 0;
+#if defined(__CUDA_ARCH__)
+    // two (float) / four (double) 128-bit stores
+    const uint4* s = reinterpret_cast<const uint4*>(&n);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    #pragma unroll
+    for (int k = 0; k < (int)(sizeof(DevNode<T>) / 16); ++k) d[k] = s[k];
+#else
+    *dst = n;
+#endif
+}
+
+// Memory-ordering hooks: the device version uses __threadfence / atomicExch / L2 loads; the host
+// emulation runs leaves sequentially, so plain accesses suffice.
+struct HostSync {
+    static inline void fence() {}
+    static inline int exchange(int* p, int v) { int o = *p; *p = v; return o; }
+    template <typename X> static inline X load(const X* p) { return *p; }
+    static inline void store_max(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
+};
+
+// The bottom-up pass for sorted leaf `i` whose box is [bmin, bmax].  Called once per leaf; the
+// thread that arrives SECOND at an internal node continues upwards with the merged node.
+template <typename T, typename K, typename Sync>
+BVH_HD void build_bottom_up(const BuildParams<T>& p, const K* __restrict__ keys, uint32_t i,
+                            T bmin[3], T bmax[3]) {
+    using R = Real<T>;
+    using U = typename R::UInt;
+    const uint32_t n = p.n;
+    uint32_t l = i, r = i;
+    U index = make_index<U>((U)i, 1);                       // Index::make_leaf(i, 1)
+    T cost = half_area(bmin, bmax);                         // leaf cost = half_area * prim_count
+    uint32_t depth = 0;
+
+    if (n == 1) {                                           // the root is a leaf (bvh.h:128 handles it)
+        write_node(p.nodes + 1, bmin, bmax, index);
+        p.info[0] = 0; p.info[1] = 0;
+        return;
+    }
+
+    for (;;) {
+        // Choose the parent: merge across the more similar boundary (ties -> left boundary).
+        uint32_t parent; uint32_t side;
+        if (l == 0 || (r != n - 1 && delta_less(delta_at(keys, r), delta_at(keys, l - 1)))) {
+            parent = r; side = 0;                           // we are the child covering [l, parent]
+        } else {
+            parent = l - 1; side = 1;                       // we are the child covering [parent+1, r]
+        }
+        const size_t slot = 2 * (size_t)parent + 1 + side + 1;   // reference index 2p+1+side, +1 device shift
+        write_node(p.nodes + slot, bmin, bmax, index);
+        p.aux[slot].cost = cost; p.aux[slot].depth = depth;
+        Sync::fence();
+        const int other = Sync::exchange(p.flags + parent, (int)(side == 0 ? l : r));
+        if (other < 0) return;                              // first to arrive: the sibling will carry on
+        Sync::fence();
+
+        // Second to arrive: fetch the sibling's record and merge.
+        const size_t sib = 2 * (size_t)parent + 1 + (1 - side) + 1;
+        const DevNode<T> sn = Sync::load(p.nodes + sib);
+        const NodeAux<T> sa = Sync::load(p.aux + sib);
+        T smin[3] = { sn.bounds[0], sn.bounds[2], sn.bounds[4] };
+        T smax[3] = { sn.bounds[1], sn.bounds[3], sn.bounds[5] };
+        const T own_area = half_area(bmin, bmax), sib_area = half_area(smin, smax);
+
+        // SATO: the child with the larger half-area must be the LEFT one (top_down_sah_builder.h:101-108).
+        const bool own_is_left = side == 0;
+        const T left_area = own_is_left ? own_area : sib_area, right_area = own_is_left ? sib_area : own_area;
+        if (left_area < right_area) {
+            write_node(p.nodes + sib, bmin, bmax, index);
+            write_node(p.nodes + slot, smin, smax, sn.index);
+        }
+
+        if (side == 0) r = (uint32_t)other; else l = (uint32_t)other;
+        // parent box = left.get_bbox().extend(right.get_bbox()) (bvh.h:213-217) with left/right as
+        // they now sit in memory
+        const bool own_first = (left_area < right_area) ? !own_is_left : own_is_left;
+        for (int k = 0; k < 3; ++k) {
+            const T a_min = own_first ? bmin[k] : smin[k], b_min = own_first ? smin[k] : bmin[k];
+            const T a_max = own_first ? bmax[k] : smax[k], b_max = own_first ? smax[k] : bmax[k];
+            bmin[k] = robust_min(a_min, b_min);
+            bmax[k] = robust_max(a_max, b_max);
+        }
+
+        const uint32_t count = r - l + 1;
+        const T area = half_area(bmin, bmax);
+        const T split_cost = R::add(area, R::add(cost, sa.cost));   // node cost_ratio 1 (split_heuristic.h:18-24)
+        const T leaf_cost = R::mul(area, (T)count);                 // get_leaf_cost, split_heuristic.h:30-33
+        const uint32_t sub_depth = (depth > sa.depth ? depth : sa.depth) + 1;
+        if (count <= p.max_leaf && (count <= p.min_leaf || leaf_cost <= split_cost)) {
+            index = make_index<U>((U)l, count);             // collapse the subtree into one leaf
+            cost = leaf_cost; depth = 0;
+        } else {
+            index = make_index<U>((U)(2 * (size_t)parent + 1), 0);   // Index::make_inner(first child)
+            cost = split_cost; depth = sub_depth;
+        }
+
+        if (l == 0 && r == n - 1) {                         // this is the root: reference index 0
+            write_node(p.nodes + 1, bmin, bmax, index);
+            p.info[0] = depth; p.info[1] = parent;
+            return;
+        }
+    }
+}
+
+} // namespace bvhb200

@@ -1,0 +1,592 @@
+// bvh_b200/csrc/c_api.cu — the extern "C" boundary (include/bvh/v2/c_api/bvh.h + include/bvh_b200.h).
+//
+// A handle (struct bvh3f / bvh3d) owns
+//   * the device-resident BVH (engine.h: DeviceBvh) that the batched entry points trace against, and
+//   * a lazily synchronised HOST MIRROR in the reference's exact layout — vector of Node<T,3>
+//     (28 / 56 bytes: six bounds + packed index, reference node.h:31-37) plus size_t prim_ids
+//     (reference bvh.h:17-23) — which is what the reference's per-node accessors, refit, save/load and
+//     the per-ray callback API operate on (reference c_api/bvh_impl.h:118-250).
+// A GPU build leaves the mirror empty until a legacy accessor asks for it; a mirror that may have been
+// edited through bvhNN_get_node / bvhNN_load is re-uploaded before the next batched call.
+#define BVH_BUILD_API
+#include <bvh_b200.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "engine.h"
+
+namespace bvhb200 {
+
+// ---- errors, allocation ---------------------------------------------------------------------
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+const char* last_error() { return g_error.c_str(); }
+
+static thread_local int g_device = 0;
+static thread_local cudaStream_t g_user_stream = nullptr;
+static thread_local bool g_have_user_stream = false;
+
+int prepare_device(int device) {
+    static std::mutex mutex;
+    static bool prepared[64] = {};
+    BVH_CUDA_TRY(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lock(mutex);
+    if (device >= 0 && device < 64 && !prepared[device]) {
+        cudaMemPool_t pool;
+        BVH_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long threshold = ~0ull;      // keep freed blocks cached: rebuilds never hit the driver
+        BVH_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        prepared[device] = true;
+    }
+    return 0;
+}
+
+int device_alloc(void** ptr, size_t bytes, cudaStream_t stream) {
+    *ptr = nullptr;
+    BVH_CUDA_TRY(cudaMallocAsync(ptr, bytes ? bytes : 16, stream));
+    return 0;
+}
+void device_free(void* ptr, cudaStream_t stream) { if (ptr) cudaFreeAsync(ptr, stream); }
+
+// ---- host mirror ------------------------------------------------------------------------------
+template <typename T> struct HostNode { T bounds[6]; typename Real<T>::UInt index; };
+static_assert(sizeof(HostNode<float>) == 28 && sizeof(HostNode<double>) == 56, "reference Node<T,3> layout");
+
+template <typename T> struct Handle {
+    using U = typename Real<T>::UInt;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    DeviceBvh<T> dev;
+    bool device_valid = false;
+
+    std::vector<HostNode<T>> nodes;           // reference layout
+    std::vector<size_t> prim_ids;
+    bool host_valid = false;
+    bool maybe_edited = false;                // a mutable node pointer was handed out since the last upload
+    uint64_t synced_hash = 0;
+
+    // staging for host-pointer batches
+    void* d_rays = nullptr; size_t d_rays_bytes = 0;
+    void* d_hits = nullptr; size_t d_hits_bytes = 0;
+    void* d_stats = nullptr; size_t d_stats_bytes = 0;
+};
+
+template <typename T> int init_handle(Handle<T>& h) {
+    h.device = g_device;
+    if (prepare_device(h.device)) return -1;
+    h.dev.device = h.device;
+    if (g_have_user_stream) { h.stream = g_user_stream; h.own_stream = false; }
+    else { BVH_CUDA_TRY(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking)); h.own_stream = true; }
+    return 0;
+}
+
+template <typename T> void destroy_handle(Handle<T>* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    release(h->dev, h->stream);
+    device_free(h->d_rays, h->stream); device_free(h->d_hits, h->stream); device_free(h->d_stats, h->stream);
+    cudaStreamSynchronize(h->stream);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static uint64_t hash_bytes(const void* data, size_t size, uint64_t seed) {
+    // FNV-1a over 64-bit words (the tail bytewise); only used to detect edits of the mirror
+    uint64_t h = 1469598103934665603ull ^ seed;
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    size_t words = size / 8;
+    for (size_t i = 0; i < words; ++i) { uint64_t w; std::memcpy(&w, p + 8 * i, 8); h = (h ^ w) * 1099511628211ull; }
+    for (size_t i = words * 8; i < size; ++i) h = (h ^ p[i]) * 1099511628211ull;
+    return h;
+}
+
+template <typename T> uint64_t mirror_hash(const Handle<T>& h) {
+    uint64_t a = hash_bytes(h.nodes.data(), h.nodes.size() * sizeof(HostNode<T>), h.nodes.size());
+    return hash_bytes(h.prim_ids.data(), h.prim_ids.size() * sizeof(size_t), a);
+}
+
+// Device -> mirror.  The device array may contain dead slots (subtrees collapsed into leaves by the
+// builder); the mirror must be a dense array in which every node is reachable (the reference's
+// refit / reinsertion code walks all of `nodes`, bvh.h:184-218), so live nodes are re-emitted in
+// depth-first order: root at 0, children of a node adjacent, left child at an odd index (bvh.h:34-54).
+template <typename T> int download_mirror(Handle<T>& h) {
+    using U = typename Real<T>::UInt;
+    if (h.host_valid) return 0;
+    if (!h.device_valid) { set_error("handle holds no BVH"); return -1; }
+    BVH_CUDA_TRY(cudaSetDevice(h.device));
+    std::vector<DevNode<T>> dev_nodes(h.dev.node_slots);
+    std::vector<uint32_t> dev_ids(h.dev.prim_count);
+    BVH_CUDA_TRY(cudaMemcpyAsync(dev_nodes.data(), h.dev.nodes, dev_nodes.size() * sizeof(DevNode<T>), cudaMemcpyDeviceToHost, h.stream));
+    BVH_CUDA_TRY(cudaMemcpyAsync(dev_ids.data(), h.dev.prim_ids, dev_ids.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, h.stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(h.stream));
+
+    h.nodes.clear();
+    h.nodes.reserve(2 * (size_t)h.dev.prim_count);
+    auto emit = [&] (const DevNode<T>& src) {
+        HostNode<T> n;
+        std::memcpy(n.bounds, src.bounds, sizeof(n.bounds));
+        n.index = src.index;
+        h.nodes.push_back(n);
+    };
+    emit(dev_nodes[1]);
+    std::vector<size_t> stack;                         // destination indices of inner nodes still to expand
+    if (index_count(h.nodes[0].index) == 0) stack.push_back(0);
+    while (!stack.empty()) {
+        const size_t dst = stack.back();
+        stack.pop_back();
+        const size_t first_src = (size_t)index_first(h.nodes[dst].index);     // reference index of the left child
+        const size_t first_dst = h.nodes.size();
+        emit(dev_nodes[first_src + 1]);
+        emit(dev_nodes[first_src + 2]);
+        h.nodes[dst].index = make_index<U>((U)first_dst, 0);
+        // right first so that the left subtree is laid out right after its parent pair
+        if (index_count(h.nodes[first_dst + 1].index) == 0) stack.push_back(first_dst + 1);
+        if (index_count(h.nodes[first_dst + 0].index) == 0) stack.push_back(first_dst + 0);
+    }
+    h.nodes.shrink_to_fit();
+    h.prim_ids.assign(dev_ids.begin(), dev_ids.end());
+    h.host_valid = true;
+    h.maybe_edited = false;
+    return 0;
+}
+
+// Mirror -> device: reference node i goes to device slot i + 1, padded to 32 / 64 bytes.
+template <typename T> int upload_mirror(Handle<T>& h) {
+    BVH_CUDA_TRY(cudaSetDevice(h.device));
+    const size_t node_count = h.nodes.size();
+    if (node_count == 0) { set_error("upload: empty BVH"); return -1; }
+    std::vector<DevNode<T>> dev_nodes(node_count + 1);
+    std::memset(dev_nodes.data(), 0, sizeof(DevNode<T>));
+    for (size_t i = 0; i < node_count; ++i) {
+        std::memcpy(dev_nodes[i + 1].bounds, h.nodes[i].bounds, sizeof(h.nodes[i].bounds));
+        dev_nodes[i + 1].index = h.nodes[i].index;
+        dev_nodes[i + 1].pad = 0;
+    }
+    std::vector<uint32_t> ids(h.prim_ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) ids[i] = (uint32_t)h.prim_ids[i];
+
+    // depth = longest chain of inner nodes (bounds the traversal stack); also validates child indices
+    uint32_t depth = 0;
+    {
+        std::vector<std::pair<size_t, uint32_t>> stack;
+        stack.emplace_back(0, 0);
+        size_t visited = 0;
+        while (!stack.empty()) {
+            auto [i, d] = stack.back();
+            stack.pop_back();
+            if (++visited > node_count) { set_error("upload: the node graph is not a tree"); return -1; }
+            if (index_count(h.nodes[i].index) != 0) continue;
+            const size_t first = (size_t)index_first(h.nodes[i].index);
+            if (first == 0 || first + 1 >= node_count) { set_error("upload: child index out of range"); return -1; }
+            depth = std::max(depth, d + 1);
+            stack.emplace_back(first, d + 1);
+            stack.emplace_back(first + 1, d + 1);
+        }
+    }
+
+    const bool had_tris = h.dev.tris != nullptr && h.dev.prim_count == ids.size();
+    DevTri<T>* keep_tris = had_tris ? h.dev.tris : nullptr;
+    if (had_tris) h.dev.tris = nullptr;
+    release(h.dev, h.stream);
+    h.dev.device = h.device;
+    h.dev.prim_count = (uint32_t)ids.size();
+    h.dev.node_slots = dev_nodes.size();
+    h.dev.depth = depth;
+    h.dev.compact = true;
+    h.dev.tris = keep_tris;
+    if (device_alloc(reinterpret_cast<void**>(&h.dev.nodes), dev_nodes.size() * sizeof(DevNode<T>), h.stream)) return -1;
+    if (device_alloc(reinterpret_cast<void**>(&h.dev.prim_ids), ids.size() * sizeof(uint32_t), h.stream)) return -1;
+    BVH_CUDA_TRY(cudaMemcpyAsync(h.dev.nodes, dev_nodes.data(), dev_nodes.size() * sizeof(DevNode<T>), cudaMemcpyHostToDevice, h.stream));
+    BVH_CUDA_TRY(cudaMemcpyAsync(h.dev.prim_ids, ids.data(), ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h.stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(h.stream));
+    h.device_valid = true;
+    h.maybe_edited = false;
+    h.synced_hash = mirror_hash(h);
+    return 0;
+}
+
+// Called before any batched call: make the device copy current.
+template <typename T> int ensure_device(Handle<T>& h) {
+    if (h.device_valid && !(h.host_valid && h.maybe_edited)) return 0;
+    if (!h.host_valid) { set_error("handle holds no BVH"); return -1; }
+    if (h.device_valid && mirror_hash(h) == h.synced_hash) { h.maybe_edited = false; return 0; }
+    // prim ids may have been permuted by an edit: triangles would be stale
+    if (h.device_valid && h.dev.tris) { device_free(h.dev.tris, h.stream); h.dev.tris = nullptr; }
+    return upload_mirror(h);
+}
+
+// ---- reference semantics on the mirror ---------------------------------------------------------
+// Bvh::refit with no leaf function (reference bvh.h:184-218; c_api/bvh_impl.h:218-221).
+template <typename T> void refit_mirror(Handle<T>& h) {
+    const size_t n = h.nodes.size();
+    std::vector<size_t> parents(n, 0);
+    std::vector<unsigned char> seen(n, 0);
+    for (size_t i = 0; i < n; ++i) {
+        if (index_count(h.nodes[i].index) != 0) continue;
+        const size_t first = (size_t)index_first(h.nodes[i].index);
+        if (first + 1 < n) { parents[first] = i; parents[first + 1] = i; }
+    }
+    for (size_t i = n; i-- > 0;) {
+        if (index_count(h.nodes[i].index) == 0) continue;
+        seen[i] = 1;
+        for (size_t j = parents[i];; j = parents[j]) {
+            auto& node = h.nodes[j];
+            const size_t first = (size_t)index_first(node.index);
+            if (seen[j] || index_count(node.index) != 0 || first + 1 >= n || !seen[first] || !seen[first + 1]) break;
+            const auto& l = h.nodes[first];
+            const auto& r = h.nodes[first + 1];
+            for (int k = 0; k < 3; ++k) {
+                node.bounds[2 * k]     = robust_min(l.bounds[2 * k], r.bounds[2 * k]);
+                node.bounds[2 * k + 1] = robust_max(l.bounds[2 * k + 1], r.bounds[2 * k + 1]);
+            }
+            seen[j] = 1;
+            if (j == 0) break;
+        }
+    }
+}
+
+// Bvh::intersect for one ray with a host callback (reference bvh.h:124-182, c_api/bvh_impl.h:235-250).
+template <typename T, bool kAny, bool kRobust, typename Callback>
+void intersect_mirror(const Handle<T>& h, const T* ray8, const Callback* cb) {
+    using U = typename Real<T>::UInt;
+    RayCtx<T> r;
+    for (int k = 0; k < 3; ++k) { r.org[k] = ray8[k]; r.dir[k] = ray8[3 + k]; }
+    r.tmin = ray8[6]; r.tmax = ray8[7];
+    ray_prologue<T, kRobust>(r);
+    U stack[64];                                           // SmallStack<Index, 64>, bvh_impl.h:241
+    unsigned sp = 0;
+    U top = h.nodes[0].index;
+    for (;;) {
+        bool alive = true;
+        while (index_count(top) == 0) {
+            const auto& left = h.nodes[(size_t)index_first(top)];
+            const auto& right = h.nodes[(size_t)index_first(top) + 1];
+            T l0, l1, r0, r1;
+            node_test<T, kRobust>(left.bounds, r, l0, l1);
+            node_test<T, kRobust>(right.bounds, r, r0, r1);
+            const bool hl = l0 <= l1, hr = r0 <= r1;
+            if (hl) {
+                U near_i = left.index;
+                if (hr) {
+                    U far_i = right.index;
+                    if (!kAny && l0 > r0) std::swap(near_i, far_i);
+                    if (sp < 64) stack[sp++] = far_i;
+                }
+                top = near_i;
+            } else if (hr) top = right.index;
+            else { if (sp == 0) { alive = false; break; } top = stack[--sp]; }
+        }
+        if (!alive) break;
+        const size_t begin = (size_t)index_first(top), end = begin + index_count(top);
+        const bool was_hit = cb->user_fn(cb->user_data, &r.tmax, begin, end);
+        if (kAny && was_hit) break;
+        if (sp == 0) break;
+        top = stack[--sp];
+    }
+}
+
+template <typename T> BuildOptions translate_config(const bvh_build_config* config) {
+    BuildOptions o;                                         // defaults of DefaultBuilder::Config
+    if (config) {
+        o.quality = (int)config->quality;
+        o.min_leaf = (uint32_t)std::min<size_t>(config->min_leaf_size ? config->min_leaf_size : 1, 15);
+        o.max_leaf = (uint32_t)std::min<size_t>(config->max_leaf_size ? config->max_leaf_size : 1, 15);
+    }
+    return o;
+}
+
+// Copies a host array to the device (or passes a device pointer through).
+template <typename X> struct DeviceInput {
+    const X* ptr = nullptr;
+    void* owned = nullptr;
+    cudaStream_t stream;
+    explicit DeviceInput(cudaStream_t s) : stream(s) {}
+    ~DeviceInput() { device_free(owned, stream); }
+    int set(const X* src, size_t count, bool is_device) {
+        if (is_device) { ptr = src; return 0; }
+        if (device_alloc(&owned, count * sizeof(X), stream)) return -1;
+        BVH_CUDA_TRY(cudaMemcpyAsync(owned, src, count * sizeof(X), cudaMemcpyHostToDevice, stream));
+        ptr = static_cast<const X*>(owned);
+        return 0;
+    }
+};
+
+template <typename T>
+Handle<T>* build_handle(const T* verts, const T* bboxes, const T* centers, size_t n,
+                        const bvh_build_config* config, bool device_ptrs) {
+    if (n == 0 || n > 0xFFFFFFFFull) { set_error("build: prim_count out of range"); return nullptr; }
+    auto h = new Handle<T>();
+    if (init_handle(*h)) { delete h; return nullptr; }
+    int rc = 0;
+    {
+        DeviceInput<T> dv(h->stream), db(h->stream), dc(h->stream);
+        if (verts) rc = dv.set(verts, 9 * n, device_ptrs);
+        else { rc = db.set(bboxes, 6 * n, device_ptrs); if (!rc) rc = dc.set(centers, 3 * n, device_ptrs); }
+        if (!rc) rc = build_lbvh<T>(h->dev, dv.ptr, db.ptr, dc.ptr, (uint32_t)n, translate_config<T>(config), h->stream);
+    }
+    if (rc) { destroy_handle(h); return nullptr; }
+    h->device_valid = true;
+    return h;
+}
+
+template <typename T> int ensure_staging(Handle<T>& h, void** buf, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return 0;
+    device_free(*buf, h.stream);
+    *buf = nullptr; *cap = 0;
+    if (device_alloc(buf, bytes, h.stream)) return -1;
+    *cap = bytes;
+    return 0;
+}
+
+template <typename T, typename RayPod, typename HitPod>
+int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bvh_ray_stats* stats, unsigned flags) {
+    static_assert(sizeof(RayPod) == sizeof(DevRay<T>) && sizeof(HitPod) == sizeof(DevHit<T>), "POD layouts");
+    if (!h) { set_error("null handle"); return -1; }
+    if (n == 0) return 0;
+    BVH_CUDA_TRY(cudaSetDevice(h->device));
+    if (ensure_device(*h)) return -1;
+    unsigned tf = 0;
+    if (flags & BVH_ANY_HIT) tf |= kTraceAnyHit;
+    if (flags & BVH_ROBUST) tf |= kTraceRobust;
+    if (flags & BVH_TIE_LAST_VISITED) tf |= kTraceLastVisited;
+    if (flags & BVH_KERNEL_SIMPLE) tf |= kTraceSimple;
+    if (flags & BVH_DEVICE_POINTERS) {
+        return trace_rays<T>(h->dev, reinterpret_cast<const DevRay<T>*>(rays), reinterpret_cast<DevHit<T>*>(hits), n, tf,
+                             reinterpret_cast<uint32_t*>(stats), h->stream);
+    }
+    // Host buffers: H2D, trace, D2H on the handle's stream.
+    if (ensure_staging(*h, &h->d_rays, &h->d_rays_bytes, n * sizeof(RayPod))) return -1;
+    if (ensure_staging(*h, &h->d_hits, &h->d_hits_bytes, n * sizeof(HitPod))) return -1;
+    if (stats && ensure_staging(*h, &h->d_stats, &h->d_stats_bytes, n * sizeof(bvh_ray_stats))) return -1;
+    auto d_rays = static_cast<DevRay<T>*>(h->d_rays);
+    auto d_hits = static_cast<DevHit<T>*>(h->d_hits);
+    auto d_stats = static_cast<uint32_t*>(h->d_stats);
+    BVH_CUDA_TRY(cudaMemcpyAsync(d_rays, rays, n * sizeof(RayPod), cudaMemcpyHostToDevice, h->stream));
+    if (trace_rays<T>(h->dev, d_rays, d_hits, n, tf, stats ? d_stats : nullptr, h->stream)) return -1;
+    BVH_CUDA_TRY(cudaMemcpyAsync(hits, d_hits, n * sizeof(HitPod), cudaMemcpyDeviceToHost, h->stream));
+    if (stats) BVH_CUDA_TRY(cudaMemcpyAsync(stats, d_stats, n * sizeof(bvh_ray_stats), cudaMemcpyDeviceToHost, h->stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// reference bvh.h:220-242 / node.h:90-102: [node_count][prim_count] nodes (6 bounds + index) prim ids
+template <typename T> void save_mirror(Handle<T>& h, FILE* file) {
+    using U = typename Real<T>::UInt;
+    if (download_mirror(h)) return;
+    U v = (U)h.nodes.size(); fwrite(&v, sizeof v, 1, file);
+    v = (U)h.prim_ids.size(); fwrite(&v, sizeof v, 1, file);
+    for (const auto& n : h.nodes) { fwrite(n.bounds, sizeof(T), 6, file); fwrite(&n.index, sizeof(U), 1, file); }
+    for (size_t id : h.prim_ids) { v = (U)id; fwrite(&v, sizeof v, 1, file); }
+}
+
+template <typename T> Handle<T>* load_mirror(FILE* file) {
+    using U = typename Real<T>::UInt;
+    auto h = new Handle<T>();
+    if (init_handle(*h)) { delete h; return nullptr; }
+    U node_count = 0, prim_count = 0;                       // short reads give defaults (stream.h:13-18)
+    if (fread(&node_count, sizeof(U), 1, file) != 1) node_count = 0;
+    if (fread(&prim_count, sizeof(U), 1, file) != 1) prim_count = 0;
+    h->nodes.resize((size_t)node_count);
+    h->prim_ids.resize((size_t)prim_count);
+    for (auto& n : h->nodes) {
+        std::memset(&n, 0, sizeof n);
+        if (fread(n.bounds, sizeof(T), 6, file) != 6) std::memset(n.bounds, 0, sizeof n.bounds);
+        if (fread(&n.index, sizeof(U), 1, file) != 1) n.index = 0;
+    }
+    for (auto& id : h->prim_ids) { U v = 0; if (fread(&v, sizeof(U), 1, file) != 1) v = 0; id = (size_t)v; }
+    h->host_valid = true;
+    h->device_valid = false;
+    return h;
+}
+
+} // namespace bvhb200
+
+using namespace bvhb200;
+
+// ---- exported symbols ---------------------------------------------------------------------------
+extern "C" {
+
+BVH_EXPORT const char* bvh_last_error(void) { return last_error(); }
+BVH_EXPORT int bvh_cuda_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+BVH_EXPORT int bvh_cuda_set_device(int device) {
+    if (device < 0 || device >= bvh_cuda_device_count()) { set_error("no such CUDA device"); return -1; }
+    g_device = device;
+    return 0;
+}
+BVH_EXPORT void bvh_cuda_set_stream(void* cuda_stream) {
+    g_user_stream = static_cast<cudaStream_t>(cuda_stream);
+    g_have_user_stream = cuda_stream != nullptr;
+}
+BVH_EXPORT void* bvh_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) { set_error("cudaMallocHost failed"); cudaGetLastError(); return nullptr; }
+    return p;
+}
+BVH_EXPORT void bvh_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
+// The pool is an API token only: CUDA streams do the work that ThreadPool does in the reference.
+struct bvh_thread_pool { size_t thread_count; };
+BVH_EXPORT struct bvh_thread_pool* bvh_thread_pool_create(size_t thread_count) { return new bvh_thread_pool { thread_count }; }
+BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete pool; }
+
+#define H(T, bvh) (reinterpret_cast<Handle<T>*>(bvh))
+#define HC(T, bvh) (const_cast<Handle<T>*>(reinterpret_cast<const Handle<T>*>(bvh)))
+#define N(T, node) (reinterpret_cast<HostNode<T>*>(node))
+#define NC(T, node) (reinterpret_cast<const HostNode<T>*>(node))
+
+#define BVH_IMPL_3D(T, S, CALLBACK)                                                                               \
+    BVH_EXPORT struct bvh##S* bvh##S##_build(struct bvh_thread_pool*, const struct bvh_bbox##S* bboxes,            \
+            const struct bvh_vec##S* centers, size_t prim_count, const struct bvh_build_config* config) {          \
+        return reinterpret_cast<bvh##S*>(build_handle<T>(nullptr, reinterpret_cast<const T*>(bboxes),              \
+            reinterpret_cast<const T*>(centers), prim_count, config, false));                                      \
+    }                                                                                                              \
+    BVH_EXPORT struct bvh##S* bvh##S##_build_triangles(const T* vertices, size_t prim_count,                       \
+            const struct bvh_build_config* config, unsigned flags) {                                               \
+        return reinterpret_cast<bvh##S*>(build_handle<T>(vertices, nullptr, nullptr, prim_count, config,           \
+            (flags & BVH_DEVICE_POINTERS) != 0));                                                                  \
+    }                                                                                                              \
+    BVH_EXPORT void bvh##S##_destroy(struct bvh##S* bvh) { destroy_handle(H(T, bvh)); }                            \
+    BVH_EXPORT void bvh##S##_save(const struct bvh##S* bvh, FILE* file) { save_mirror(*HC(T, bvh), file); }        \
+    BVH_EXPORT struct bvh##S* bvh##S##_load(FILE* file) { return reinterpret_cast<bvh##S*>(load_mirror<T>(file)); } \
+    BVH_EXPORT struct bvh_node##S* bvh##S##_get_node(struct bvh##S* bvh, size_t node_id) {                         \
+        auto h = H(T, bvh);                                                                                        \
+        if (download_mirror(*h) || node_id >= h->nodes.size()) return nullptr;                                     \
+        if (!h->maybe_edited && h->device_valid) h->synced_hash = mirror_hash(*h);                                 \
+        h->maybe_edited = true;                                                                                    \
+        return reinterpret_cast<bvh_node##S*>(&h->nodes[node_id]);                                                 \
+    }                                                                                                              \
+    BVH_EXPORT size_t bvh##S##_get_prim_id(const struct bvh##S* bvh, size_t i) {                                   \
+        auto h = HC(T, bvh);                                                                                       \
+        if (download_mirror(*h) || i >= h->prim_ids.size()) return BVH_INVALID_PRIM_ID;                            \
+        return h->prim_ids[i];                                                                                     \
+    }                                                                                                              \
+    BVH_EXPORT size_t bvh##S##_get_prim_count(const struct bvh##S* bvh) {                                          \
+        auto h = HC(T, bvh);                                                                                       \
+        return h->host_valid ? h->prim_ids.size() : h->dev.prim_count;                                             \
+    }                                                                                                              \
+    BVH_EXPORT size_t bvh##S##_get_node_count(const struct bvh##S* bvh) {                                          \
+        auto h = HC(T, bvh);                                                                                       \
+        return download_mirror(*h) ? 0 : h->nodes.size();                                                          \
+    }                                                                                                              \
+    BVH_EXPORT bool bvh_node##S##_is_leaf(const struct bvh_node##S* node) { return index_count(NC(T, node)->index) != 0; } \
+    BVH_EXPORT size_t bvh_node##S##_get_prim_count(const struct bvh_node##S* node) { return index_count(NC(T, node)->index); } \
+    BVH_EXPORT void bvh_node##S##_set_prim_count(struct bvh_node##S* node, size_t count) {                         \
+        using U = Real<T>::UInt;                                                                                   \
+        N(T, node)->index = make_index<U>(index_first(N(T, node)->index), (uint32_t)(count & kMaxLeafPrims));      \
+    }                                                                                                              \
+    BVH_EXPORT size_t bvh_node##S##_get_first_id(const struct bvh_node##S* node) { return (size_t)index_first(NC(T, node)->index); } \
+    BVH_EXPORT void bvh_node##S##_set_first_id(struct bvh_node##S* node, size_t first_id) {                        \
+        using U = Real<T>::UInt;                                                                                   \
+        N(T, node)->index = make_index<U>((U)first_id, index_count(N(T, node)->index));                            \
+    }                                                                                                              \
+    BVH_EXPORT struct bvh_bbox##S bvh_node##S##_get_bbox(const struct bvh_node##S* node) {                         \
+        const T* b = NC(T, node)->bounds;                                                                          \
+        return bvh_bbox##S { { b[0], b[2], b[4] }, { b[1], b[3], b[5] } };                                         \
+    }                                                                                                              \
+    BVH_EXPORT void bvh_node##S##_set_bbox(struct bvh_node##S* node, const struct bvh_bbox##S* bbox) {             \
+        T* b = N(T, node)->bounds;                                                                                 \
+        b[0] = bbox->min.x; b[1] = bbox->max.x; b[2] = bbox->min.y; b[3] = bbox->max.y; b[4] = bbox->min.z; b[5] = bbox->max.z; \
+    }                                                                                                              \
+    BVH_EXPORT void bvh##S##_append_node(struct bvh##S* bvh) {                                                     \
+        auto h = H(T, bvh);                                                                                        \
+        if (download_mirror(*h)) return;                                                                           \
+        h->nodes.emplace_back(); h->maybe_edited = true; h->synced_hash = 0;                                       \
+    }                                                                                                              \
+    BVH_EXPORT void bvh##S##_remove_last_node(struct bvh##S* bvh) {                                                \
+        auto h = H(T, bvh);                                                                                        \
+        if (download_mirror(*h) || h->nodes.empty()) return;                                                       \
+        h->nodes.pop_back(); h->maybe_edited = true; h->synced_hash = 0;                                           \
+    }                                                                                                              \
+    BVH_EXPORT void bvh##S##_refit(struct bvh##S* bvh) {                                                           \
+        auto h = H(T, bvh);                                                                                        \
+        if (download_mirror(*h)) return;                                                                           \
+        refit_mirror(*h); h->maybe_edited = true; h->synced_hash = 0;                                              \
+    }                                                                                                              \
+    BVH_EXPORT void bvh##S##_optimize(struct bvh_thread_pool*, struct bvh##S*) {}                                  \
+    BVH_EXPORT void bvh##S##_intersect_ray_any(const struct bvh##S* bvh, const struct bvh_ray##S* ray, const struct CALLBACK* cb) { \
+        auto h = HC(T, bvh); if (!download_mirror(*h)) intersect_mirror<T, true, false>(*h, reinterpret_cast<const T*>(ray), cb); } \
+    BVH_EXPORT void bvh##S##_intersect_ray_any_robust(const struct bvh##S* bvh, const struct bvh_ray##S* ray, const struct CALLBACK* cb) { \
+        auto h = HC(T, bvh); if (!download_mirror(*h)) intersect_mirror<T, true, true>(*h, reinterpret_cast<const T*>(ray), cb); } \
+    BVH_EXPORT void bvh##S##_intersect_ray(const struct bvh##S* bvh, const struct bvh_ray##S* ray, const struct CALLBACK* cb) { \
+        auto h = HC(T, bvh); if (!download_mirror(*h)) intersect_mirror<T, false, false>(*h, reinterpret_cast<const T*>(ray), cb); } \
+    BVH_EXPORT void bvh##S##_intersect_ray_robust(const struct bvh##S* bvh, const struct bvh_ray##S* ray, const struct CALLBACK* cb) { \
+        auto h = HC(T, bvh); if (!download_mirror(*h)) intersect_mirror<T, false, true>(*h, reinterpret_cast<const T*>(ray), cb); } \
+    BVH_EXPORT int bvh##S##_set_triangles(struct bvh##S* bvh, const T* vertices, size_t prim_count, unsigned flags) { \
+        auto h = H(T, bvh);                                                                                        \
+        if (!h) { set_error("null handle"); return -1; }                                                           \
+        BVH_CUDA_TRY(cudaSetDevice(h->device));                                                                    \
+        if (ensure_device(*h)) return -1;                                                                          \
+        if (prim_count != h->dev.prim_count) { set_error("set_triangles: prim_count mismatch"); return -1; }       \
+        DeviceInput<T> dv(h->stream);                                                                              \
+        if (dv.set(vertices, 9 * prim_count, (flags & BVH_DEVICE_POINTERS) != 0)) return -1;                       \
+        if (attach_triangles<T>(h->dev, dv.ptr, h->stream)) return -1;                                             \
+        BVH_CUDA_TRY(cudaStreamSynchronize(h->stream));                                                            \
+        return 0;                                                                                                  \
+    }                                                                                                              \
+    BVH_EXPORT int bvh##S##_intersect_rays(struct bvh##S* bvh, const struct bvh_ray##S* rays, size_t ray_count,    \
+            struct bvh_hit##S* hits, unsigned flags) {                                                             \
+        return intersect_batch<T>(H(T, bvh), rays, ray_count, hits, nullptr, flags);                               \
+    }                                                                                                              \
+    BVH_EXPORT int bvh##S##_intersect_rays_stats(struct bvh##S* bvh, const struct bvh_ray##S* rays, size_t ray_count, \
+            struct bvh_hit##S* hits, struct bvh_ray_stats* stats, unsigned flags) {                                \
+        if (!stats) { set_error("stats pointer is null"); return -1; }                                             \
+        return intersect_batch<T>(H(T, bvh), rays, ray_count, hits, stats, flags);                                 \
+    }                                                                                                              \
+    BVH_EXPORT int bvh##S##_sync(struct bvh##S* bvh) {                                                             \
+        auto h = H(T, bvh);                                                                                        \
+        if (!h) { set_error("null handle"); return -1; }                                                           \
+        BVH_CUDA_TRY(cudaSetDevice(h->device));                                                                    \
+        BVH_CUDA_TRY(cudaStreamSynchronize(h->stream));                                                            \
+        return 0;                                                                                                  \
+    }                                                                                                              \
+    BVH_EXPORT size_t bvh##S##_get_depth(struct bvh##S* bvh) {                                                     \
+        auto h = H(T, bvh);                                                                                        \
+        if (!h || ensure_device(*h)) return 0;                                                                     \
+        return h->dev.depth;                                                                                       \
+    }
+
+BVH_IMPL_3D(float, 3f, bvh_intersect_callbackf)
+BVH_IMPL_3D(double, 3d, bvh_intersect_callbackd)
+
+// 2-D suffixes: part of the reference ABI (c_api/bvh.cpp:7-25) but outside this round's hot path
+// (SURVEY.md §8(f) rank 4).  The symbols exist so that callers link; they report "not implemented".
+#define BVH_STUB_2D(T, S, CALLBACK)                                                                                \
+    static void not_impl##S() { set_error("bvh" #S ": 2-D instantiation is not implemented in this build"); }      \
+    BVH_EXPORT struct bvh##S* bvh##S##_build(struct bvh_thread_pool*, const struct bvh_bbox##S*, const struct bvh_vec##S*, \
+            size_t, const struct bvh_build_config*) { not_impl##S(); return nullptr; }                             \
+    BVH_EXPORT void bvh##S##_destroy(struct bvh##S*) {}                                                            \
+    BVH_EXPORT void bvh##S##_save(const struct bvh##S*, FILE*) { not_impl##S(); }                                  \
+    BVH_EXPORT struct bvh##S* bvh##S##_load(FILE*) { not_impl##S(); return nullptr; }                              \
+    BVH_EXPORT struct bvh_node##S* bvh##S##_get_node(struct bvh##S*, size_t) { not_impl##S(); return nullptr; }    \
+    BVH_EXPORT size_t bvh##S##_get_prim_id(const struct bvh##S*, size_t) { not_impl##S(); return BVH_INVALID_PRIM_ID; } \
+    BVH_EXPORT size_t bvh##S##_get_prim_count(const struct bvh##S*) { not_impl##S(); return 0; }                   \
+    BVH_EXPORT size_t bvh##S##_get_node_count(const struct bvh##S*) { not_impl##S(); return 0; }                   \
+    BVH_EXPORT bool bvh_node##S##_is_leaf(const struct bvh_node##S*) { not_impl##S(); return true; }               \
+    BVH_EXPORT size_t bvh_node##S##_get_prim_count(const struct bvh_node##S*) { not_impl##S(); return 0; }         \
+    BVH_EXPORT void bvh_node##S##_set_prim_count(struct bvh_node##S*, size_t) { not_impl##S(); }                   \
+    BVH_EXPORT size_t bvh_node##S##_get_first_id(const struct bvh_node##S*) { not_impl##S(); return 0; }           \
+    BVH_EXPORT void bvh_node##S##_set_first_id(struct bvh_node##S*, size_t) { not_impl##S(); }                     \
+    BVH_EXPORT struct bvh_bbox##S bvh_node##S##_get_bbox(const struct bvh_node##S*) { not_impl##S(); return bvh_bbox##S {}; } \
+    BVH_EXPORT void bvh_node##S##_set_bbox(struct bvh_node##S*, const struct bvh_bbox##S*) { not_impl##S(); }      \
+    BVH_EXPORT void bvh##S##_append_node(struct bvh##S*) { not_impl##S(); }                                        \
+    BVH_EXPORT void bvh##S##_remove_last_node(struct bvh##S*) { not_impl##S(); }                                   \
+    BVH_EXPORT void bvh##S##_refit(struct bvh##S*) { not_impl##S(); }                                              \
+    BVH_EXPORT void bvh##S##_optimize(struct bvh_thread_pool*, struct bvh##S*) { not_impl##S(); }                  \
+    BVH_EXPORT void bvh##S##_intersect_ray_any(const struct bvh##S*, const struct bvh_ray##S*, const struct CALLBACK*) { not_impl##S(); } \
+    BVH_EXPORT void bvh##S##_intersect_ray_any_robust(const struct bvh##S*, const struct bvh_ray##S*, const struct CALLBACK*) { not_impl##S(); } \
+    BVH_EXPORT void bvh##S##_intersect_ray(const struct bvh##S*, const struct bvh_ray##S*, const struct CALLBACK*) { not_impl##S(); } \
+    BVH_EXPORT void bvh##S##_intersect_ray_robust(const struct bvh##S*, const struct bvh_ray##S*, const struct CALLBACK*) { not_impl##S(); }
+
+BVH_STUB_2D(float, 2f, bvh_intersect_callbackf)
+BVH_STUB_2D(double, 2d, bvh_intersect_callbackd)
+
+} // extern "C"

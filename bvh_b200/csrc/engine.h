@@ -1,0 +1,80 @@
+// bvh_b200/csrc/engine.h — internal host-side interface between the C ABI (c_api.cu) and the CUDA
+// pipelines (lbvh_build.cu, traverse.cu).  Nothing here is exported.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <string>
+
+#include "core.cuh"
+
+namespace bvhb200 {
+
+// Error plumbing: every engine call returns 0 on success; the message of the last failure on the
+// calling thread is kept for bvh_last_error().
+void set_error(const std::string& msg);
+const char* last_error();
+
+#define BVH_CUDA_TRY(expr)                                                                   \
+    do {                                                                                     \
+        cudaError_t err__ = (expr);                                                          \
+        if (err__ != cudaSuccess) {                                                          \
+            ::bvhb200::set_error(std::string(#expr) + ": " + cudaGetErrorString(err__));     \
+            return -1;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+// Stream-ordered allocation from the device's default memory pool (release threshold raised once
+// per device so that rebuilds do not go back to the driver).
+int device_alloc(void** ptr, size_t bytes, cudaStream_t stream);
+void device_free(void* ptr, cudaStream_t stream);
+int prepare_device(int device);
+
+struct BuildOptions {
+    uint32_t min_leaf = 1;          // TopDownSahBuilder::Config (top_down_sah_builder.h:27-40)
+    uint32_t max_leaf = 8;
+    int quality = 2;                // DefaultBuilder::Quality (default_builder.h:21); see DESIGN.md
+    int morton_bits = 0;            // 0 = auto, 30 or 63
+};
+
+// The device-resident BVH: reference-layout nodes (shifted by one slot, padded), BVH-order
+// primitive ids and, when triangles were supplied, BVH-order precomputed triangles.
+template <typename T> struct DeviceBvh {
+    int device = 0;
+    uint32_t prim_count = 0;
+    size_t node_slots = 0;              // allocated device slots (slot 0 is padding, slot 1 the root)
+    DevNode<T>* nodes = nullptr;
+    uint32_t* prim_ids = nullptr;       // prim_ids[i] = original id of BVH-order primitive i
+    DevTri<T>* tris = nullptr;          // nullptr until triangles are attached
+    uint32_t depth = 0;                 // longest chain of inner nodes below the root (stack bound)
+    bool compact = false;               // true when every slot 1..node_slots-1 is a live node
+};
+
+// LBVH build.  Exactly one of d_verts (n x 9) or d_bboxes (n x 6 as min3,max3) + d_centers (n x 3)
+// is given; all pointers are device pointers.  With d_verts the BVH-order PrecomputedTri array is
+// produced in the same pass.
+template <typename T>
+int build_lbvh(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const T* d_centers,
+               uint32_t n, const BuildOptions& options, cudaStream_t stream);
+
+// Attach triangles to a BVH that was built from boxes/centres or uploaded from a host mirror.
+template <typename T>
+int attach_triangles(DeviceBvh<T>& bvh, const T* d_verts, cudaStream_t stream);
+
+template <typename T> void release(DeviceBvh<T>& bvh, cudaStream_t stream);
+
+enum TraceFlags : unsigned {
+    kTraceAnyHit      = 1u << 0,
+    kTraceRobust      = 1u << 1,
+    kTraceLastVisited = 1u << 2,   // reference example tie semantics instead of the canonical lowest id
+    kTraceSimple      = 1u << 8,   // one-thread-per-ray kernel instead of the persistent one
+};
+
+// Batched traversal; all pointers are device pointers.  ray_stats (nullable): n x 3 uint32
+// {inner steps, leaves, triangle tests}; it selects the statistics variant of the kernel.
+template <typename T>
+int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hits, size_t n,
+               unsigned flags, uint32_t* d_ray_stats, cudaStream_t stream);
+
+} // namespace bvhb200

@@ -1,0 +1,295 @@
+// bvh_b200/csrc/lbvh_build.cu — the CUDA LBVH construction pipeline (sm_100a).
+//
+// Replaces DefaultBuilder<Node>::build (reference default_builder.h:33-62) and everything under it.
+// Kernels, in launch order (DESIGN.md has the byte accounting):
+//   K1 centre_bounds_kernel   per-primitive centre (tri.h:25) -> per-block min/max partials
+//   K2 morton_kernel          final bounds reduce, grid quantisation (mini_tree_builder.h:170-183),
+//                             Morton interleave (utils.h:103-120), clears the arrival flags
+//   K3 radix sort             radix_sort.cuh, 3 kernels x 4 (30-bit keys) or x 8 (63-bit keys) passes
+//   K4 hierarchy_kernel       one thread per sorted primitive: leaf box (tri.h:24), BVH-order
+//                             PrecomputedTri (tri.h:35-37), then the bottom-up pass of build_core.cuh
+//                             that links parents, unions boxes (bvh.h:213-217), collapses subtrees into
+//                             leaves by SAH (split_heuristic.h:30-38) and stores each node once, in its
+//                             final reference-layout slot.
+#include "build_core.cuh"
+#include "engine.h"
+#include "radix_sort.cuh"
+
+namespace bvhb200 {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+// ---- device-side memory ordering for the bottom-up pass ---------------------------------------
+struct DeviceSync {
+    static __device__ __forceinline__ void fence() { __threadfence(); }
+    static __device__ __forceinline__ int exchange(int* p, int v) { return atomicExch(p, v); }
+    // read through L2 (the sibling's record was written by another SM)
+    template <typename X> static __device__ __forceinline__ X load(const X* p) {
+        static_assert(sizeof(X) % 8 == 0, "load granularity");
+        X out;
+        const unsigned long long* s = reinterpret_cast<const unsigned long long*>(p);
+        unsigned long long* d = reinterpret_cast<unsigned long long*>(&out);
+        #pragma unroll
+        for (int k = 0; k < (int)(sizeof(X) / 8); ++k) d[k] = __ldcg(s + k);
+        return out;
+    }
+};
+
+template <typename T> struct MinMax3 { T mn[3], mx[3]; };
+
+template <typename T> __device__ __forceinline__ T shfl_down(T v, int o) { return __shfl_down_sync(0xFFFFFFFFu, v, o); }
+
+// K1.  mode 0: verts (n x 9) -> centre of each triangle; mode 1: centres given (n x 3).
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+centre_bounds_kernel(const T* __restrict__ src, uint32_t n, int mode, MinMax3<T>* __restrict__ partials) {
+    using R = Real<T>;
+    T mn[3] = { R::max(), R::max(), R::max() };
+    T mx[3] = { R::neg(R::max()), R::neg(R::max()), R::neg(R::max()) };       // BBox::make_empty, bbox.h:40-44
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        T c[3];
+        if (mode == 0) {
+            T v[9];
+            #pragma unroll
+            for (int k = 0; k < 9; ++k) v[k] = __ldg(src + 9 * (size_t)i + k);
+            T bmin[3], bmax[3];
+            tri_bounds_center(v, bmin, bmax, c);
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 3; ++k) c[k] = __ldg(src + 3 * (size_t)i + k);
+        }
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) { mn[k] = robust_min(mn[k], c[k]); mx[k] = robust_max(mx[k], c[k]); }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = robust_min(mn[k], shfl_down(mn[k], o));
+            mx[k] = robust_max(mx[k], shfl_down(mx[k], o));
+        }
+    }
+    __shared__ MinMax3<T> warp_part[kBlock / 32];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { for (int k = 0; k < 3; ++k) { warp_part[warp].mn[k] = mn[k]; warp_part[warp].mx[k] = mx[k]; } }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MinMax3<T> acc = warp_part[0];
+        for (int w = 1; w < kBlock / 32; ++w)
+            for (int k = 0; k < 3; ++k) {
+                acc.mn[k] = robust_min(acc.mn[k], warp_part[w].mn[k]);
+                acc.mx[k] = robust_max(acc.mx[k], warp_part[w].mx[k]);
+            }
+        partials[blockIdx.x] = acc;
+    }
+}
+
+// K2.
+template <typename T, typename K>
+__global__ void __launch_bounds__(kBlock)
+morton_kernel(const T* __restrict__ src, uint32_t n, int mode, const MinMax3<T>* __restrict__ partials,
+              uint32_t num_partials, K* __restrict__ keys, int* __restrict__ flags) {
+    using R = Real<T>;
+    __shared__ MinMax3<T> warp_part[kBlock / 32];
+    __shared__ GridXform<T> xform;
+    {
+        T mn[3] = { R::max(), R::max(), R::max() };
+        T mx[3] = { R::neg(R::max()), R::neg(R::max()), R::neg(R::max()) };
+        for (uint32_t i = threadIdx.x; i < num_partials; i += kBlock) {
+            const MinMax3<T> p = partials[i];
+            #pragma unroll
+            for (int k = 0; k < 3; ++k) { mn[k] = robust_min(mn[k], p.mn[k]); mx[k] = robust_max(mx[k], p.mx[k]); }
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            #pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                mn[k] = robust_min(mn[k], shfl_down(mn[k], o));
+                mx[k] = robust_max(mx[k], shfl_down(mx[k], o));
+            }
+        }
+        const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) { for (int k = 0; k < 3; ++k) { warp_part[warp].mn[k] = mn[k]; warp_part[warp].mx[k] = mx[k]; } }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            MinMax3<T> acc = warp_part[0];
+            for (int w = 1; w < kBlock / 32; ++w)
+                for (int k = 0; k < 3; ++k) {
+                    acc.mn[k] = robust_min(acc.mn[k], warp_part[w].mn[k]);
+                    acc.mx[k] = robust_max(acc.mx[k], warp_part[w].mx[k]);
+                }
+            xform = make_grid_xform(acc.mn, acc.mx, MortonTraits<K>::bits_per_axis);
+        }
+        __syncthreads();
+    }
+    const GridXform<T> g = xform;
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        T c[3];
+        if (mode == 0) {
+            T v[9];
+            #pragma unroll
+            for (int k = 0; k < 9; ++k) v[k] = __ldg(src + 9 * (size_t)i + k);
+            T bmin[3], bmax[3];
+            tri_bounds_center(v, bmin, bmax, c);
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 3; ++k) c[k] = __ldg(src + 3 * (size_t)i + k);
+        }
+        keys[i] = morton_key<T, K>(c, g);
+        if (i + 1 < n) flags[i] = -1;
+    }
+}
+
+// K4.  leaf_mode 0: verts (n x 9), also writes BVH-order triangles; 1: bboxes (n x 6, min3 max3).
+template <typename T, typename K>
+__global__ void __launch_bounds__(kBlock)
+hierarchy_kernel(BuildParams<T> p, const K* __restrict__ keys, const uint32_t* __restrict__ vals,
+                 const T* __restrict__ leaf_src, int leaf_mode, DevTri<T>* __restrict__ tris) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= p.n) return;
+    const uint32_t id = vals[i];
+    T bmin[3], bmax[3];
+    if (leaf_mode == 0) {
+        T v[9];
+        #pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = __ldg(leaf_src + 9 * (size_t)id + k);
+        T c[3];
+        tri_bounds_center(v, bmin, bmax, c);
+        const DevTri<T> t = precompute_tri(v);
+        const uint4* s = reinterpret_cast<const uint4*>(&t);
+        uint4* d = reinterpret_cast<uint4*>(tris + i);
+        #pragma unroll
+        for (int k = 0; k < (int)(sizeof(DevTri<T>) / 16); ++k) d[k] = s[k];
+    } else {
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            bmin[k] = __ldg(leaf_src + 6 * (size_t)id + k);
+            bmax[k] = __ldg(leaf_src + 6 * (size_t)id + 3 + k);
+        }
+    }
+    build_bottom_up<T, K, DeviceSync>(p, keys, i, bmin, bmax);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+permute_tris_kernel(const T* __restrict__ verts, const uint32_t* __restrict__ prim_ids, uint32_t n,
+                    DevTri<T>* __restrict__ tris) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t id = prim_ids[i];
+    T v[9];
+    #pragma unroll
+    for (int k = 0; k < 9; ++k) v[k] = __ldg(verts + 9 * (size_t)id + k);
+    const DevTri<T> t = precompute_tri(v);
+    const uint4* s = reinterpret_cast<const uint4*>(&t);
+    uint4* d = reinterpret_cast<uint4*>(tris + i);
+    #pragma unroll
+    for (int k = 0; k < (int)(sizeof(DevTri<T>) / 16); ++k) d[k] = s[k];
+}
+
+struct Scratch {
+    cudaStream_t stream;
+    void* ptrs[16];
+    int count = 0;
+    explicit Scratch(cudaStream_t s) : stream(s) {}
+    ~Scratch() { for (int i = 0; i < count; ++i) device_free(ptrs[i], stream); }
+    template <typename X> int alloc(X** out, size_t elems) {
+        void* p = nullptr;
+        if (device_alloc(&p, elems * sizeof(X), stream)) return -1;
+        ptrs[count++] = p;
+        *out = static_cast<X*>(p);
+        return 0;
+    }
+};
+
+template <typename T, typename K>
+int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const T* d_centers,
+                   uint32_t n, const BuildOptions& options, int key_bits, cudaStream_t stream) {
+    Scratch scratch(stream);
+    const int mode = d_verts ? 0 : 1;
+    const T* centre_src = d_verts ? d_verts : d_centers;
+    const T* leaf_src = d_verts ? d_verts : d_bboxes;
+
+    int sm_count = 148;
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, out.device);
+    const uint32_t blocks_needed = (n + kBlock - 1) / kBlock;
+    const uint32_t grid = blocks_needed < (uint32_t)(sm_count * 4) ? blocks_needed : (uint32_t)(sm_count * 4);
+    const uint32_t num_tiles = (n + kRsTile - 1) / kRsTile;
+
+    MinMax3<T>* partials; K* keys_a; K* keys_b; uint32_t* vals_b; uint32_t* tile_hist; int* flags;
+    NodeAux<T>* aux; uint32_t* info;
+    if (scratch.alloc(&partials, grid) || scratch.alloc(&keys_a, n) || scratch.alloc(&keys_b, n) ||
+        scratch.alloc(&vals_b, n) || scratch.alloc(&tile_hist, (size_t)num_tiles * kRsBins) ||
+        scratch.alloc(&flags, n) || scratch.alloc(&aux, 2 * (size_t)n + 2) || scratch.alloc(&info, 4))
+        return -1;
+
+    out.prim_count = n;
+    out.node_slots = 2 * (size_t)n;                     // slot 0 padding + 2n-1 reference nodes
+    if (device_alloc(reinterpret_cast<void**>(&out.nodes), out.node_slots * sizeof(DevNode<T>), stream)) return -1;
+    if (device_alloc(reinterpret_cast<void**>(&out.prim_ids), (size_t)n * sizeof(uint32_t), stream)) return -1;
+    if (d_verts && device_alloc(reinterpret_cast<void**>(&out.tris), (size_t)n * sizeof(DevTri<T>), stream)) return -1;
+
+    centre_bounds_kernel<T><<<grid, kBlock, 0, stream>>>(centre_src, n, mode, partials);
+    morton_kernel<T, K><<<grid, kBlock, 0, stream>>>(centre_src, n, mode, partials, grid, keys_a, flags);
+    BVH_CUDA_TRY(radix_sort_pairs<K>(keys_a, out.prim_ids, keys_b, vals_b, tile_hist, n, key_bits, stream));
+
+    BuildParams<T> p;
+    p.nodes = out.nodes; p.aux = aux; p.flags = flags; p.info = info; p.n = n;
+    p.min_leaf = options.min_leaf < 1 ? 1 : options.min_leaf;
+    p.max_leaf = options.max_leaf > kMaxLeafPrims ? kMaxLeafPrims : (options.max_leaf < 1 ? 1 : options.max_leaf);
+    if (p.min_leaf > p.max_leaf) p.min_leaf = p.max_leaf;
+    hierarchy_kernel<T, K><<<blocks_needed, kBlock, 0, stream>>>(p, keys_a, out.prim_ids, leaf_src, mode, out.tris);
+    BVH_CUDA_TRY(cudaGetLastError());
+
+    uint32_t host_info[4] = { 0, 0, 0, 0 };
+    BVH_CUDA_TRY(cudaMemcpyAsync(host_info, info, sizeof(host_info), cudaMemcpyDeviceToHost, stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(stream));
+    out.depth = host_info[0];
+    out.compact = false;
+    return 0;
+}
+
+} // namespace
+
+template <typename T>
+int build_lbvh(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const T* d_centers,
+               uint32_t n, const BuildOptions& options, cudaStream_t stream) {
+    if (n == 0) { set_error("build: prim_count == 0 (undefined in the reference, index.h:53)"); return -1; }
+    if (!d_verts && (!d_bboxes || !d_centers)) { set_error("build: need vertices or boxes+centres"); return -1; }
+    // first_id must fit Index<32,4>: 2n-1 <= 2^28-1 for float (index.h:39)
+    if (sizeof(T) == 4 && 2 * (uint64_t)n > ((uint64_t)1 << 28)) { set_error("build: too many primitives for a 32-bit index"); return -1; }
+    int bits = options.morton_bits;
+    if (bits == 0) bits = n >= (1u << 22) ? 63 : 30;
+    int rc;
+    if (bits <= 30) rc = build_with_key<T, uint32_t>(out, d_verts, d_bboxes, d_centers, n, options, 30, stream);
+    else            rc = build_with_key<T, uint64_t>(out, d_verts, d_bboxes, d_centers, n, options, 63, stream);
+    if (rc) release(out, stream);
+    return rc;
+}
+
+template <typename T>
+int attach_triangles(DeviceBvh<T>& bvh, const T* d_verts, cudaStream_t stream) {
+    if (!bvh.tris && device_alloc(reinterpret_cast<void**>(&bvh.tris), (size_t)bvh.prim_count * sizeof(DevTri<T>), stream)) return -1;
+    const uint32_t blocks = (bvh.prim_count + kBlock - 1) / kBlock;
+    permute_tris_kernel<T><<<blocks, kBlock, 0, stream>>>(d_verts, bvh.prim_ids, bvh.prim_count, bvh.tris);
+    BVH_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename T> void release(DeviceBvh<T>& bvh, cudaStream_t stream) {
+    device_free(bvh.nodes, stream); bvh.nodes = nullptr;
+    device_free(bvh.prim_ids, stream); bvh.prim_ids = nullptr;
+    device_free(bvh.tris, stream); bvh.tris = nullptr;
+    bvh.prim_count = 0; bvh.node_slots = 0;
+}
+
+template int build_lbvh<float>(DeviceBvh<float>&, const float*, const float*, const float*, uint32_t, const BuildOptions&, cudaStream_t);
+template int build_lbvh<double>(DeviceBvh<double>&, const double*, const double*, const double*, uint32_t, const BuildOptions&, cudaStream_t);
+template int attach_triangles<float>(DeviceBvh<float>&, const float*, cudaStream_t);
+template int attach_triangles<double>(DeviceBvh<double>&, const double*, cudaStream_t);
+template void release<float>(DeviceBvh<float>&, cudaStream_t);
+template void release<double>(DeviceBvh<double>&, cudaStream_t);
+
+} // namespace bvhb200

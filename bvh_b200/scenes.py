@@ -88,8 +88,8 @@ def primary_rays(width: int, height: int, eye, direction, up=(0.0, 1.0, 0.0), dt
 # Cameras used by the tests and the bench for each mesh family.
 CAMERAS = {
     "soup": dict(eye=(0.5, 0.5, -0.55), direction=(0.0, 0.0, 1.0), up=(0.0, 1.0, 0.0)),
-    "grid": dict(eye=(0.5, 0.9, -0.6), direction=(0.0, -0.55, 0.75), up=(0.0, 1.0, 0.0)),
-    "box12": dict(eye=(0.5, 0.5, -2.0), direction=(0.0, 0.0, 1.0), up=(0.0, 1.0, 0.0)),
+    "grid": dict(eye=(0.5, 0.35, 0.2), direction=(0.0, -1.0, 0.4472136), up=(0.0, 1.0, 0.0)),
+    "box12": dict(eye=(0.45, 0.55, -0.6), direction=(0.0, 0.0, 1.0), up=(0.0, 1.0, 0.0)),
 }
 
 

@@ -1,0 +1,93 @@
+/* include/bvh_b200.h — C ABI of the B200-native BVH engine (libbvh_c.so).
+ *
+ * Two groups of entry points, all `extern "C"`, plain pointers and sizes:
+ *
+ * 1. The reference's own C API, unchanged in name, signature and POD layout — declared in
+ *    <bvh/v2/c_api/bvh.h> of this repository, which mirrors reference src/bvh/v2/c_api/bvh.h:90-295
+ *    (94 symbols).  bvhNN_build runs the CUDA LBVH pipeline instead of DefaultBuilder
+ *    (reference c_api/bvh_impl.h:82-116 -> default_builder.h:33-62); the thread-pool argument is
+ *    accepted and ignored (CUDA streams replace ThreadPool, reference thread_pool.h:13-100).
+ *
+ * 2. Batched extensions (this file).  The reference traverses ONE ray per call and intersects
+ *    leaf primitives through a host callback (reference c_api/bvh.h:233-295, bvh_impl.h:235-250);
+ *    a device kernel cannot call a host function, so the GPU hot path needs entry points that own
+ *    the triangle test.  They replace, for whole batches:
+ *       caller-side Tri::get_bbox/get_center loop   reference test/benchmark.cpp:205-212, tri.h:24-25
+ *       DefaultBuilder<Node>::build                 reference default_builder.h:33-62
+ *       PrecomputedTri permutation                  reference test/benchmark.cpp:221-225, tri.h:35-37
+ *       the per-ray loop around Bvh::intersect      reference test/benchmark.cpp:277-298,351-377,
+ *                                                   bvh.h:159-182, tri.h:55-74
+ *
+ * Conventions: functions returning int give 0 on success and non-zero on failure, with a
+ * human-readable message available from bvh_last_error() on the same thread.  There is NO CPU
+ * fallback: without a CUDA device every batched entry point fails.  Pointers are host pointers
+ * unless BVH_DEVICE_POINTERS is passed, in which case they are device pointers on the handle's GPU
+ * and the call is asynchronous on the handle's stream (bvhNN_sync waits for it).
+ */
+#ifndef BVH_B200_H
+#define BVH_B200_H
+
+#include <bvh/v2/c_api/bvh.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Hit record of the batched traversal.  A miss has prim_id = all ones (BVH_INVALID_PRIM_ID
+ * truncated to the field width), t = the ray's tmax and u = v = 0.  prim_id is an ORIGINAL
+ * primitive index (what the reference's callers obtain through bvh.prim_ids[i],
+ * test/benchmark.cpp:285); u, v are the barycentrics of PrecomputedTri::intersect (tri.h:55-74). */
+struct bvh_hit3f { uint32_t prim_id; float  t, u, v; };   /* 16 bytes */
+struct bvh_hit3d { uint64_t prim_id; double t, u, v; };   /* 32 bytes */
+
+/* Per-ray traversal counters (the reference's InnerFn hook, bvh.h:168; test/benchmark.cpp:282-296) */
+struct bvh_ray_stats { uint32_t inner_steps, leaves, prim_tests; };
+
+enum bvh_intersect_flags {
+    BVH_ANY_HIT          = 1u << 0,  /* Bvh::intersect<IsAnyHit = true>: stop at the first leaf that reports a hit */
+    BVH_ROBUST           = 1u << 1,  /* Node::intersect_robust (node.h:68-77) instead of intersect_fast */
+    BVH_TIE_LAST_VISITED = 1u << 2,  /* equal-t hits: the last one visited wins, as in the reference's example
+                                        leaf loops (tri.h:69 `t <= tmax`); default is the tree-independent
+                                        rule "lowest original primitive id wins" */
+    BVH_DEVICE_POINTERS  = 1u << 3,  /* rays/hits/vertices are device pointers; the call is stream-ordered */
+    BVH_KERNEL_SIMPLE    = 1u << 8   /* one-thread-per-ray kernel instead of the persistent one (diagnostics) */
+};
+
+/* ---- runtime ------------------------------------------------------------------------------- */
+BVH_API const char* bvh_last_error(void);
+BVH_API int bvh_cuda_device_count(void);
+/* Device used by subsequent bvhNN_build* calls on this thread (default 0). */
+BVH_API int bvh_cuda_set_device(int device);
+/* CUDA stream (cudaStream_t) used by handles created afterwards on this thread; NULL = a private
+ * non-blocking stream per handle.  Lets a host framework keep everything on its current stream. */
+BVH_API void bvh_cuda_set_stream(void* cuda_stream);
+/* Pinned host memory for ray / hit buffers (so that host<->device copies run at PCIe speed). */
+BVH_API void* bvh_host_alloc(size_t bytes);
+BVH_API void bvh_host_free(void* ptr);
+
+#define BVH_B200_DECLARE(T, S)                                                                          \
+    /* Fused prep + build + triangle permutation from raw vertices (prim_count x 9: p0 p1 p2). */        \
+    BVH_API struct bvh##S* bvh##S##_build_triangles(const T* vertices, size_t prim_count,               \
+                                                    const struct bvh_build_config* config, unsigned flags); \
+    /* Attach triangles (original order) to a BVH made by bvhNN_build / bvhNN_load so that it can be   \
+       traced in batches; precomputes and permutes them into BVH order on the device. */                \
+    BVH_API int bvh##S##_set_triangles(struct bvh##S* bvh, const T* vertices, size_t prim_count, unsigned flags); \
+    /* Intersect ray_count rays; hits[i] answers rays[i]. */                                            \
+    BVH_API int bvh##S##_intersect_rays(struct bvh##S* bvh, const struct bvh_ray##S* rays, size_t ray_count, \
+                                        struct bvh_hit##S* hits, unsigned flags);                       \
+    /* Same, also returning the per-ray traversal counters (statistics kernel). */                      \
+    BVH_API int bvh##S##_intersect_rays_stats(struct bvh##S* bvh, const struct bvh_ray##S* rays, size_t ray_count, \
+                                              struct bvh_hit##S* hits, struct bvh_ray_stats* stats, unsigned flags); \
+    /* Wait for the handle's stream. */                                                                 \
+    BVH_API int bvh##S##_sync(struct bvh##S* bvh);                                                      \
+    /* Longest chain of inner nodes below the root (the traversal stack bound). */                      \
+    BVH_API size_t bvh##S##_get_depth(struct bvh##S* bvh);
+
+BVH_B200_DECLARE(float, 3f)
+BVH_B200_DECLARE(double, 3d)
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,121 @@
+"""Test helpers: the host emulation of the device code (tests/host_emul.cpp) and comparison utilities."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INVALID = 0xFFFFFFFF
+P = C.c_void_p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(P)
+
+
+def aligned_zeros(shape, dtype, align=128):
+    """numpy zeros whose data pointer is `align`-byte aligned (the device structs are alignas(32/64) and
+    g++ emits aligned vector moves for them; cudaMalloc gives 256-byte alignment on the GPU)."""
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    raw = np.zeros(count * dtype.itemsize + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + count * dtype.itemsize].view(dtype).reshape(shape)
+
+
+def build_host_emul() -> str:
+    src = os.path.join(ROOT, "tests", "host_emul.cpp")
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    out = os.path.join(out_dir, "libhost_emul.so")
+    csrc = os.path.join(ROOT, "bvh_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("core.cuh", "build_core.cuh", "traverse_core.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC",
+                               "-shared", "-x", "c++", "-I", csrc, src, "-o", out])
+    return out
+
+
+class HostEmul:
+    """Runs the per-thread device functions sequentially on the CPU (logic check without a GPU)."""
+
+    def __init__(self):
+        self.lib = L = C.CDLL(build_host_emul())
+        for s in ("3f", "3d"):
+            getattr(L, f"emul_build{s}").restype = C.c_uint32
+            getattr(L, f"emul_build{s}").argtypes = [P, P, P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, P, P, P, P]
+            getattr(L, f"emul_compact{s}").restype = C.c_size_t
+            getattr(L, f"emul_compact{s}").argtypes = [P, P, P, C.c_size_t]
+            getattr(L, f"emul_trace{s}").argtypes = [P, P, P, P, C.c_size_t, C.c_uint, P, P, P, P, P]
+            getattr(L, f"emul_from_reference{s}").argtypes = [P, P, C.c_size_t, P]
+            getattr(L, f"emul_precompute{s}").argtypes = [P, P, C.c_size_t, P]
+        L.emul_morton30.restype = C.c_uint32
+        L.emul_morton30.argtypes = [C.c_uint32] * 3
+        L.emul_morton63.restype = C.c_uint64
+        L.emul_morton63.argtypes = [C.c_uint64] * 3
+
+    @staticmethod
+    def _s(dtype):
+        return "3f" if np.dtype(dtype) == np.float32 else "3d"
+
+    def build(self, tris=None, bboxes=None, centers=None, min_leaf=1, max_leaf=8, morton_bits=30):
+        src = tris if tris is not None else bboxes
+        dtype, n = src.dtype, src.shape[0]
+        s = self._s(dtype)
+        words = 8  # a device node is 8 scalars wide (6 bounds + index + pad) for both float and double
+        nodes = aligned_zeros((2 * n, words), dtype)
+        ids = np.zeros(n, np.uint32)
+        dtris = aligned_zeros((n, 12), dtype) if tris is not None else None
+        depth = C.c_uint32(0)
+        getattr(self.lib, f"emul_build{s}")(_ptr(tris), _ptr(bboxes), _ptr(centers), n, min_leaf, max_leaf, morton_bits,
+                                            _ptr(nodes), _ptr(ids), _ptr(dtris), C.byref(depth))
+        return dict(nodes=nodes, prim_ids=ids, tris=dtris, depth=depth.value, dtype=dtype, n=n)
+
+    def compact(self, tree):
+        n, dtype = tree["n"], tree["dtype"]
+        bounds = np.zeros((2 * n, 6), dtype)
+        index_values = np.zeros(2 * n, np.uint64)
+        cnt = getattr(self.lib, f"emul_compact{self._s(dtype)}")(_ptr(tree["nodes"]), _ptr(bounds), _ptr(index_values), 2 * n)
+        return bounds[:cnt].copy(), index_values[:cnt].copy()
+
+    def from_reference(self, bounds, index_values, prim_ids, tris):
+        """Device-layout copy of a reference-layout tree (what c_api.cu upload_mirror produces)."""
+        dtype = bounds.dtype
+        n_nodes = bounds.shape[0]
+        nodes = aligned_zeros((n_nodes + 1, 8), dtype)
+        s = self._s(dtype)
+        getattr(self.lib, f"emul_from_reference{s}")(_ptr(np.ascontiguousarray(bounds)),
+                                                    _ptr(np.ascontiguousarray(index_values, dtype=np.uint64)), n_nodes, _ptr(nodes))
+        ids = np.ascontiguousarray(prim_ids, dtype=np.uint32)
+        dtris = aligned_zeros((ids.shape[0], 12), dtype)
+        getattr(self.lib, f"emul_precompute{s}")(_ptr(np.ascontiguousarray(tris)), _ptr(ids), ids.shape[0], _ptr(dtris))
+        return dict(nodes=nodes, prim_ids=ids, tris=dtris, depth=None, dtype=dtype, n=ids.shape[0])
+
+    def trace(self, tree, rays, flags):
+        dtype = tree["dtype"]
+        rays = np.ascontiguousarray(rays, dtype=dtype)
+        m = rays.shape[0]
+        ids = np.zeros(m, np.uint32)
+        t, u, v = (np.zeros(m, dtype) for _ in range(3))
+        st = np.zeros((m, 3), np.uint32)
+        getattr(self.lib, f"emul_trace{self._s(dtype)}")(_ptr(tree["nodes"]), _ptr(tree["tris"]), _ptr(tree["prim_ids"]),
+                                                       _ptr(rays), m, flags, _ptr(ids), _ptr(t), _ptr(u), _ptr(v), _ptr(st))
+        return ids, t, u, v, st
+
+
+def assert_hits_equal(got, want, what=""):
+    """Bit-exact comparison of (ids, t, u, v) tuples."""
+    names = ("ids", "t", "u", "v")
+    for name, a, b in zip(names, got, want):
+        a, b = np.asarray(a), np.asarray(b)
+        if a.dtype.kind == "f":
+            same = a.view(np.uint32 if a.dtype == np.float32 else np.uint64) == b.view(np.uint32 if b.dtype == np.float32 else np.uint64)
+        else:
+            same = a.astype(np.uint64) == b.astype(np.uint64)
+        assert same.all(), f"{what}: {name} differs at {np.nonzero(~same)[0][:8]} ({(~same).sum()} of {same.size})"
+
+
+def hits_tuple(hits):
+    """structured bvh_hit array -> (ids, t, u, v) with 32-bit ids"""
+    return hits["prim_id"].astype(np.uint32), hits["t"], hits["u"], hits["v"]

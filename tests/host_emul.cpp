@@ -1,0 +1,167 @@
+// tests/host_emul.cpp — CPU emulation of the device code, FOR TESTS ONLY.
+//
+// Compiles the very headers the CUDA kernels are made of (bvh_b200/csrc/core.cuh, build_core.cuh,
+// traverse_core.cuh) with g++ -ffp-contract=off and runs the per-thread functions sequentially, so
+// that the logic of the LBVH bottom-up pass and of the traversal stack machine can be checked against
+// the oracle on a machine without a GPU.  It is not part of the product and is never loaded by it;
+// the GPU tests (pytest -m gpu) exercise the real kernels through the C ABI.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "build_core.cuh"
+#include "traverse_core.cuh"
+
+using namespace bvhb200;
+
+namespace {
+
+template <typename U> struct HostStack {
+    U data[256];
+    uint32_t sp = 0;
+    void push(U v) { data[sp++] = v; }
+    U pop() { return data[--sp]; }
+    bool empty() const { return sp == 0; }
+};
+
+template <typename T, typename K>
+uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t n, uint32_t min_leaf, uint32_t max_leaf,
+                    DevNode<T>* nodes /* 2n slots */, uint32_t* prim_ids, DevTri<T>* tris, uint32_t* depth_out) {
+    using R = Real<T>;
+    // K1: centre bounds
+    std::vector<T> cs(3 * (size_t)n);
+    T mn[3] = { R::max(), R::max(), R::max() }, mx[3] = { R::neg(R::max()), R::neg(R::max()), R::neg(R::max()) };
+    for (uint32_t i = 0; i < n; ++i) {
+        T c[3];
+        if (verts) { T bmin[3], bmax[3]; tri_bounds_center(verts + 9 * (size_t)i, bmin, bmax, c); }
+        else for (int k = 0; k < 3; ++k) c[k] = centers[3 * (size_t)i + k];
+        for (int k = 0; k < 3; ++k) { cs[3 * (size_t)i + k] = c[k]; mn[k] = robust_min(mn[k], c[k]); mx[k] = robust_max(mx[k], c[k]); }
+    }
+    // K2: keys
+    const GridXform<T> g = make_grid_xform(mn, mx, MortonTraits<K>::bits_per_axis);
+    std::vector<K> keys(n);
+    for (uint32_t i = 0; i < n; ++i) keys[i] = morton_key<T, K>(&cs[3 * (size_t)i], g);
+    // K3: stable sort by key
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&] (uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::vector<K> sorted(n);
+    for (uint32_t i = 0; i < n; ++i) { sorted[i] = keys[order[i]]; prim_ids[i] = order[i]; }
+    // K4: bottom-up, leaves in order (any order is valid: the second arrival continues)
+    std::vector<NodeAux<T>> aux(2 * (size_t)n + 2);
+    std::vector<int> flags(n, -1);
+    uint32_t info[4] = { 0, 0, 0, 0 };
+    std::memset(nodes, 0, 2 * (size_t)n * sizeof(DevNode<T>));
+    BuildParams<T> p;
+    p.nodes = nodes; p.aux = aux.data(); p.flags = flags.data(); p.info = info; p.n = n;
+    p.min_leaf = min_leaf; p.max_leaf = max_leaf;
+    for (uint32_t i = 0; i < n; ++i) {
+        T bmin[3], bmax[3];
+        const uint32_t id = order[i];
+        if (verts) {
+            T c[3];
+            tri_bounds_center(verts + 9 * (size_t)id, bmin, bmax, c);
+            if (tris) tris[i] = precompute_tri(verts + 9 * (size_t)id);
+        } else {
+            for (int k = 0; k < 3; ++k) { bmin[k] = bboxes[6 * (size_t)id + k]; bmax[k] = bboxes[6 * (size_t)id + 3 + k]; }
+        }
+        build_bottom_up<T, K, HostSync>(p, sorted.data(), i, bmin, bmax);
+    }
+    *depth_out = info[0];
+    return info[1];
+}
+
+// dense reference layout out of the sparse device array (same walk as c_api.cu download_mirror)
+template <typename T>
+size_t emul_compact(const DevNode<T>* dev, T* bounds, uint64_t* index_values, size_t cap) {
+    using U = typename Real<T>::UInt;
+    struct Out { T b[6]; U index; };
+    std::vector<Out> out;
+    auto emit = [&] (const DevNode<T>& s) { Out o; std::memcpy(o.b, s.bounds, sizeof o.b); o.index = s.index; out.push_back(o); };
+    emit(dev[1]);
+    std::vector<size_t> stack;
+    if (index_count(out[0].index) == 0) stack.push_back(0);
+    while (!stack.empty()) {
+        size_t dst = stack.back(); stack.pop_back();
+        size_t first_src = (size_t)index_first(out[dst].index), first_dst = out.size();
+        emit(dev[first_src + 1]); emit(dev[first_src + 2]);
+        out[dst].index = make_index<U>((U)first_dst, 0);
+        if (index_count(out[first_dst + 1].index) == 0) stack.push_back(first_dst + 1);
+        if (index_count(out[first_dst].index) == 0) stack.push_back(first_dst);
+    }
+    if (out.size() <= cap) for (size_t i = 0; i < out.size(); ++i) {
+        std::memcpy(bounds + 6 * i, out[i].b, sizeof out[i].b);
+        index_values[i] = out[i].index;
+    }
+    return out.size();
+}
+
+template <typename T>
+void emul_trace(const DevNode<T>* nodes, const DevTri<T>* tris, const uint32_t* prim_ids, const T* rays, size_t m,
+                unsigned flags, uint32_t* ids, T* ts, T* us, T* vs, uint32_t* stats) {
+    using U = typename Real<T>::UInt;
+    const bool any = flags & 1u, robust = flags & 2u, lowest = flags & 4u;
+    for (size_t i = 0; i < m; ++i) {
+        RayCtx<T> r;
+        for (int k = 0; k < 3; ++k) { r.org[k] = rays[8 * i + k]; r.dir[k] = rays[8 * i + 3 + k]; }
+        r.tmin = rays[8 * i + 6]; r.tmax = rays[8 * i + 7];
+        const T tmax_in = r.tmax;
+        HitState<T> hit { kInvalidId, r.tmax, (T)0, (T)0 };
+        HostStack<U> stack;
+        uint32_t st[3] = { 0, 0, 0 };
+        const U root = nodes[1].index;
+        if (robust) {
+            ray_prologue<T, true>(r);
+            if (any) traverse_ray<T, true, true>(nodes, tris, prim_ids, lowest, root, r, hit, stack, st);
+            else     traverse_ray<T, false, true>(nodes, tris, prim_ids, lowest, root, r, hit, stack, st);
+        } else {
+            ray_prologue<T, false>(r);
+            if (any) traverse_ray<T, true, false>(nodes, tris, prim_ids, lowest, root, r, hit, stack, st);
+            else     traverse_ray<T, false, false>(nodes, tris, prim_ids, lowest, root, r, hit, stack, st);
+        }
+        const bool was_hit = hit.slot != kInvalidId;
+        ids[i] = was_hit ? prim_ids[hit.slot] : kInvalidId;
+        ts[i] = was_hit ? hit.t : tmax_in; us[i] = was_hit ? hit.u : (T)0; vs[i] = was_hit ? hit.v : (T)0;
+        if (stats) { stats[3 * i] = st[0]; stats[3 * i + 1] = st[1]; stats[3 * i + 2] = st[2]; }
+    }
+}
+
+// upload path: dense reference arrays -> device layout (slot = index + 1)
+template <typename T>
+void emul_from_reference(const T* bounds, const uint64_t* index_values, size_t node_count, DevNode<T>* dev) {
+    using U = typename Real<T>::UInt;
+    std::memset(dev, 0, sizeof(DevNode<T>));
+    for (size_t i = 0; i < node_count; ++i) {
+        std::memcpy(dev[i + 1].bounds, bounds + 6 * i, 6 * sizeof(T));
+        dev[i + 1].index = (U)index_values[i];
+        dev[i + 1].pad = 0;
+    }
+}
+
+} // namespace
+
+#define EMUL_API(T, S) \
+    uint32_t emul_build##S(const T* verts, const T* bboxes, const T* centers, uint32_t n, uint32_t min_leaf, uint32_t max_leaf, \
+                           int morton_bits, void* nodes, uint32_t* prim_ids, void* tris, uint32_t* depth) { \
+        if (morton_bits <= 30) return emul_build<T, uint32_t>(verts, bboxes, centers, n, min_leaf, max_leaf, (DevNode<T>*)nodes, prim_ids, (DevTri<T>*)tris, depth); \
+        return emul_build<T, uint64_t>(verts, bboxes, centers, n, min_leaf, max_leaf, (DevNode<T>*)nodes, prim_ids, (DevTri<T>*)tris, depth); } \
+    size_t emul_compact##S(const void* dev, T* bounds, uint64_t* index_values, size_t cap) { \
+        return emul_compact<T>((const DevNode<T>*)dev, bounds, index_values, cap); } \
+    void emul_trace##S(const void* nodes, const void* tris, const uint32_t* prim_ids, const T* rays, size_t m, unsigned flags, \
+                       uint32_t* ids, T* ts, T* us, T* vs, uint32_t* stats) { \
+        emul_trace<T>((const DevNode<T>*)nodes, (const DevTri<T>*)tris, prim_ids, rays, m, flags, ids, ts, us, vs, stats); } \
+    void emul_from_reference##S(const T* bounds, const uint64_t* index_values, size_t node_count, void* dev) { \
+        emul_from_reference<T>(bounds, index_values, node_count, (DevNode<T>*)dev); } \
+    void emul_precompute##S(const T* verts, const uint32_t* prim_ids, size_t n, void* tris) { \
+        for (size_t i = 0; i < n; ++i) ((DevTri<T>*)tris)[i] = precompute_tri(verts + 9 * (size_t)prim_ids[i]); }
+
+extern "C" {
+EMUL_API(float, 3f)
+EMUL_API(double, 3d)
+uint32_t emul_morton30(uint32_t x, uint32_t y, uint32_t z) { return MortonTraits<uint32_t>::encode(x, y, z); }
+uint64_t emul_morton63(uint64_t x, uint64_t y, uint64_t z) { return MortonTraits<uint64_t>::encode(x, y, z); }
+size_t emul_sizeof_node(int is_double) { return is_double ? sizeof(DevNode<double>) : sizeof(DevNode<float>); }
+size_t emul_sizeof_tri(int is_double) { return is_double ? sizeof(DevTri<double>) : sizeof(DevTri<float>); }
+}

@@ -1,0 +1,142 @@
+"""CPU check of the device code's logic: the headers the CUDA kernels are made of are compiled by g++
+(tests/host_emul.cpp) and compared with the oracle.  Covers the LBVH bottom-up pass (structure
+invariants, box unions, SAH leaf collapse, depth bound) and the traversal stack machine (same-tree
+bit-exactness incl. step counters; cross-tree exactness under the canonical tie-break)."""
+import numpy as np
+import pytest
+
+from bvh_b200 import scenes
+from oracle.pyoracle import ANY_HIT, ROBUST, TIE_LOWEST_ID
+from tests.conftest import golden
+from tests.helpers import INVALID, assert_hits_equal
+
+MODES = (("lowest", TIE_LOWEST_ID), ("last", 0), ("any", ANY_HIT | TIE_LOWEST_ID), ("robust", ROBUST | TIE_LOWEST_ID))
+
+
+def _tree_depth(index_values):
+    depth, stack = 0, [(0, 0)]
+    while stack:
+        i, d = stack.pop()
+        v = int(index_values[i])
+        if v & 15:
+            continue
+        depth = max(depth, d + 1)
+        stack.append((v >> 4, d + 1))
+        stack.append(((v >> 4) + 1, d + 1))
+    return depth
+
+
+@pytest.mark.parametrize("kind,n,dtype,bits", [
+    ("soup", 1, np.float32, 30), ("soup", 2, np.float32, 30), ("soup", 3, np.float32, 30), ("soup", 17, np.float32, 30),
+    ("soup", 5000, np.float32, 30), ("soup", 5000, np.float32, 63), ("grid", 5000, np.float32, 30),
+    ("box12", 12, np.float32, 30), ("soup", 2000, np.float64, 30), ("soup", 2000, np.float64, 63)])
+def test_lbvh_structure_and_parity(emul, oracle, kind, n, dtype, bits):
+    tris = scenes.make_mesh(kind, n, dtype=dtype)
+    n = tris.shape[0]
+    tree = emul.build(tris=tris, morton_bits=bits)
+    bounds, index_values = emul.compact(tree)
+    otree = oracle.from_arrays(bounds, index_values, tree["prim_ids"])
+    assert oracle.check_invariants(otree, 8) == 0
+    assert tree["depth"] == _tree_depth(index_values)
+    assert sorted(tree["prim_ids"].tolist()) == list(range(n))
+    # inner boxes are exactly what the reference's refit computes from the leaf boxes
+    before = otree.arrays()[0]
+    oracle.refit(otree)
+    assert (otree.arrays()[0] == before).all()
+    # SATO: left child has the larger (or equal) half-area
+    for i in np.nonzero((index_values & 15) == 0)[0]:
+        f = int(index_values[i]) >> 4
+        d = bounds[[f, f + 1], 1::2] - bounds[[f, f + 1], 0::2]
+        area = (d[:, 0] + d[:, 1]) * d[:, 2] + d[:, 0] * d[:, 1]
+        assert area[0] >= area[1]
+    # traversal
+    oracle.set_triangles(otree, tris)
+    rays = scenes.make_primary(kind, 64, 64, dtype=dtype)
+    for _, flags in MODES:
+        got = emul.trace(tree, rays, flags)
+        want = oracle.trace(otree, rays, flags=flags, stats=True)
+        assert_hits_equal(got[:4], want[:4], f"{kind}/{n}/{flags}")
+        assert (got[4] == want[4]).all()
+    if n * rays.shape[0] <= 4_000_000:
+        assert_hits_equal(emul.trace(tree, rays, TIE_LOWEST_ID)[:4], oracle.brute_force(tris, rays), "brute force")
+
+
+@pytest.mark.parametrize("name", ["soup2k_f32", "grid2k_f32", "box12_f32", "soup1k_f64", "soup_incoherent_f32"])
+def test_against_golden(emul, name):
+    """LBVH tree vs the reference's tree (golden outputs): identical under the canonical tie-break;
+    reference tree run through the device stack machine: identical in every mode, counters included."""
+    g = golden(name)
+    tris, rays = g["tris"], g["rays"]
+    lbvh = emul.build(tris=tris)
+    ids, t, u, v, _ = emul.trace(lbvh, rays, TIE_LOWEST_ID)
+    assert_hits_equal((ids, t, u, v), tuple(g[f"lowest_{k}"] for k in ("ids", "t", "u", "v")), name)
+    any_ids = emul.trace(lbvh, rays, ANY_HIT | TIE_LOWEST_ID)[0]
+    assert ((any_ids != INVALID) == (g["any_ids"] != INVALID)).all()
+    same = emul.from_reference(g["ref_bounds"], g["ref_index"], g["ref_prim_ids"], tris)
+    for mode, flags in MODES:
+        got = emul.trace(same, rays, flags)
+        assert_hits_equal(got[:4], tuple(g[f"{mode}_{k}"] for k in ("ids", "t", "u", "v")), f"{name}/{mode}")
+        assert (got[4] == g[f"{mode}_stats"]).all()
+
+
+def test_duplicate_and_degenerate_primitives(emul, oracle):
+    """All-identical Morton keys (balanced by the index tie-break), zero-area and repeated triangles."""
+    base = scenes.soup(1, seed=5)
+    tris = np.repeat(base, 300, axis=0)
+    tris[100:200, 3:] = tris[100:200, :3].repeat(2, axis=0).reshape(100, 6)[:, :6]     # degenerate: p1 = p2 = p0
+    tree = emul.build(tris=tris)
+    bounds, index_values = emul.compact(tree)
+    otree = oracle.from_arrays(bounds, index_values, tree["prim_ids"])
+    assert oracle.check_invariants(otree, 8) == 0
+    assert tree["depth"] <= 12
+    rays = scenes.make_primary("soup", 32, 32)
+    got = emul.trace(tree, rays, TIE_LOWEST_ID)
+    assert_hits_equal(got[:4], oracle.brute_force(tris, rays), "duplicates")
+    hit = got[0] != INVALID
+    assert (got[0][hit] == got[0][hit].min()).all()          # lowest id among identical triangles
+
+
+def test_axis_parallel_rays(emul, oracle):
+    """Zero direction components give +-FLT_MAX inverse directions and inf-inf NaNs in the slab test;
+    the reference swallows them through argument order (utils.h:40-43, node.h:112-115)."""
+    tris = scenes.grid(800)
+    tree = emul.build(tris=tris)
+    bounds, index_values = emul.compact(tree)
+    otree = oracle.from_arrays(bounds, index_values, tree["prim_ids"])
+    oracle.set_triangles(otree, tris)
+    rng = np.random.RandomState(11)
+    m = 2000
+    rays = np.zeros((m, 8), np.float32)
+    rays[:, 0] = rng.uniform(0, 1, m); rays[:, 1] = 0.5; rays[:, 2] = rng.uniform(0, 1, m)
+    rays[:, 4] = -1.0                                         # straight down: dir = (0, -1, 0)
+    rays[: m // 2, 0] = np.round(rays[: m // 2, 0] * 20) / 20  # many exactly on grid lines / vertices
+    rays[:, 7] = np.finfo(np.float32).max
+    for _, flags in MODES:
+        got = emul.trace(tree, rays, flags)
+        want = oracle.trace(otree, rays, flags=flags, stats=True)
+        assert_hits_equal(got[:4], want[:4], f"axis-parallel/{flags}")
+        assert (got[4] == want[4]).all()
+    # Rays lying exactly in box faces are where the FAST slab test is not watertight (the result then
+    # depends on the tree, in the reference too); the ROBUST test is, so it must agree with brute force.
+    assert_hits_equal(emul.trace(tree, rays, ROBUST | TIE_LOWEST_ID)[:4], oracle.brute_force(tris, rays), "axis-parallel brute force")
+
+
+def test_boxes_and_centres_input(emul, oracle):
+    tris = scenes.soup(3000)
+    bb, cc = oracle.tri_bboxes_centers(tris)
+    a = emul.build(tris=tris)
+    b = emul.build(bboxes=bb, centers=cc)
+    assert (a["nodes"] == b["nodes"]).all() and (a["prim_ids"] == b["prim_ids"]).all()
+
+
+def test_leaf_size_config(emul, oracle):
+    tris = scenes.soup(4000)
+    for min_leaf, max_leaf in ((1, 1), (1, 4), (4, 8), (1, 15)):
+        tree = emul.build(tris=tris, min_leaf=min_leaf, max_leaf=max_leaf)
+        bounds, index_values = emul.compact(tree)
+        otree = oracle.from_arrays(bounds, index_values, tree["prim_ids"])
+        assert oracle.check_invariants(otree, max_leaf) == 0
+        counts = index_values & 15
+        assert counts.max() <= max_leaf
+        if max_leaf == 1:
+            assert index_values.shape[0] == 2 * tris.shape[0] - 1

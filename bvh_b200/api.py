@@ -262,15 +262,8 @@ class Bvh:
         bounds = nodes["bounds"].copy()
         index_values = nodes["index"].astype(np.uint64)
         get_id = self._f("get_prim_id")
-        step = max(1, p // 64)
-        ids = np.fromiter((get_id(self.handle, i) for i in range(p)), dtype=np.uint64, count=p) if p <= 4096 else None
-        if ids is None:
-            ids = self._prim_ids_bulk(p)
+        ids = np.fromiter((get_id(self.handle, i) for i in range(p)), dtype=np.uint64, count=p)
         return bounds, index_values, ids
-
-    def _prim_ids_bulk(self, p):
-        get_id = self._f("get_prim_id")
-        return np.fromiter((get_id(self.handle, i) for i in range(p)), dtype=np.uint64, count=p)
 
     def refit(self) -> None:
         self._f("refit")(self.handle)

@@ -1,0 +1,81 @@
+"""Ray-batch sharding across GPUs.
+
+The traversal has no exchange step: rays are independent units, the BVH is replicated (every rank runs
+the same deterministic build), each rank traces a contiguous range of the global batch.  The only
+collective is the gather of 16-byte hit records the north star asks for, issued per chunk on a side
+stream so that it overlaps the traversal of the next chunk.  ``torch.distributed`` is plumbing only
+(NCCL on GPUs, gloo in the CPU tests); the tracer is injected so the host logic is testable without
+a device.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous shard [begin, end) of ``total`` units for ``rank`` — contiguity keeps primary-ray
+    coherence per GPU.  The first ``total % world`` ranks get one extra unit."""
+    base, extra = divmod(total, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def chunk_bounds(count: int, chunks: int) -> list[tuple[int, int]]:
+    chunks = max(1, min(chunks, count)) if count else 1
+    return [shard_range(count, c, chunks) for c in range(chunks)]
+
+
+class ShardedTracer:
+    """Traces this rank's shard chunk by chunk and all-gathers the hit records.
+
+    ``trace(begin, end, out)`` must enqueue the traversal of local rays [begin, end) into ``out``
+    (a ``(end-begin, words)`` tensor) on the CURRENT stream.  All ranks must hold equally sized shards
+    (pad the batch) because ``all_gather_into_tensor`` needs equal contributions.
+    """
+
+    def __init__(self, local_count: int, hit_words: int, dtype: torch.dtype, device: torch.device,
+                 trace: Callable[[int, int, torch.Tensor], None], chunks: int = 4, group=None):
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.group = group
+        self.trace = trace
+        self.local_count = local_count
+        self.bounds = chunk_bounds(local_count, chunks)
+        self.local = torch.empty((local_count, hit_words), dtype=dtype, device=device)
+        # gathered[c] is the concatenation over ranks of chunk c: (world * chunk_len, words), rank-major
+        self.gathered = [torch.empty((self.world * (e - b), hit_words), dtype=dtype, device=device) for b, e in self.bounds]
+        self.is_cuda = device.type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=device) if self.is_cuda else None
+
+    def step(self) -> None:
+        """One pass: trace every chunk, gather each as soon as it is done.  Returns with all work
+        enqueued; the caller synchronises."""
+        handles = []
+        for c, (b, e) in enumerate(self.bounds):
+            self.trace(b, e, self.local[b:e])
+            if self.world == 1:
+                continue
+            if self.is_cuda:
+                done = torch.cuda.Event()
+                done.record()
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(done)
+                    dist.all_gather_into_tensor(self.gathered[c], self.local[b:e], group=self.group)
+            else:
+                handles.append(dist.all_gather_into_tensor(self.gathered[c], self.local[b:e].contiguous(),
+                                                           group=self.group, async_op=True))
+        for h in handles:
+            h.wait()
+        if self.is_cuda and self.world > 1:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def global_hits(self) -> torch.Tensor:
+        """The whole batch's hit records in global ray order: (world * local_count, words)."""
+        if self.world == 1:
+            return self.local
+        views = [g.view(self.world, e - b, -1) for g, (b, e) in zip(self.gathered, self.bounds)]
+        per_rank = [torch.cat([v[r] for v in views], dim=0) for r in range(self.world)]
+        return torch.cat(per_rank, dim=0)

@@ -1,0 +1,326 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against the oracle, the
+committed golden vectors of the unmodified reference, and — when present — the reference itself.
+Bit-exact everywhere: ids, t, u, v (float and double), node arrays, step counters."""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from bvh_b200 import scenes
+from oracle.pyoracle import ANY_HIT as O_ANY, ROBUST as O_ROBUST, TIE_LOWEST_ID as O_LOWEST
+from tests.conftest import golden
+from tests.helpers import INVALID, assert_hits_equal, hits_tuple
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_SCENES = ["soup2k_f32", "grid2k_f32", "box12_f32", "soup1k_f64", "soup_incoherent_f32"]
+
+
+def modes(api):
+    """(golden key, oracle flags, C-ABI flags)"""
+    return (("lowest", O_LOWEST, 0), ("last", 0, api.TIE_LAST_VISITED),
+            ("any", O_ANY | O_LOWEST, api.ANY_HIT), ("robust", O_ROBUST | O_LOWEST, api.ROBUST))
+
+
+@pytest.mark.parametrize("name", GOLDEN_SCENES)
+def test_lbvh_vs_reference_golden(gpu_lib, name):
+    """GPU-built LBVH + GPU traversal reproduce the reference's closest hits on the reference's own
+    (different) tree under the canonical tie-break; any-hit agrees on occlusion."""
+    api = gpu_lib
+    g = golden(name)
+    bvh = api.Bvh.build_triangles(g["tris"])
+    for kernel in (0, api.KERNEL_SIMPLE):
+        hits = bvh.intersect_rays(g["rays"], flags=kernel)
+        assert_hits_equal(hits_tuple(hits), tuple(g[f"lowest_{k}"] for k in ("ids", "t", "u", "v")), f"{name}/closest/{kernel}")
+        hits = bvh.intersect_rays(g["rays"], flags=kernel | api.ROBUST)
+        assert_hits_equal(hits_tuple(hits), tuple(g[f"robust_{k}"] for k in ("ids", "t", "u", "v")), f"{name}/robust/{kernel}")
+        occl = bvh.intersect_rays(g["rays"], flags=kernel | api.ANY_HIT)
+        assert ((occl["prim_id"].astype(np.uint32) != INVALID) == (g["any_ids"] != INVALID)).all()
+        miss = occl["prim_id"].astype(np.uint32) == INVALID
+        assert (occl["t"][miss] == g["rays"][miss, 7]).all()
+
+
+@pytest.mark.parametrize("name", GOLDEN_SCENES)
+def test_reference_tree_on_gpu(gpu_lib, name):
+    """The reference's own tree, loaded through bvhNN_load (reference file format) and traced on the
+    GPU, gives the reference's outputs in EVERY mode — including the visit-order dependent
+    last-visited tie rule and the per-ray step counters: same nodes visited in the same order."""
+    api = gpu_lib
+    g = golden(name)
+    dtype = g["tris"].dtype
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "ref.bvh")
+        open(path, "wb").write(g["ref_serialized"].tobytes())
+        bvh = api.Bvh.load(path, dtype=dtype)
+        assert bvh.node_count == g["ref_bounds"].shape[0]
+        bounds, index_values, prim_ids = bvh.arrays()
+        assert (bounds == g["ref_bounds"]).all() and (index_values == g["ref_index"]).all() and (prim_ids == g["ref_prim_ids"]).all()
+        bvh.set_triangles(g["tris"])
+        for mode, _, flags in modes(api):
+            hits, st = bvh.intersect_rays(g["rays"], flags=flags, stats=True)
+            assert_hits_equal(hits_tuple(hits), tuple(g[f"{mode}_{k}"] for k in ("ids", "t", "u", "v")), f"{name}/{mode}")
+            want = g[f"{mode}_stats"]
+            assert (st["inner_steps"] == want[:, 0]).all() and (st["leaves"] == want[:, 1]).all() and (st["prim_tests"] == want[:, 2]).all()
+            hits2 = bvh.intersect_rays(g["rays"], flags=flags)          # persistent kernel, same answers
+            assert_hits_equal(hits_tuple(hits2), hits_tuple(hits), f"{name}/{mode}/persistent")
+        # save -> byte-identical file
+        out = os.path.join(tmp, "out.bvh")
+        bvh.save(out)
+        assert open(out, "rb").read() == g["ref_serialized"].tobytes()
+
+
+@pytest.mark.parametrize("kind,n,dtype", [("soup", 20000, np.float32), ("grid", 20000, np.float32), ("soup", 8000, np.float64)])
+def test_gpu_tree_is_a_valid_reference_bvh(gpu_lib, oracle, emul, kind, n, dtype):
+    """Download the GPU-built tree through the reference accessors: structure invariants hold, boxes are
+    what the reference's refit computes, it equals the host emulation's tree node for node, and the
+    oracle (reference algorithm) traversing it agrees with the GPU bit for bit, counters included."""
+    api = gpu_lib
+    tris = scenes.make_mesh(kind, n, dtype=dtype)
+    bvh = api.Bvh.build_triangles(tris)
+    bounds, index_values, prim_ids = bvh.arrays()
+    tree = oracle.from_arrays(bounds, index_values, prim_ids)
+    assert oracle.check_invariants(tree, 8) == 0
+    before = tree.arrays()[0]
+    oracle.refit(tree)
+    assert (tree.arrays()[0] == before).all()
+    etree = emul.build(tris=tris)
+    eb, ei = emul.compact(etree)
+    assert eb.shape == bounds.shape and (eb == bounds).all() and (ei == index_values).all()
+    assert (etree["prim_ids"] == prim_ids).all()
+    assert bvh.depth == etree["depth"]
+    oracle.set_triangles(tree, tris)
+    rays = scenes.make_primary(kind, 129, 127, dtype=dtype)
+    for mode, oflags, flags in modes(api):
+        hits, st = bvh.intersect_rays(rays, flags=flags, stats=True)
+        want = oracle.trace(tree, rays, flags=oflags, stats=True)
+        assert_hits_equal(hits_tuple(hits), want[:4], f"{kind}/{mode}")
+        assert (st["inner_steps"] == want[4][:, 0]).all() and (st["prim_tests"] == want[4][:, 2]).all()
+        assert_hits_equal(hits_tuple(bvh.intersect_rays(rays, flags=flags)), want[:4], f"{kind}/{mode}/persistent")
+    # bvhNN_refit on an untouched tree changes nothing; the device copy stays usable
+    bvh.refit()
+    assert (bvh.arrays()[0] == bounds).all()
+    assert_hits_equal(hits_tuple(bvh.intersect_rays(rays)), oracle.trace(tree, rays, flags=O_LOWEST)[:4], "after refit")
+
+
+def test_build_from_boxes_and_centres(gpu_lib, oracle):
+    """bvh3f_build(pool, bboxes, centers, n, config) — the reference's own entry point — builds the same
+    tree as the fused triangle path; bvh3f_set_triangles makes it traceable."""
+    api = gpu_lib
+    tris = scenes.soup(5000)
+    bb, cc = oracle.tri_bboxes_centers(tris)
+    a = api.Bvh.build_triangles(tris)
+    pool = api.lib().bvh_thread_pool_create(0)
+    b = api.Bvh.build(bb, cc, thread_pool=pool)
+    api.lib().bvh_thread_pool_destroy(pool)
+    for x, y in zip(a.arrays(), b.arrays()):
+        assert (x == y).all()
+    b.set_triangles(tris)
+    rays = scenes.make_primary("soup", 100, 100)
+    assert_hits_equal(hits_tuple(a.intersect_rays(rays)), hits_tuple(b.intersect_rays(rays)), "boxes vs triangles")
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 33])
+def test_tiny_inputs(gpu_lib, oracle, n):
+    api = gpu_lib
+    tris = scenes.soup(n, seed=n)
+    bvh = api.Bvh.build_triangles(tris)
+    rays = scenes.make_primary("soup", 31, 33)
+    assert_hits_equal(hits_tuple(bvh.intersect_rays(rays, flags=api.ROBUST)), oracle.brute_force(tris, rays), f"n={n}")
+    bounds, index_values, prim_ids = bvh.arrays()
+    assert oracle.check_invariants(oracle.from_arrays(bounds, index_values, prim_ids), 8) == 0
+
+
+@pytest.mark.parametrize("m", [0, 1, 31, 32, 33, 127, 129, 1000])
+def test_ragged_ray_counts(gpu_lib, m):
+    api = gpu_lib
+    g = golden("soup2k_f32")
+    bvh = api.Bvh.build_triangles(g["tris"])
+    rays = g["rays"][:m]
+    hits = bvh.intersect_rays(rays) if m else bvh.intersect_rays(np.zeros((0, 8), np.float32))
+    assert hits.shape[0] == m
+    assert_hits_equal(hits_tuple(hits), tuple(g[f"lowest_{k}"][:m] for k in ("ids", "t", "u", "v")), f"m={m}")
+
+
+def test_duplicates_degenerates_and_leaf_config(gpu_lib, oracle):
+    api = gpu_lib
+    base = scenes.soup(1, seed=5)
+    tris = np.repeat(base, 300, axis=0)
+    tris[100:200, 3:6] = tris[100:200, 0:3]
+    tris[100:200, 6:9] = tris[100:200, 0:3]
+    more = scenes.soup(2000, seed=9)
+    tris = np.concatenate([tris, more])
+    rays = scenes.make_primary("soup", 64, 64)
+    want = oracle.brute_force(tris, rays)
+    for min_leaf, max_leaf in ((None, None), (1, 1), (2, 4), (1, 15)):
+        bvh = api.Bvh.build_triangles(tris, min_leaf_size=min_leaf, max_leaf_size=max_leaf)
+        assert_hits_equal(hits_tuple(bvh.intersect_rays(rays, flags=api.ROBUST)), want, f"leaf {min_leaf},{max_leaf}")
+        bounds, index_values, prim_ids = bvh.arrays()
+        assert oracle.check_invariants(oracle.from_arrays(bounds, index_values, prim_ids), max_leaf or 8) == 0
+
+
+def test_per_ray_callback_api(gpu_lib):
+    """bvh3f_intersect_ray with a C leaf callback (reference c_api/bvh.h:233-295) on a GPU-built tree:
+    same closest hits as the batched kernel."""
+    api = gpu_lib
+    g = golden("soup2k_f32")
+    tris, rays = g["tris"], g["rays"][:512]
+    bvh = api.Bvh.build_triangles(tris)
+    _, _, prim_ids = bvh.arrays()
+    batched = bvh.intersect_rays(rays)
+    state = {}
+
+    def moller(tri, ray, tmax):
+        p0, p1, p2 = tri[0:3], tri[3:6], tri[6:9]
+        e1, e2 = p0 - p1, p2 - p0
+        n = np.cross(e1, e2)
+        c = p0 - ray[0:3]
+        r = np.cross(ray[3:6], c)
+        det = np.dot(n, ray[3:6])
+        if det == 0:
+            return None
+        inv = 1.0 / det
+        u, v = np.dot(r, e2) * inv, np.dot(r, e1) * inv
+        if u >= -1e-7 and v >= -1e-7 and 1 - u - v >= -1e-7:
+            t = np.dot(n, c) * inv
+            if ray[6] <= t <= tmax:
+                return t
+        return None
+
+    CB = C.CFUNCTYPE(C.c_bool, C.c_void_p, C.POINTER(C.c_float), C.c_size_t, C.c_size_t)
+
+    def leaf(_, t_ptr, begin, end):
+        was_hit = False
+        for i in range(begin, end):
+            pid = int(prim_ids[i])
+            t = moller(tris[pid].astype(np.float64), state["ray"].astype(np.float64), t_ptr[0])
+            if t is not None:
+                t_ptr[0] = t
+                state["id"] = pid
+                was_hit = True
+        return was_hit
+
+    class Callback(C.Structure):
+        _fields_ = [("user_data", C.c_void_p), ("user_fn", CB)]
+
+    cb = Callback(None, CB(leaf))
+    fn = api.lib().bvh3f_intersect_ray
+    agree = 0
+    for i in range(rays.shape[0]):
+        state["ray"], state["id"] = rays[i], INVALID
+        fn(bvh.handle, C.c_void_p(rays[i].ctypes.data), C.byref(cb))
+        agree += int(state["id"] == int(batched["prim_id"][i]))
+    assert agree >= rays.shape[0] - 2        # the python triangle test is float64: allow grazing-edge flips
+
+
+def test_device_pointers_on_torch_stream(gpu_lib):
+    """BVH_DEVICE_POINTERS: rays and hits stay on the device, work is ordered on the caller's stream."""
+    import torch
+    api = gpu_lib
+    g = golden("soup2k_f32")
+    api.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        verts = torch.from_numpy(g["tris"]).cuda()
+        bvh = api.Bvh.build_triangles(verts.data_ptr(), count=verts.shape[0], dtype=np.float32, flags=api.DEVICE_POINTERS)
+        rays = torch.from_numpy(g["rays"]).cuda()
+        hits = torch.empty((rays.shape[0], 4), dtype=torch.int32, device="cuda")
+        bvh.intersect_rays(rays.data_ptr(), count=rays.shape[0], hits=hits.data_ptr(), flags=api.DEVICE_POINTERS)
+        torch.cuda.synchronize()
+        out = hits.cpu().numpy().view(api.HIT3F).reshape(-1)
+        assert_hits_equal(hits_tuple(out), tuple(g[f"lowest_{k}"] for k in ("ids", "t", "u", "v")), "device pointers")
+    finally:
+        api.set_stream(None)
+
+
+@pytest.mark.parametrize("kind", ["soup", "grid"])
+def test_full_size_properties(gpu_lib, oracle, kind):
+    """BASELINE configs 2/3 at full size (1M triangles, 10M rays): size-independent properties plus an
+    exact check of a 20k-ray sample against the reference algorithm on the downloaded tree and, when the
+    compiled reference is available, against the reference's own High-quality tree."""
+    api = gpu_lib
+    tris = scenes.make_mesh(kind, 1_000_000)
+    n = tris.shape[0]
+    bvh = api.Bvh.build_triangles(tris)
+    rays = scenes.make_primary(kind, 3163, 3163)
+    m = rays.shape[0]
+    hits = bvh.intersect_rays(rays)
+    ids = hits["prim_id"]
+    hit = ids != INVALID
+    assert 0.3 < hit.mean() <= 1.0
+    assert (ids[hit] < n).all()
+    assert (hits["t"][~hit] == rays[~hit, 7]).all() and (hits["t"][hit] > 0).all()
+    assert (hits["u"][hit] >= -1e-6).all() and (hits["v"][hit] >= -1e-6).all() and ((hits["u"] + hits["v"])[hit] <= 1 + 1e-5).all()
+    # both kernels agree exactly
+    simple = bvh.intersect_rays(rays, flags=api.KERNEL_SIMPLE)
+    assert (simple.view(np.uint8) == hits.view(np.uint8)).all()
+    # nothing lies in front of a reported closest hit: re-trace with tmax just below t as any-hit
+    sel = np.nonzero(hit)[0][:: max(1, int(hit.sum()) // 200_000)]
+    shortened = rays[sel].copy()
+    shortened[:, 7] = hits["t"][sel] * np.float32(1 - 1e-5)
+    occl = bvh.intersect_rays(shortened, flags=api.ANY_HIT)
+    assert (occl["prim_id"] == INVALID).mean() > 0.999
+    # ... and the hit itself is found again as an occluder when tmax is the reported t
+    exact = rays[sel].copy()
+    exact[:, 7] = hits["t"][sel]
+    occl = bvh.intersect_rays(exact, flags=api.ANY_HIT)
+    assert (occl["prim_id"] != INVALID).all()
+    # exact check of a sample against the oracle on the same tree
+    rng = np.random.RandomState(1)
+    sample = np.sort(rng.choice(m, 20_000, replace=False))
+    bounds, index_values, prim_ids = bvh.arrays()
+    tree = oracle.from_arrays(bounds, index_values, prim_ids)
+    assert oracle.check_invariants(tree, 8) == 0
+    oracle.set_triangles(tree, tris)
+    want = oracle.trace(tree, rays[sample], flags=O_LOWEST)
+    assert_hits_equal(hits_tuple(hits[sample]), want, f"{kind}-1M sample vs oracle")
+    from oracle.pyoracle import Ref, ref_available
+    if ref_available():
+        ref = Ref()
+        bb, cc = ref.tri_bboxes_centers(tris)
+        rtree = ref.build(bb, cc, quality="high", threads=0)
+        ref.set_triangles(rtree, tris)
+        want = ref.trace(rtree, rays[sample], flags=O_LOWEST, threads=0)
+        got = hits_tuple(hits[sample])
+        same = got[0] == want[0]
+        # the fast slab test is tree-dependent only for rays grazing box faces exactly; require exactness
+        assert same.all(), f"{(~same).sum()} ids differ from the reference's own tree"
+        assert_hits_equal(got, want, f"{kind}-1M sample vs reference tree")
+
+
+def test_incoherent_any_hit_full_size(gpu_lib, oracle):
+    """BASELINE config 3: 1M-triangle soup, incoherent AO-style rays, any-hit: occlusion agrees with the
+    oracle on a sample; a ray reported occluded really has a hit within [tmin, tmax]."""
+    api = gpu_lib
+    tris = scenes.soup(1_000_000)
+    bvh = api.Bvh.build_triangles(tris)
+    rays = scenes.incoherent_rays(tris, 2_000_000)
+    occl = bvh.intersect_rays(rays, flags=api.ANY_HIT)
+    closest = bvh.intersect_rays(rays)
+    assert ((occl["prim_id"] != INVALID) == (closest["prim_id"] != INVALID)).all()
+    hit = occl["prim_id"] != INVALID
+    assert (occl["t"][hit] <= rays[hit, 7]).all() and (occl["t"][hit] >= closest["t"][hit]).all()
+    sample = np.arange(0, rays.shape[0], 100)
+    bounds, index_values, prim_ids = bvh.arrays()
+    tree = oracle.from_arrays(bounds, index_values, prim_ids)
+    oracle.set_triangles(tree, tris)
+    want = oracle.trace(tree, rays[sample], flags=O_ANY | O_LOWEST)
+    assert_hits_equal(hits_tuple(occl[sample]), want, "incoherent any-hit sample")
+
+
+def test_double_precision_config5(gpu_lib, oracle):
+    """BASELINE config 5: Node<double,3>, 100K triangles, 1M rays, exact against the oracle."""
+    api = gpu_lib
+    tris = scenes.soup(100_000, dtype=np.float64)
+    bvh = api.Bvh.build_triangles(tris)
+    rays = scenes.make_primary("soup", 1000, 1000, dtype=np.float64)
+    hits = bvh.intersect_rays(rays)
+    bounds, index_values, prim_ids = bvh.arrays()
+    tree = oracle.from_arrays(bounds, index_values, prim_ids)
+    assert oracle.check_invariants(tree, 8) == 0
+    oracle.set_triangles(tree, tris)
+    sample = np.arange(0, rays.shape[0], 25)
+    want = oracle.trace(tree, rays[sample], flags=O_LOWEST)
+    assert_hits_equal(hits_tuple(hits[sample]), want, "double")
+    simple = bvh.intersect_rays(rays, flags=api.KERNEL_SIMPLE)
+    assert (simple.view(np.uint8) == hits.view(np.uint8)).all()

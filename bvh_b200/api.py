@@ -57,6 +57,7 @@ def lib() -> C.CDLL:
     L.bvh_cuda_device_count.restype = C.c_int
     L.bvh_cuda_set_device.argtypes = [C.c_int]
     L.bvh_cuda_set_stream.argtypes = [P]
+    L.bvh_cuda_reset_stream.argtypes = []
     L.bvh_host_alloc.restype = P
     L.bvh_host_alloc.argtypes = [SZ]
     L.bvh_host_free.argtypes = [P]
@@ -121,9 +122,12 @@ def set_device(device: int) -> None:
 
 
 def set_stream(cuda_stream: int | None) -> None:
-    """Use a caller-owned CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``) for handles
-    created from now on; ``None`` restores one private stream per handle."""
-    lib().bvh_cuda_set_stream(C.c_void_p(cuda_stream) if cuda_stream else None)
+    """Use a caller-owned CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``; 0 is the legacy
+    default stream) for handles created from now on; ``None`` restores one private stream per handle."""
+    if cuda_stream is None:
+        lib().bvh_cuda_reset_stream()
+    else:
+        lib().bvh_cuda_set_stream(C.c_void_p(int(cuda_stream)))
 
 
 def _sfx(dtype) -> str:

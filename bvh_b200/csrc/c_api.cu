@@ -69,8 +69,12 @@ template <typename T> struct Handle {
     bool host_valid = false;
     bool maybe_edited = false;                // a mutable node pointer was handed out since the last upload
     uint64_t synced_hash = 0;
+    uint64_t synced_ids_hash = 0;             // hash of prim_ids the device triangles were permuted with
 
-    // staging for host-pointer batches
+    // staging and side streams for host-pointer batches
+    static constexpr size_t kMaxChunks = 16;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t events[1 + 2 * kMaxChunks] = {};
     void* d_rays = nullptr; size_t d_rays_bytes = 0;
     void* d_hits = nullptr; size_t d_hits_bytes = 0;
     void* d_stats = nullptr; size_t d_stats_bytes = 0;
@@ -91,6 +95,10 @@ template <typename T> void destroy_handle(Handle<T>* h) {
     release(h->dev, h->stream);
     device_free(h->d_rays, h->stream); device_free(h->d_hits, h->stream); device_free(h->d_stats, h->stream);
     cudaStreamSynchronize(h->stream);
+    if (h->copy_in) {
+        cudaStreamDestroy(h->copy_in); cudaStreamDestroy(h->copy_out);
+        for (auto& e : h->events) if (e) cudaEventDestroy(e);
+    }
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -103,6 +111,10 @@ static uint64_t hash_bytes(const void* data, size_t size, uint64_t seed) {
     for (size_t i = 0; i < words; ++i) { uint64_t w; std::memcpy(&w, p + 8 * i, 8); h = (h ^ w) * 1099511628211ull; }
     for (size_t i = words * 8; i < size; ++i) h = (h ^ p[i]) * 1099511628211ull;
     return h;
+}
+
+template <typename T> uint64_t ids_hash(const Handle<T>& h) {
+    return hash_bytes(h.prim_ids.data(), h.prim_ids.size() * sizeof(size_t), h.prim_ids.size());
 }
 
 template <typename T> uint64_t mirror_hash(const Handle<T>& h) {
@@ -152,6 +164,7 @@ template <typename T> int download_mirror(Handle<T>& h) {
     h.prim_ids.assign(dev_ids.begin(), dev_ids.end());
     h.host_valid = true;
     h.maybe_edited = false;
+    h.synced_ids_hash = ids_hash(h);
     return 0;
 }
 
@@ -207,6 +220,7 @@ template <typename T> int upload_mirror(Handle<T>& h) {
     h.device_valid = true;
     h.maybe_edited = false;
     h.synced_hash = mirror_hash(h);
+    h.synced_ids_hash = ids_hash(h);
     return 0;
 }
 
@@ -215,8 +229,8 @@ template <typename T> int ensure_device(Handle<T>& h) {
     if (h.device_valid && !(h.host_valid && h.maybe_edited)) return 0;
     if (!h.host_valid) { set_error("handle holds no BVH"); return -1; }
     if (h.device_valid && mirror_hash(h) == h.synced_hash) { h.maybe_edited = false; return 0; }
-    // prim ids may have been permuted by an edit: triangles would be stale
-    if (h.device_valid && h.dev.tris) { device_free(h.dev.tris, h.stream); h.dev.tris = nullptr; }
+    // if the primitive order was edited the BVH-order triangles are stale: drop them
+    if (h.device_valid && h.dev.tris && ids_hash(h) != h.synced_ids_hash) { device_free(h.dev.tris, h.stream); h.dev.tris = nullptr; }
     return upload_mirror(h);
 }
 
@@ -359,17 +373,40 @@ int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bv
         return trace_rays<T>(h->dev, reinterpret_cast<const DevRay<T>*>(rays), reinterpret_cast<DevHit<T>*>(hits), n, tf,
                              reinterpret_cast<uint32_t*>(stats), h->stream);
     }
-    // Host buffers: H2D, trace, D2H on the handle's stream.
+    // Host buffers: the batch is cut into chunks and software-pipelined over three streams — H2D of
+    // chunk k+1 (copy-in stream), traversal of chunk k (the handle's stream) and D2H of chunk k-1
+    // (copy-out stream) overlap, so a PCIe-bound call costs about max(H2D, trace, D2H), not their sum.
     if (ensure_staging(*h, &h->d_rays, &h->d_rays_bytes, n * sizeof(RayPod))) return -1;
     if (ensure_staging(*h, &h->d_hits, &h->d_hits_bytes, n * sizeof(HitPod))) return -1;
     if (stats && ensure_staging(*h, &h->d_stats, &h->d_stats_bytes, n * sizeof(bvh_ray_stats))) return -1;
+    if (!h->copy_in) {
+        BVH_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+        BVH_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+        for (auto& e : h->events) BVH_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     auto d_rays = static_cast<DevRay<T>*>(h->d_rays);
     auto d_hits = static_cast<DevHit<T>*>(h->d_hits);
     auto d_stats = static_cast<uint32_t*>(h->d_stats);
-    BVH_CUDA_TRY(cudaMemcpyAsync(d_rays, rays, n * sizeof(RayPod), cudaMemcpyHostToDevice, h->stream));
-    if (trace_rays<T>(h->dev, d_rays, d_hits, n, tf, stats ? d_stats : nullptr, h->stream)) return -1;
-    BVH_CUDA_TRY(cudaMemcpyAsync(hits, d_hits, n * sizeof(HitPod), cudaMemcpyDeviceToHost, h->stream));
-    if (stats) BVH_CUDA_TRY(cudaMemcpyAsync(stats, d_stats, n * sizeof(bvh_ray_stats), cudaMemcpyDeviceToHost, h->stream));
+    constexpr size_t kMinChunk = 1u << 18;                   // 256K rays = 8 MB of float rays
+    size_t chunks = n / kMinChunk;
+    if (chunks < 1) chunks = 1;
+    if (chunks > Handle<T>::kMaxChunks) chunks = Handle<T>::kMaxChunks;
+    // the staging buffers may still be in use by earlier work on the handle's stream
+    BVH_CUDA_TRY(cudaEventRecord(h->events[0], h->stream));
+    BVH_CUDA_TRY(cudaStreamWaitEvent(h->copy_in, h->events[0], 0));
+    for (size_t c = 0; c < chunks; ++c) {
+        const size_t b = n * c / chunks, e = n * (c + 1) / chunks;
+        cudaEvent_t in_done = h->events[1 + 2 * c], tr_done = h->events[2 + 2 * c];
+        BVH_CUDA_TRY(cudaMemcpyAsync(d_rays + b, rays + b, (e - b) * sizeof(RayPod), cudaMemcpyHostToDevice, h->copy_in));
+        BVH_CUDA_TRY(cudaEventRecord(in_done, h->copy_in));
+        BVH_CUDA_TRY(cudaStreamWaitEvent(h->stream, in_done, 0));
+        if (trace_rays<T>(h->dev, d_rays + b, d_hits + b, e - b, tf, stats ? d_stats + 3 * b : nullptr, h->stream)) return -1;
+        BVH_CUDA_TRY(cudaEventRecord(tr_done, h->stream));
+        BVH_CUDA_TRY(cudaStreamWaitEvent(h->copy_out, tr_done, 0));
+        BVH_CUDA_TRY(cudaMemcpyAsync(hits + b, d_hits + b, (e - b) * sizeof(HitPod), cudaMemcpyDeviceToHost, h->copy_out));
+        if (stats) BVH_CUDA_TRY(cudaMemcpyAsync(stats + b, d_stats + 3 * b, (e - b) * sizeof(bvh_ray_stats), cudaMemcpyDeviceToHost, h->copy_out));
+    }
+    BVH_CUDA_TRY(cudaStreamSynchronize(h->copy_out));
     BVH_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -424,8 +461,9 @@ BVH_EXPORT int bvh_cuda_set_device(int device) {
 }
 BVH_EXPORT void bvh_cuda_set_stream(void* cuda_stream) {
     g_user_stream = static_cast<cudaStream_t>(cuda_stream);
-    g_have_user_stream = cuda_stream != nullptr;
+    g_have_user_stream = true;
 }
+BVH_EXPORT void bvh_cuda_reset_stream(void) { g_user_stream = nullptr; g_have_user_stream = false; }
 BVH_EXPORT void* bvh_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) { set_error("cudaMallocHost failed"); cudaGetLastError(); return nullptr; }

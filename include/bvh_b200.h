@@ -59,9 +59,12 @@ BVH_API const char* bvh_last_error(void);
 BVH_API int bvh_cuda_device_count(void);
 /* Device used by subsequent bvhNN_build* calls on this thread (default 0). */
 BVH_API int bvh_cuda_set_device(int device);
-/* CUDA stream (cudaStream_t) used by handles created afterwards on this thread; NULL = a private
- * non-blocking stream per handle.  Lets a host framework keep everything on its current stream. */
+/* By default every handle owns a private non-blocking stream.  bvh_cuda_set_stream makes handles
+ * created afterwards on this thread use the caller's stream instead (a cudaStream_t; NULL is the legacy
+ * default stream), which lets a host framework keep all work ordered on its current stream;
+ * bvh_cuda_reset_stream goes back to private streams. */
 BVH_API void bvh_cuda_set_stream(void* cuda_stream);
+BVH_API void bvh_cuda_reset_stream(void);
 /* Pinned host memory for ray / hit buffers (so that host<->device copies run at PCIe speed). */
 BVH_API void* bvh_host_alloc(size_t bytes);
 BVH_API void bvh_host_free(void* ptr);

@@ -21,6 +21,7 @@ ROBUST = 1 << 1
 TIE_LAST_VISITED = 1 << 2
 DEVICE_POINTERS = 1 << 3
 KERNEL_SIMPLE = 1 << 8
+KERNEL_NO_TMA = 1 << 9
 INVALID_ID = 0xFFFFFFFF
 
 QUALITY = {"low": 0, "medium": 1, "high": 2}

@@ -211,6 +211,26 @@ template <typename T, bool kRobust> BVH_HD void ray_prologue(RayCtx<T>& r) {
     }
 }
 
+// Accumulation step of make_intersection_result (node.h:105-117): t0 = robust_max(tn, t0),
+// t1 = robust_min(tf, t1), i.e. `tn > t0 ? tn : t0` — the accumulator comes back when tn is a NaN.
+// On the device this is one FMNMX: fmaxf/fminf also return the non-NaN operand, the accumulator
+// itself is never a NaN (rays whose tmin/tmax is a NaN are retired as misses before traversal, which
+// is what the reference's comparisons do with them), and the only other difference — which zero comes
+// back when the operands are +0 and -0 — cannot change `t0 <= t1` or `t0L > t0R`, the only uses.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float acc_max(float tn, float t0) { return fmaxf(tn, t0); }
+__device__ __forceinline__ float acc_min(float tf, float t1) { return fminf(tf, t1); }
+__device__ __forceinline__ double acc_max(double tn, double t0) { return fmax(tn, t0); }
+__device__ __forceinline__ double acc_min(double tf, double t1) { return fmin(tf, t1); }
+#else
+template <typename T> inline T acc_max(T tn, T t0) { return robust_max(tn, t0); }
+template <typename T> inline T acc_min(T tf, T t1) { return robust_min(tf, t1); }
+#endif
+
+// A ray with a NaN interval can never report a hit in the reference (every comparison against
+// tmin/tmax fails: node.h:110-115, tri.h:69); callers retire it as a miss without traversing.
+template <typename T> BVH_HD bool ray_interval_is_nan(const RayCtx<T>& r) { return r.tmin != r.tmin || r.tmax != r.tmax; }
+
 // reference node.h:68-88 + make_intersection_result (:105-117).  b = [minx,maxx,miny,maxy,minz,maxz]
 template <typename T, bool kRobust> BVH_HD void node_test(const T b[6], const RayCtx<T>& r, T& t0, T& t1) {
     using R = Real<T>;
@@ -227,8 +247,8 @@ template <typename T, bool kRobust> BVH_HD void node_test(const T b[6], const Ra
             tn = R::fma(bnear, r.inv_dir[i], r.aux[i]);      // fast_mul_add is std::fma (utils.h:75-76)
             tf = R::fma(bfar,  r.inv_dir[i], r.aux[i]);
         }
-        t0 = robust_max(tn, t0);
-        t1 = robust_min(tf, t1);
+        t0 = acc_max(tn, t0);
+        t1 = acc_min(tf, t1);
     }
 }
 

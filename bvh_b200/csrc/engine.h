@@ -69,6 +69,7 @@ enum TraceFlags : unsigned {
     kTraceRobust      = 1u << 1,
     kTraceLastVisited = 1u << 2,   // reference example tie semantics instead of the canonical lowest id
     kTraceSimple      = 1u << 8,   // one-thread-per-ray kernel instead of the persistent one
+    kTraceNoTma       = 1u << 9,   // persistent kernel without the bulk-copy ray staging
 };
 
 // Batched traversal; all pointers are device pointers.  ray_stats (nullable): n x 3 uint32

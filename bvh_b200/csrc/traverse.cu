@@ -17,6 +17,8 @@
 //
 // Both kernels execute the reference's per-ray algorithm exactly (traverse_core.cuh), so on the same
 // tree they visit nodes in the same order as the CPU code and produce bit-identical ids, t, u, v.
+#include <cstdlib>
+
 #include "engine.h"
 #include "traverse_core.cuh"
 
@@ -84,6 +86,8 @@ template <typename T> struct TraceArgs {
     unsigned long long* next_ray;     // persistent kernel: global ray cursor
     uint32_t* ray_stats;              // statistics variant: n x 3
     uint32_t stack_entries;
+    bool use_tma;                     // persistent kernel: stage ray chunks with cp.async.bulk
+    uint32_t inner_budget;            // persistent kernel: inner steps per lane per round (0xFFFFFFFF = unbounded)
     int lowest_id;
 };
 
@@ -112,21 +116,101 @@ trace_simple_kernel(TraceArgs<T> a) {
     }
 }
 
-template <typename T, bool kAny, bool kRobust>
+// ---- TMA (bulk async copy) helpers for the ray-chunk prefetch ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void read_ray_smem(const DevRay<float>* p, RayCtx<float>& r) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+    const float4 a = q[0], b = q[1];
+    r.org[0] = a.x; r.org[1] = a.y; r.org[2] = a.z; r.dir[0] = a.w;
+    r.dir[1] = b.x; r.dir[2] = b.y; r.tmin = b.z; r.tmax = b.w;
+}
+__device__ __forceinline__ void read_ray_smem(const DevRay<double>* p, RayCtx<double>& r) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = q[0], b = q[1], c = q[2], d = q[3];
+    r.org[0] = a.x; r.org[1] = a.y; r.org[2] = b.x; r.dir[0] = b.y;
+    r.dir[1] = c.x; r.dir[2] = c.y; r.tmin = d.x; r.tmax = d.y;
+}
+
+constexpr int kTmaChunkRays = 64;        // rays per bulk copy (2 KB of float rays), two buffers per warp
+
+template <typename T> __host__ __device__ constexpr size_t tma_smem_bytes() {
+    return (size_t)(kTraceBlock / 32) * 2 * kTmaChunkRays * sizeof(DevRay<T>) + (size_t)(kTraceBlock / 32) * 2 * 8;
+}
+
+// Persistent kernel.  kTma = true stages the warp's next ray chunk into shared memory with a bulk
+// asynchronous copy (cp.async.bulk, SASS UBLKCP) signalled through an mbarrier, double-buffered, so
+// that the ray fetch of the refill path never waits on DRAM; kTma = false reads rays with streaming
+// 128-bit loads.
+template <typename T, bool kAny, bool kRobust, bool kTma>
 __global__ void __launch_bounds__(kTraceBlock)
 trace_persistent_kernel(TraceArgs<T> a) {
     using U = typename Real<T>::UInt;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr unsigned kFull = 0xFFFFFFFFu;
-    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     SmemStack<U> stack { reinterpret_cast<U*>(smem_raw) + threadIdx.x, kTraceBlock, 0 };
     const bool lowest_id = a.lowest_id != 0;
     const U root_index = a.nodes[1].index;
+    const uint32_t inner_budget = a.inner_budget;
 
-    // warp-uniform cursor over the warp's private chunk of rays
-    unsigned long long chunk_pos = 0, chunk_end = 0;
+    // warp-uniform cursor over the warp's private chunk(s) of rays
+    unsigned long long chunk_pos = 0, chunk_end = 0;           // !kTma: global ray indices
     bool exhausted = false;
+    // kTma state (warp-uniform)
+    // (kept as scalars selected by `cur`, not arrays, so that nothing is spilled to local memory)
+    DevRay<T>* ray_buf0 = nullptr; DevRay<T>* ray_buf1 = nullptr;
+    uint32_t bar0 = 0, bar1 = 0, phase0 = 0, phase1 = 0, count0 = 0, count1 = 0;
+    unsigned long long base0 = 0, base1 = 0;
+    uint32_t cur = 0, buf_pos = 0;
+
+    auto prefetch = [&] (uint32_t b) {      // claim the next chunk and start its bulk copy into buffer b
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.next_ray, (unsigned long long)kTmaChunkRays);
+        base = __shfl_sync(kFull, base, 0);
+        uint32_t cnt = 0;
+        if (base < a.n) cnt = (uint32_t)(base + kTmaChunkRays < a.n ? kTmaChunkRays : a.n - base);
+        if (b == 0) { count0 = cnt; base0 = base; } else { count1 = cnt; base1 = base; }
+        if (cnt != 0 && lane == 0) {
+            const uint32_t bar = b == 0 ? bar0 : bar1;
+            fence_proxy_async_smem();       // earlier generic reads of this buffer happen-before the async write
+            mbar_arrive_expect_tx(bar, cnt * (uint32_t)sizeof(DevRay<T>));
+            bulk_copy_g2s(smem_u32(b == 0 ? ray_buf0 : ray_buf1), a.rays + base, cnt * (uint32_t)sizeof(DevRay<T>), bar);
+        }
+    };
+
+    if (kTma) {
+        unsigned char* tma_base = smem_raw + (size_t)a.stack_entries * kTraceBlock * sizeof(U);
+        DevRay<T>* bufs = reinterpret_cast<DevRay<T>*>(tma_base);
+        uint64_t* bars = reinterpret_cast<uint64_t*>(tma_base + (size_t)(kTraceBlock / 32) * 2 * kTmaChunkRays * sizeof(DevRay<T>));
+        ray_buf0 = bufs + ((size_t)warp * 2 + 0) * kTmaChunkRays;
+        ray_buf1 = bufs + ((size_t)warp * 2 + 1) * kTmaChunkRays;
+        bar0 = smem_u32(bars + warp * 2 + 0);
+        bar1 = smem_u32(bars + warp * 2 + 1);
+        if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); fence_mbar_init(); fence_proxy_async_smem(); }
+        __syncwarp();
+        prefetch(0);
+        prefetch(1);
+    }
 
     bool has_ray = false;
     unsigned long long ray_index = 0;
@@ -139,36 +223,70 @@ trace_persistent_kernel(TraceArgs<T> a) {
         // ---- refill idle lanes from the private chunk (claiming a new chunk when it runs dry) ----
         unsigned idle = __ballot_sync(kFull, !has_ray);
         while (idle != 0u && !exhausted) {
-            if (chunk_pos == chunk_end) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(a.next_ray, (unsigned long long)kChunkRays);
-                base = __shfl_sync(kFull, base, 0);
-                if (base >= a.n) { exhausted = true; break; }
-                chunk_pos = base;
-                chunk_end = base + kChunkRays < a.n ? base + kChunkRays : a.n;
+            unsigned take, rank = __popc(idle & lt_mask);
+            bool got = false;
+            if (kTma) {
+                const uint32_t cur_count = cur == 0 ? count0 : count1;
+                if (cur_count == 0) { exhausted = true; break; }
+                const uint32_t cur_bar = cur == 0 ? bar0 : bar1, cur_phase = cur == 0 ? phase0 : phase1;
+                while (!mbar_try_wait(cur_bar, cur_phase)) { }
+                const unsigned avail = cur_count - buf_pos, want = __popc(idle);
+                take = want < avail ? want : avail;
+                if (!has_ray && rank < take) {
+                    ray_index = (cur == 0 ? base0 : base1) + buf_pos + rank;
+                    read_ray_smem((cur == 0 ? ray_buf0 : ray_buf1) + buf_pos + rank, r);
+                    got = true;
+                }
+                buf_pos += take;
+                if (buf_pos == cur_count) {                // buffer drained: re-arm it with the next chunk
+                    __syncwarp();
+                    if (cur == 0) phase0 ^= 1u; else phase1 ^= 1u;
+                    prefetch(cur);
+                    cur ^= 1u; buf_pos = 0;
+                }
+            } else {
+                if (chunk_pos == chunk_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(a.next_ray, (unsigned long long)kChunkRays);
+                    base = __shfl_sync(kFull, base, 0);
+                    if (base >= a.n) { exhausted = true; break; }
+                    chunk_pos = base;
+                    chunk_end = base + kChunkRays < a.n ? base + kChunkRays : a.n;
+                }
+                const unsigned avail = (unsigned)(chunk_end - chunk_pos), want = __popc(idle);
+                take = want < avail ? want : avail;
+                if (!has_ray && rank < take) {
+                    ray_index = chunk_pos + rank;
+                    load_ray(a.rays, ray_index, r);
+                    got = true;
+                }
+                chunk_pos += take;
             }
-            const unsigned avail = (unsigned)(chunk_end - chunk_pos);
-            const unsigned want = __popc(idle);
-            const unsigned take = want < avail ? want : avail;
-            const unsigned rank = __popc(idle & lt_mask);
-            if (!has_ray && rank < take) {
-                ray_index = chunk_pos + rank;
-                load_ray(a.rays, ray_index, r);
-                ray_prologue<T, kRobust>(r);
+            if (got) {
                 tmax_in = r.tmax;
                 hit.slot = kInvalidId; hit.t = r.tmax; hit.u = (T)0; hit.v = (T)0;
-                top = root_index;
-                stack.sp = 0;
-                has_ray = true;
+                if (ray_interval_is_nan(r)) {
+                    store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);     // can never hit: retire as a miss
+                } else {
+                    ray_prologue<T, kRobust>(r);
+                    top = root_index;
+                    stack.sp = 0;
+                    has_ray = true;
+                }
             }
-            chunk_pos += take;
             idle = __ballot_sync(kFull, !has_ray);
         }
-        if (__ballot_sync(kFull, has_ray) == 0u) break;      // nothing in flight and nothing left
+        if (__ballot_sync(kFull, has_ray) == 0u) {
+            if (exhausted) break;                            // nothing in flight and nothing left
+            continue;                                        // (only NaN rays were drawn: refill again)
+        }
 
-        // ---- inner phase: descend until this lane holds a leaf (or its ray is finished) ----------
+        // ---- inner phase: descend until this lane holds a leaf, its ray is finished, or the step
+        //      budget of this round is spent (bounding the wait of lanes that already hold a leaf) ----
         if (has_ray) {
-            while (index_count(top) == 0) {
+            uint32_t budget = inner_budget;
+            while (index_count(top) == 0 && budget != 0) {
+                --budget;
                 if (!inner_step<T, kAny, kRobust>(a.nodes, r, top, stack)) { has_ray = false; break; }
             }
             if (!has_ray) store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
@@ -176,7 +294,7 @@ trace_persistent_kernel(TraceArgs<T> a) {
         __syncwarp();
 
         // ---- leaf phase ---------------------------------------------------------------------------
-        if (has_ray) {
+        if (has_ray && index_count(top) != 0) {
             leaf_step<T>(a.tris, a.prim_ids, lowest_id, top, r, hit, nullptr);
             if ((kAny && hit.slot != kInvalidId) || stack.empty()) {
                 store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
@@ -187,6 +305,18 @@ trace_persistent_kernel(TraceArgs<T> a) {
         }
         __syncwarp();
     }
+}
+
+// Tunables of the persistent kernel; environment overrides exist for experiments only.
+struct Tuning { uint32_t inner_budget; bool use_tma; };
+const Tuning& tuning() {
+    static const Tuning t = [] {
+        Tuning v { 8u, true };
+        if (const char* e = getenv("BVH_B200_INNER_BUDGET")) { long k = atol(e); v.inner_budget = k <= 0 ? 0xFFFFFFFFu : (uint32_t)k; }
+        if (const char* e = getenv("BVH_B200_TMA")) v.use_tma = atoi(e) != 0;
+        return v;
+    }();
+    return t;
 }
 
 template <typename KernelT>
@@ -212,17 +342,19 @@ int launch(const TraceArgs<T>& args, bool simple, bool stats, int device, cudaSt
             trace_simple_kernel<T, kAny, kRobust, false><<<(unsigned)blocks, kTraceBlock, smem, stream>>>(args);
         }
     } else {
-        auto kernel = trace_persistent_kernel<T, kAny, kRobust>;
-        if (configure_smem(kernel, smem)) return -1;
+        const bool tma = args.use_tma;
+        auto kernel = tma ? trace_persistent_kernel<T, kAny, kRobust, true> : trace_persistent_kernel<T, kAny, kRobust, false>;
+        const size_t total_smem = smem + (tma ? tma_smem_bytes<T>() : 0);
+        if (configure_smem(kernel, total_smem)) return -1;
         int sm_count = 148, per_sm = 1;
         BVH_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
-        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceBlock, smem));
+        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceBlock, total_smem));
         if (per_sm < 1) per_sm = 1;
         unsigned long long grid = (unsigned long long)sm_count * per_sm;      // one resident wave
         const unsigned long long max_useful = (args.n + 31) / 32 / (kTraceBlock / 32) + 1;
         if (grid > max_useful) grid = max_useful;
         BVH_CUDA_TRY(cudaMemsetAsync(args.next_ray, 0, sizeof(unsigned long long), stream));
-        kernel<<<(unsigned)grid, kTraceBlock, smem, stream>>>(args);
+        kernel<<<(unsigned)grid, kTraceBlock, total_smem, stream>>>(args);
     }
     BVH_CUDA_TRY(cudaGetLastError());
     return 0;
@@ -245,6 +377,8 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     if (entries < 16) entries = 16;
     args.stack_entries = entries;
     args.next_ray = nullptr;
+    args.inner_budget = tuning().inner_budget;
+    args.use_tma = (flags & kTraceNoTma) ? false : tuning().use_tma;
     const bool simple = (flags & kTraceSimple) != 0, stats = d_ray_stats != nullptr;
     void* cursor = nullptr;
     if (!simple && !stats) {

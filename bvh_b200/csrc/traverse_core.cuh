@@ -22,26 +22,33 @@ template <typename T> struct NodePair {
 };
 
 #if defined(__CUDA_ARCH__)
-// float: one 64-byte aligned pair = 4 x 128-bit loads through the read-only path
-__device__ __forceinline__ void load_pair(const DevNode<float>* __restrict__ p, NodePair<float>& o) {
-    const float4* q = reinterpret_cast<const float4*>(p);
-    const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
-    o.lb[0] = a.x; o.lb[1] = a.y; o.lb[2] = a.z; o.lb[3] = a.w; o.lb[4] = b.x; o.lb[5] = b.y;
-    o.li = __float_as_uint(b.z);
-    o.rb[0] = c.x; o.rb[1] = c.y; o.rb[2] = c.z; o.rb[3] = c.w; o.rb[4] = d.x; o.rb[5] = d.y;
-    o.ri = __float_as_uint(d.z);
+// sm_100 has 256-bit global loads (SASS LDG.E.256): a node is ONE load, a sibling pair two, from one
+// naturally aligned 64-byte (float) / 128-byte (double) block, through the read-only path.  Halving the
+// number of load instructions matters because with divergent rays every load costs one L1 tag lookup per
+// distinct line touched by the warp (profiles/: the traversal is L1-tag bound, not DRAM bound).
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&w)[8]) {
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
 }
-// double: one 128-byte aligned pair = 8 x 128-bit loads (the 4th and 8th carry index + pad)
+__device__ __forceinline__ void ldg256(const void* p, unsigned long long (&w)[4]) {
+    asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(p));
+}
+__device__ __forceinline__ void load_pair(const DevNode<float>* __restrict__ p, NodePair<float>& o) {
+    uint32_t a[8], b[8];
+    ldg256(p, a);
+    ldg256(p + 1, b);
+    #pragma unroll
+    for (int k = 0; k < 6; ++k) { o.lb[k] = __uint_as_float(a[k]); o.rb[k] = __uint_as_float(b[k]); }
+    o.li = a[6]; o.ri = b[6];
+}
 __device__ __forceinline__ void load_pair(const DevNode<double>* __restrict__ p, NodePair<double>& o) {
-    const double2* q = reinterpret_cast<const double2*>(p);
-    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    const ulonglong2 ai = __ldg(reinterpret_cast<const ulonglong2*>(q + 3));
-    const double2 d = __ldg(q + 4), e = __ldg(q + 5), f = __ldg(q + 6);
-    const ulonglong2 di = __ldg(reinterpret_cast<const ulonglong2*>(q + 7));
-    o.lb[0] = a.x; o.lb[1] = a.y; o.lb[2] = b.x; o.lb[3] = b.y; o.lb[4] = c.x; o.lb[5] = c.y;
-    o.li = ai.x;
-    o.rb[0] = d.x; o.rb[1] = d.y; o.rb[2] = e.x; o.rb[3] = e.y; o.rb[4] = f.x; o.rb[5] = f.y;
-    o.ri = di.x;
+    unsigned long long a[4], b[4], c[4], d[4];
+    const unsigned char* q = reinterpret_cast<const unsigned char*>(p);
+    ldg256(q, a); ldg256(q + 32, b); ldg256(q + 64, c); ldg256(q + 96, d);
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) { o.lb[k] = __longlong_as_double((long long)a[k]); o.rb[k] = __longlong_as_double((long long)c[k]); }
+    o.lb[4] = __longlong_as_double((long long)b[0]); o.lb[5] = __longlong_as_double((long long)b[1]); o.li = b[2];
+    o.rb[4] = __longlong_as_double((long long)d[0]); o.rb[5] = __longlong_as_double((long long)d[1]); o.ri = d[2];
 }
 __device__ __forceinline__ void load_tri(const DevTri<float>* __restrict__ p, DevTri<float>& o) {
     const float4* q = reinterpret_cast<const float4*>(p);
@@ -112,6 +119,7 @@ template <typename T, bool kAny, bool kRobust, typename Stack>
 BVH_HD void traverse_ray(const DevNode<T>* __restrict__ nodes, const DevTri<T>* __restrict__ tris,
                          const uint32_t* __restrict__ prim_ids, bool lowest_id, typename Real<T>::UInt root_index,
                          RayCtx<T>& r, HitState<T>& hit, Stack& stack, uint32_t* stats) {
+    if (ray_interval_is_nan(r)) return;                         // can never hit (node.h:110-115, tri.h:69)
     typename Real<T>::UInt top = root_index;                    // get_root().index, bvh.h:54
     for (;;) {
         bool alive = true;

@@ -51,7 +51,8 @@ enum bvh_intersect_flags {
                                         leaf loops (tri.h:69 `t <= tmax`); default is the tree-independent
                                         rule "lowest original primitive id wins" */
     BVH_DEVICE_POINTERS  = 1u << 3,  /* rays/hits/vertices are device pointers; the call is stream-ordered */
-    BVH_KERNEL_SIMPLE    = 1u << 8   /* one-thread-per-ray kernel instead of the persistent one (diagnostics) */
+    BVH_KERNEL_SIMPLE    = 1u << 8,  /* one-thread-per-ray kernel instead of the persistent one (diagnostics) */
+    BVH_KERNEL_NO_TMA    = 1u << 9   /* persistent kernel without the bulk-copy (TMA) staging of ray chunks (diagnostics) */
 };
 
 /* ---- runtime ------------------------------------------------------------------------------- */

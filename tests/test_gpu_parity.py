@@ -31,7 +31,7 @@ def test_lbvh_vs_reference_golden(gpu_lib, name):
     api = gpu_lib
     g = golden(name)
     bvh = api.Bvh.build_triangles(g["tris"])
-    for kernel in (0, api.KERNEL_SIMPLE):
+    for kernel in (0, api.KERNEL_NO_TMA, api.KERNEL_SIMPLE):
         hits = bvh.intersect_rays(g["rays"], flags=kernel)
         assert_hits_equal(hits_tuple(hits), tuple(g[f"lowest_{k}"] for k in ("ids", "t", "u", "v")), f"{name}/closest/{kernel}")
         hits = bvh.intersect_rays(g["rays"], flags=kernel | api.ROBUST)
@@ -63,8 +63,9 @@ def test_reference_tree_on_gpu(gpu_lib, name):
             assert_hits_equal(hits_tuple(hits), tuple(g[f"{mode}_{k}"] for k in ("ids", "t", "u", "v")), f"{name}/{mode}")
             want = g[f"{mode}_stats"]
             assert (st["inner_steps"] == want[:, 0]).all() and (st["leaves"] == want[:, 1]).all() and (st["prim_tests"] == want[:, 2]).all()
-            hits2 = bvh.intersect_rays(g["rays"], flags=flags)          # persistent kernel, same answers
-            assert_hits_equal(hits_tuple(hits2), hits_tuple(hits), f"{name}/{mode}/persistent")
+            for variant in (0, api.KERNEL_NO_TMA):                      # persistent kernels, same answers
+                hits2 = bvh.intersect_rays(g["rays"], flags=flags | variant)
+                assert_hits_equal(hits_tuple(hits2), hits_tuple(hits), f"{name}/{mode}/persistent/{variant}")
         # save -> byte-identical file
         out = os.path.join(tmp, "out.bvh")
         bvh.save(out)
@@ -141,6 +142,36 @@ def test_ragged_ray_counts(gpu_lib, m):
     hits = bvh.intersect_rays(rays) if m else bvh.intersect_rays(np.zeros((0, 8), np.float32))
     assert hits.shape[0] == m
     assert_hits_equal(hits_tuple(hits), tuple(g[f"lowest_{k}"][:m] for k in ("ids", "t", "u", "v")), f"m={m}")
+
+
+def test_nan_and_degenerate_rays(gpu_lib, oracle):
+    """NaN tmin/tmax (never hit in the reference: every comparison fails), zero directions, inverted and
+    empty intervals, infinite tmax — against the oracle traversing the same tree."""
+    api = gpu_lib
+    tris = scenes.soup(3000)
+    bvh = api.Bvh.build_triangles(tris)
+    rays = scenes.make_primary("soup", 40, 40).copy()
+    nan, inf = np.float32(np.nan), np.float32(np.inf)
+    rays[0::10, 6] = nan
+    rays[1::10, 7] = nan
+    rays[2::10, 3:6] = 0
+    rays[3::10, 6], rays[3::10, 7] = 1.0, 0.5
+    rays[4::10, 7] = inf
+    rays[5::10, 6] = rays[5::10, 7] = 0.75
+    rays[6::10, 3] = 0
+    rays[7::10, 3:5] = 0
+    bounds, index_values, prim_ids = bvh.arrays()
+    tree = oracle.from_arrays(bounds, index_values, prim_ids)
+    oracle.set_triangles(tree, tris)
+    for mode, oflags, flags in modes(api):
+        want = oracle.trace(tree, rays, flags=oflags)
+        for variant in (0, api.KERNEL_NO_TMA, api.KERNEL_SIMPLE):
+            got = hits_tuple(bvh.intersect_rays(rays, flags=flags | variant))
+            nan_rays = np.isnan(rays[:, 7])
+            assert (got[0] == want[0]).all()
+            ok = ~nan_rays
+            assert_hits_equal(tuple(x[ok] for x in got), tuple(x[ok] for x in want), f"{mode}/{variant}")
+            assert np.isnan(got[1][nan_rays]).all()           # a miss reports the ray's own tmax
 
 
 def test_duplicates_degenerates_and_leaf_config(gpu_lib, oracle):
@@ -251,9 +282,10 @@ def test_full_size_properties(gpu_lib, oracle, kind):
     assert (ids[hit] < n).all()
     assert (hits["t"][~hit] == rays[~hit, 7]).all() and (hits["t"][hit] > 0).all()
     assert (hits["u"][hit] >= -1e-6).all() and (hits["v"][hit] >= -1e-6).all() and ((hits["u"] + hits["v"])[hit] <= 1 + 1e-5).all()
-    # both kernels agree exactly
-    simple = bvh.intersect_rays(rays, flags=api.KERNEL_SIMPLE)
-    assert (simple.view(np.uint8) == hits.view(np.uint8)).all()
+    # all kernels agree exactly
+    for variant in (api.KERNEL_SIMPLE, api.KERNEL_NO_TMA):
+        other = bvh.intersect_rays(rays, flags=variant)
+        assert (other.view(np.uint8) == hits.view(np.uint8)).all()
     # nothing lies in front of a reported closest hit: re-trace with tmax just below t as any-hit
     sel = np.nonzero(hit)[0][:: max(1, int(hit.sum()) // 200_000)]
     shortened = rays[sel].copy()

@@ -121,6 +121,27 @@ def test_axis_parallel_rays(emul, oracle):
     assert_hits_equal(emul.trace(tree, rays, ROBUST | TIE_LOWEST_ID)[:4], oracle.brute_force(tris, rays), "axis-parallel brute force")
 
 
+def test_nan_and_degenerate_rays(emul, oracle):
+    tris = scenes.soup(2000)
+    tree = emul.build(tris=tris)
+    bounds, index_values = emul.compact(tree)
+    otree = oracle.from_arrays(bounds, index_values, tree["prim_ids"])
+    oracle.set_triangles(otree, tris)
+    rays = scenes.make_primary("soup", 40, 40).copy()
+    rays[0::10, 6] = np.nan
+    rays[1::10, 7] = np.nan
+    rays[2::10, 3:6] = 0
+    rays[3::10, 6], rays[3::10, 7] = 1.0, 0.5
+    rays[4::10, 7] = np.inf
+    rays[6::10, 3] = 0
+    for _, flags in MODES:
+        got = emul.trace(tree, rays, flags)
+        want = oracle.trace(otree, rays, flags=flags)
+        assert (got[0] == want[0]).all()
+        ok = ~np.isnan(rays[:, 7])
+        assert_hits_equal(tuple(x[ok] for x in got[:4]), tuple(x[ok] for x in want), f"nan/{flags}")
+
+
 def test_boxes_and_centres_input(emul, oracle):
     tris = scenes.soup(3000)
     bb, cc = oracle.tri_bboxes_centers(tris)

@@ -22,6 +22,9 @@ TIE_LAST_VISITED = 1 << 2
 DEVICE_POINTERS = 1 << 3
 KERNEL_SIMPLE = 1 << 8
 KERNEL_NO_TMA = 1 << 9
+KERNEL_TMA = 1 << 10
+KERNEL_PAIR = 1 << 11
+KERNELS = (KERNEL_PAIR, KERNEL_NO_TMA, KERNEL_TMA, KERNEL_SIMPLE)
 INVALID_ID = 0xFFFFFFFF
 
 QUALITY = {"low": 0, "medium": 1, "high": 2}

@@ -370,6 +370,8 @@ int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bv
     if (flags & BVH_TIE_LAST_VISITED) tf |= kTraceLastVisited;
     if (flags & BVH_KERNEL_SIMPLE) tf |= kTraceSimple;
     if (flags & BVH_KERNEL_NO_TMA) tf |= kTraceNoTma;
+    if (flags & BVH_KERNEL_TMA) tf |= kTraceTma;
+    if (flags & BVH_KERNEL_PAIR) tf |= kTracePair;
     if (flags & BVH_DEVICE_POINTERS) {
         return trace_rays<T>(h->dev, reinterpret_cast<const DevRay<T>*>(rays), reinterpret_cast<DevHit<T>*>(hits), n, tf,
                              reinterpret_cast<uint32_t*>(stats), h->stream);

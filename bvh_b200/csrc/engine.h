@@ -69,7 +69,9 @@ enum TraceFlags : unsigned {
     kTraceRobust      = 1u << 1,
     kTraceLastVisited = 1u << 2,   // reference example tie semantics instead of the canonical lowest id
     kTraceSimple      = 1u << 8,   // one-thread-per-ray kernel instead of the persistent one
-    kTraceNoTma       = 1u << 9,   // persistent kernel without the bulk-copy ray staging
+    kTraceNoTma       = 1u << 9,   // persistent one-lane-per-ray kernel, rays read with streaming loads
+    kTraceTma         = 1u << 10,  // persistent one-lane-per-ray kernel, ray chunks staged by bulk async copy (TMA)
+    kTracePair        = 1u << 11,  // persistent lane-pair kernel (two lanes per ray)
 };
 
 // Batched traversal; all pointers are device pointers.  ray_stats (nullable): n x 3 uint32

@@ -2,13 +2,13 @@
 //
 // 8-bit digits, stable, three kernels per pass:
 //   rs_tile_hist   per-tile digit histogram, stored digit-major  [digit][tile]
-//   rs_scan        exclusive scan of that array: element (d, t) becomes the global output position of
-//                  the first key of tile t with digit d (= keys with a smaller digit anywhere + keys
-//                  with the same digit in earlier tiles)
-//   rs_scatter     re-reads the tile, ranks keys of equal digit stably (warp-level multi-split with
-//                  __match_any_sync, then a per-digit prefix across the tile's warps) and scatters
-// A tile is 512 threads x 16 keys = 8192 keys, warp-striped so every load instruction of a warp
-// reads 32 consecutive keys (128 B / 256 B, fully coalesced).
+//   rs_scan_bins   one warp per digit: exclusive scan of that digit's counts over the tiles (= keys with
+//                  the same digit in earlier tiles) and the digit's total
+//   rs_scatter     scans the 256 digit totals (= keys with a smaller digit anywhere), re-reads the tile,
+//                  ranks keys of equal digit stably (warp-level multi-split with __match_any_sync, then
+//                  a per-digit prefix across the tile's warps) and scatters
+// A tile is 256 threads x 8 keys = 2048 keys, warp-striped so every load instruction of a warp
+// reads 32 consecutive keys (128 B / 256 B, fully coalesced).  No stage is a single serial block.
 //
 // Algorithmic HBM bytes per key per pass (32-bit key, 32-bit value): hist 4 + scatter read 8 +
 // scatter write 8 = 20 (the first pass synthesises the identity permutation instead of reading it).
@@ -19,12 +19,13 @@
 
 namespace bvhb200 {
 
-constexpr int kRsBlock = 512;
-constexpr int kRsItems = 16;
-constexpr int kRsTile = kRsBlock * kRsItems;     // 8192
+constexpr int kRsBlock = 256;
+constexpr int kRsItems = 8;
+constexpr int kRsTile = kRsBlock * kRsItems;     // 2048 keys per tile
 constexpr int kRsBins = 256;
-constexpr int kRsWarps = kRsBlock / 32;          // 16
-constexpr int kRsScanBlock = 1024;
+constexpr int kRsWarps = kRsBlock / 32;          // 8
+constexpr int kRsScanWarps = 8;                  // digits scanned per block of rs_scan_bins_kernel
+static_assert(kRsBlock == kRsBins, "thread d owns digit d");
 
 template <typename K>
 __global__ void __launch_bounds__(kRsBlock)
@@ -32,69 +33,72 @@ rs_tile_hist_kernel(const K* __restrict__ keys, uint32_t n, int shift,
                     uint32_t* __restrict__ tile_hist, uint32_t num_tiles) {
     __shared__ uint32_t hist[kRsBins];
     const uint32_t tile = blockIdx.x;
-    if (threadIdx.x < kRsBins) hist[threadIdx.x] = 0;
+    hist[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t base = tile * (uint32_t)kRsTile;
-    #pragma unroll 4
-    for (int k = threadIdx.x; k < kRsTile; k += kRsBlock) {
-        const uint32_t idx = base + k;
+    #pragma unroll
+    for (int k = 0; k < kRsItems; ++k) {
+        const uint32_t idx = base + k * kRsBlock + threadIdx.x;
         if (idx < n) atomicAdd(&hist[(uint32_t)(keys[idx] >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (threadIdx.x < kRsBins) tile_hist[(size_t)threadIdx.x * num_tiles + tile] = hist[threadIdx.x];
+    tile_hist[(size_t)threadIdx.x * num_tiles + tile] = hist[threadIdx.x];
 }
 
-// Single-block exclusive scan of `count` uint32 values, in place.
-__global__ void __launch_bounds__(kRsScanBlock)
-rs_scan_kernel(uint32_t* __restrict__ data, uint32_t count) {
-    __shared__ uint32_t warp_sums[kRsScanBlock / 32];
-    const uint32_t per = (count + kRsScanBlock - 1) / kRsScanBlock;
-    const uint32_t begin = threadIdx.x * per;
-    const uint32_t end = begin + per < count ? begin + per : count;
-    uint32_t sum = 0;
-    for (uint32_t i = begin; i < end; ++i) sum += data[i];
-    // block-wide exclusive scan of `sum`
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = sum;
-    #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= (unsigned)o) incl += v;
-    }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = warp_sums[lane];
-        uint32_t wi = w;
+// One warp per digit: exclusive scan of that digit's per-tile counts (a contiguous row of the
+// digit-major histogram), in place, plus the digit's total.  The 256 totals are scanned by every
+// scatter block itself.
+__global__ void __launch_bounds__(kRsScanWarps * 32)
+rs_scan_bins_kernel(uint32_t* __restrict__ tile_hist, uint32_t num_tiles, uint32_t* __restrict__ bin_totals) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t bin = blockIdx.x * kRsScanWarps + (threadIdx.x >> 5);
+    uint32_t* row = tile_hist + (size_t)bin * num_tiles;
+    uint32_t running = 0;
+    for (uint32_t base = 0; base < num_tiles; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t v = i < num_tiles ? row[i] : 0u;
+        uint32_t incl = v;
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-            if (lane >= (unsigned)o) wi += v;
+            const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= (unsigned)o) incl += x;
         }
-        warp_sums[lane] = wi - w;           // exclusive prefix of the warp totals
+        if (i < num_tiles) row[i] = running + incl - v;
+        running += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
-    __syncthreads();
-    uint32_t running = warp_sums[warp] + (incl - sum);
-    for (uint32_t i = begin; i < end; ++i) {
-        const uint32_t v = data[i];
-        data[i] = running;
-        running += v;
-    }
+    if (lane == 0) bin_totals[bin] = running;
 }
 
 template <typename K, bool kIota>
 __global__ void __launch_bounds__(kRsBlock)
 rs_scatter_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                   K* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
-                  const uint32_t* __restrict__ tile_offsets, uint32_t num_tiles) {
-    __shared__ uint32_t warp_hist[kRsWarps][kRsBins];     // 16 KB
+                  const uint32_t* __restrict__ tile_offsets, uint32_t num_tiles,
+                  const uint32_t* __restrict__ bin_totals) {
+    __shared__ uint32_t warp_hist[kRsWarps][kRsBins];     // 8 KB
     __shared__ uint32_t bin_base[kRsBins];
+    __shared__ uint32_t scan_tmp[kRsWarps];
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t tile = blockIdx.x;
 
-    for (int k = tid; k < kRsWarps * kRsBins; k += kRsBlock) (&warp_hist[0][0])[k] = 0;
+    #pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) warp_hist[w][tid] = 0;
+
+    // exclusive scan of the 256 digit totals (thread d owns digit d) -> start of digit d in the output
+    const uint32_t total = bin_totals[tid];
+    uint32_t incl = total;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (unsigned)o) incl += x;
+    }
+    if (lane == 31) scan_tmp[warp] = incl;
     __syncthreads();
+    uint32_t warp_prefix = 0;
+    #pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) if (w < (int)warp) warp_prefix += scan_tmp[w];
+    const uint32_t digit_start = warp_prefix + incl - total;
 
     const uint32_t warp_base = tile * (uint32_t)kRsTile + warp * (32u * kRsItems);
     K key[kRsItems];
@@ -122,7 +126,7 @@ rs_scatter_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ va
         rank[j] = base + r;
     }
     __syncthreads();
-    if (tid < kRsBins) {
+    {
         uint32_t running = 0;
         #pragma unroll
         for (int w = 0; w < kRsWarps; ++w) {
@@ -130,7 +134,7 @@ rs_scatter_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ va
             warp_hist[w][tid] = running;
             running += c;
         }
-        bin_base[tid] = tile_offsets[(size_t)tid * num_tiles + tile];
+        bin_base[tid] = digit_start + tile_offsets[(size_t)tid * num_tiles + tile];
     }
     __syncthreads();
     #pragma unroll
@@ -147,11 +151,12 @@ rs_scatter_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ va
 
 // Sorts n (key, value) pairs by the low `key_bits` bits of the key.  keys_a/vals_a hold the input
 // (vals_a is ignored: the value of element i is i) and, because the number of passes is even for
-// 30- and 63-bit keys, also the output.  tile_hist needs 256 * ceil(n / 8192) uint32.
+// 30- and 63-bit keys, also the output.  tile_hist needs 256 * ceil(n / 2048) + 256 uint32.
 template <typename K>
 inline cudaError_t radix_sort_pairs(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* vals_b,
                                     uint32_t* tile_hist, uint32_t n, int key_bits, cudaStream_t stream) {
     const uint32_t num_tiles = (n + kRsTile - 1) / kRsTile;
+    uint32_t* bin_totals = tile_hist + (size_t)num_tiles * kRsBins;
     int passes = (key_bits + 7) / 8;
     if (passes & 1) ++passes;                              // keep the result in buffer A
     K* kin = keys_a; K* kout = keys_b;
@@ -159,11 +164,11 @@ inline cudaError_t radix_sort_pairs(K* keys_a, uint32_t* vals_a, K* keys_b, uint
     for (int pass = 0; pass < passes; ++pass) {
         const int shift = pass * 8;
         rs_tile_hist_kernel<K><<<num_tiles, kRsBlock, 0, stream>>>(kin, n, shift, tile_hist, num_tiles);
-        rs_scan_kernel<<<1, kRsScanBlock, 0, stream>>>(tile_hist, num_tiles * (uint32_t)kRsBins);
+        rs_scan_bins_kernel<<<kRsBins / kRsScanWarps, kRsScanWarps * 32, 0, stream>>>(tile_hist, num_tiles, bin_totals);
         if (pass == 0)
-            rs_scatter_kernel<K, true><<<num_tiles, kRsBlock, 0, stream>>>(kin, vin, kout, vout, n, shift, tile_hist, num_tiles);
+            rs_scatter_kernel<K, true><<<num_tiles, kRsBlock, 0, stream>>>(kin, vin, kout, vout, n, shift, tile_hist, num_tiles, bin_totals);
         else
-            rs_scatter_kernel<K, false><<<num_tiles, kRsBlock, 0, stream>>>(kin, vin, kout, vout, n, shift, tile_hist, num_tiles);
+            rs_scatter_kernel<K, false><<<num_tiles, kRsBlock, 0, stream>>>(kin, vin, kout, vout, n, shift, tile_hist, num_tiles, bin_totals);
         K* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }

@@ -86,6 +86,7 @@ template <typename T> struct TraceArgs {
     unsigned long long* next_ray;     // persistent kernel: global ray cursor
     uint32_t* ray_stats;              // statistics variant: n x 3
     uint32_t stack_entries;
+    int variant;                      // 0/1: one lane per ray (direct / TMA-staged rays), 2: lane-pair kernel
     bool use_tma;                     // persistent kernel: stage ray chunks with cp.async.bulk
     uint32_t inner_budget;            // persistent kernel: inner steps per lane per round (0xFFFFFFFF = unbounded)
     int lowest_id;
@@ -150,7 +151,7 @@ __device__ __forceinline__ void read_ray_smem(const DevRay<double>* p, RayCtx<do
     r.dir[1] = c.x; r.dir[2] = c.y; r.tmin = d.x; r.tmax = d.y;
 }
 
-constexpr int kTmaChunkRays = 64;        // rays per bulk copy (2 KB of float rays), two buffers per warp
+constexpr int kTmaChunkRays = 32;        // rays per bulk copy (1 KB of float rays), two buffers per warp
 
 template <typename T> __host__ __device__ constexpr size_t tma_smem_bytes() {
     return (size_t)(kTraceBlock / 32) * 2 * kTmaChunkRays * sizeof(DevRay<T>) + (size_t)(kTraceBlock / 32) * 2 * 8;
@@ -161,7 +162,7 @@ template <typename T> __host__ __device__ constexpr size_t tma_smem_bytes() {
 // that the ray fetch of the refill path never waits on DRAM; kTma = false reads rays with streaming
 // 128-bit loads.
 template <typename T, bool kAny, bool kRobust, bool kTma>
-__global__ void __launch_bounds__(kTraceBlock)
+__global__ void __launch_bounds__(kTraceBlock, sizeof(T) == 4 ? 8 : 4)
 trace_persistent_kernel(TraceArgs<T> a) {
     using U = typename Real<T>::UInt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -308,16 +309,143 @@ trace_persistent_kernel(TraceArgs<T> a) {
 }
 
 // Tunables of the persistent kernel; environment overrides exist for experiments only.
-struct Tuning { uint32_t inner_budget; bool use_tma; };
+struct Tuning { uint32_t inner_budget; int variant; };
 const Tuning& tuning() {
     static const Tuning t = [] {
-        Tuning v { 8u, true };
+        Tuning v { 8u, 2 };
         if (const char* e = getenv("BVH_B200_INNER_BUDGET")) { long k = atol(e); v.inner_budget = k <= 0 ? 0xFFFFFFFFu : (uint32_t)k; }
-        if (const char* e = getenv("BVH_B200_TMA")) v.use_tma = atoi(e) != 0;
+        if (const char* e = getenv("BVH_B200_VARIANT")) v.variant = atoi(e);
         return v;
     }();
     return t;
 }
+
+// ---- lane-pair kernel ------------------------------------------------------------------------------
+// Two adjacent lanes serve ONE ray: in an inner step lane 0 of the pair fetches and tests the left
+// child, lane 1 the right child (one 256-bit load each, both from the same 64-byte block), and the two
+// exchange (hit, entry distance, index) with pair-masked __ballot_sync / __shfl_xor_sync.  Why: with
+// divergent rays the L1 data pipe spends one wavefront per thread per load (profiles/: the one-lane-per-ray
+// kernel is bound by l1tex__data_pipe_lsu_wavefronts at ~87 % of peak); the two lanes of a pair hit the same
+// line, so a whole sibling pair costs ONE wavefront instead of two.  Control state (top, stack pointer,
+// tmax, hit) is replicated in both lanes, which take identical decisions; the leaf phase is executed
+// redundantly by both lanes (same addresses, so no extra memory wavefronts).  Per-ray semantics are
+// unchanged: same visit order, same results as traverse_ray().
+template <typename U> __device__ __forceinline__ U shfl_xor1(unsigned mask, U v);
+template <> __device__ __forceinline__ uint32_t shfl_xor1<uint32_t>(unsigned mask, uint32_t v) { return __shfl_xor_sync(mask, v, 1); }
+template <> __device__ __forceinline__ uint64_t shfl_xor1<uint64_t>(unsigned mask, uint64_t v) { return __shfl_xor_sync(mask, (unsigned long long)v, 1); }
+template <> __device__ __forceinline__ float shfl_xor1<float>(unsigned mask, float v) { return __shfl_xor_sync(mask, v, 1); }
+template <> __device__ __forceinline__ double shfl_xor1<double>(unsigned mask, double v) { return __shfl_xor_sync(mask, v, 1); }
+
+template <typename T, bool kAny, bool kRobust>
+__global__ void __launch_bounds__(kTraceBlock, sizeof(T) == 4 ? 8 : 4)
+trace_pair_kernel(TraceArgs<T> a) {
+    using U = typename Real<T>::UInt;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    constexpr unsigned kEven = 0x55555555u;
+    const unsigned lane = threadIdx.x & 31u, sub = lane & 1u, pair_shift = lane & ~1u;
+    const unsigned pair_mask = 3u << pair_shift;
+    const unsigned lt_mask = (1u << pair_shift) - 1u;                  // pairs before this one
+    SmemStack<U> stack { reinterpret_cast<U*>(smem_raw) + (threadIdx.x >> 1), kTraceBlock / 2, 0 };
+    const bool lowest_id = a.lowest_id != 0;
+    const U root_index = a.nodes[1].index;
+    const uint32_t inner_budget = a.inner_budget;
+
+    unsigned long long chunk_pos = 0, chunk_end = 0;                   // warp-uniform
+    bool exhausted = false;
+
+    bool has_ray = false;
+    unsigned long long ray_index = 0;
+    RayCtx<T> r;
+    HitState<T> hit;
+    T tmax_in = (T)0;
+    U top = 0;
+
+    for (;;) {
+        // ---- refill idle pairs -----------------------------------------------------------------------
+        unsigned idle = __ballot_sync(kFull, !has_ray) & kEven;
+        while (idle != 0u && !exhausted) {
+            if (chunk_pos == chunk_end) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.next_ray, (unsigned long long)kChunkRays);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= a.n) { exhausted = true; break; }
+                chunk_pos = base;
+                chunk_end = base + kChunkRays < a.n ? base + kChunkRays : a.n;
+            }
+            const unsigned avail = (unsigned)(chunk_end - chunk_pos), want = __popc(idle);
+            const unsigned take = want < avail ? want : avail;
+            const unsigned rank = __popc(idle & lt_mask);
+            if (!has_ray && rank < take) {
+                ray_index = chunk_pos + rank;
+                load_ray(a.rays, ray_index, r);
+                tmax_in = r.tmax;
+                hit.slot = kInvalidId; hit.t = r.tmax; hit.u = (T)0; hit.v = (T)0;
+                if (ray_interval_is_nan(r)) {
+                    if (sub == 0) store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
+                } else {
+                    ray_prologue<T, kRobust>(r);
+                    top = root_index;
+                    stack.sp = 0;
+                    has_ray = true;
+                }
+            }
+            chunk_pos += take;
+            idle = __ballot_sync(kFull, !has_ray) & kEven;
+        }
+        if (__ballot_sync(kFull, has_ray) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---- inner phase (bounded) --------------------------------------------------------------------
+        if (has_ray) {
+            uint32_t budget = inner_budget;
+            while (index_count(top) == 0 && budget != 0) {
+                --budget;
+                T b[6]; U my_index;
+                load_node(a.nodes + (size_t)index_first(top) + 1 + sub, b, my_index);
+                T t0, t1;
+                node_test<T, kRobust>(b, r, t0, t1);
+                const bool my_hit = t0 <= t1;
+                const unsigned votes = (__ballot_sync(pair_mask, my_hit) >> pair_shift) & 3u;
+                const T other_t0 = shfl_xor1<T>(pair_mask, t0);
+                const U other_index = shfl_xor1<U>(pair_mask, my_index);
+                const U left_index = sub ? other_index : my_index, right_index = sub ? my_index : other_index;
+                const T l0 = sub ? other_t0 : t0, r0 = sub ? t0 : other_t0;
+                if (votes & 1u) {                                           // hit_left (bvh.h:138-147)
+                    U near_index = left_index;
+                    if (votes & 2u) {
+                        U far_index = right_index;
+                        if (!kAny && l0 > r0) { near_index = right_index; far_index = left_index; }
+                        stack.push(far_index);
+                    }
+                    top = near_index;
+                } else if (votes & 2u) {
+                    top = right_index;
+                } else {
+                    if (stack.empty()) { has_ray = false; break; }
+                    top = stack.pop();
+                }
+            }
+            if (!has_ray && sub == 0) store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
+        }
+        __syncwarp();
+
+        // ---- leaf phase (both lanes of the pair run it redundantly) -------------------------------------
+        if (has_ray && index_count(top) != 0) {
+            leaf_step<T>(a.tris, a.prim_ids, lowest_id, top, r, hit, nullptr);
+            if ((kAny && hit.slot != kInvalidId) || stack.empty()) {
+                if (sub == 0) store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
+                has_ray = false;
+            } else {
+                top = stack.pop();
+            }
+        }
+        __syncwarp();
+    }
+}
+
 
 template <typename KernelT>
 int configure_smem(KernelT kernel, size_t smem_bytes) {
@@ -341,6 +469,19 @@ int launch(const TraceArgs<T>& args, bool simple, bool stats, int device, cudaSt
             if (configure_smem(trace_simple_kernel<T, kAny, kRobust, false>, smem)) return -1;
             trace_simple_kernel<T, kAny, kRobust, false><<<(unsigned)blocks, kTraceBlock, smem, stream>>>(args);
         }
+    } else if (args.variant == 2) {
+        auto kernel = trace_pair_kernel<T, kAny, kRobust>;
+        const size_t pair_smem = smem / 2;                                     // one stack per lane pair
+        if (configure_smem(kernel, pair_smem)) return -1;
+        int sm_count = 148, per_sm = 1;
+        BVH_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceBlock, pair_smem));
+        if (per_sm < 1) per_sm = 1;
+        unsigned long long grid = (unsigned long long)sm_count * per_sm;
+        const unsigned long long max_useful = (args.n + 15) / 16 / (kTraceBlock / 32) + 1;
+        if (grid > max_useful) grid = max_useful;
+        BVH_CUDA_TRY(cudaMemsetAsync(args.next_ray, 0, sizeof(unsigned long long), stream));
+        kernel<<<(unsigned)grid, kTraceBlock, pair_smem, stream>>>(args);
     } else {
         const bool tma = args.use_tma;
         auto kernel = tma ? trace_persistent_kernel<T, kAny, kRobust, true> : trace_persistent_kernel<T, kAny, kRobust, false>;
@@ -378,7 +519,8 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     args.stack_entries = entries;
     args.next_ray = nullptr;
     args.inner_budget = tuning().inner_budget;
-    args.use_tma = (flags & kTraceNoTma) ? false : tuning().use_tma;
+    args.variant = (flags & kTracePair) ? 2 : ((flags & (kTraceNoTma | kTraceTma)) ? 0 : tuning().variant);
+    args.use_tma = (flags & kTraceTma) ? true : ((flags & kTraceNoTma) ? false : tuning().variant == 1);
     const bool simple = (flags & kTraceSimple) != 0, stats = d_ray_stats != nullptr;
     void* cursor = nullptr;
     if (!simple && !stats) {

@@ -50,6 +50,23 @@ __device__ __forceinline__ void load_pair(const DevNode<double>* __restrict__ p,
     o.lb[4] = __longlong_as_double((long long)b[0]); o.lb[5] = __longlong_as_double((long long)b[1]); o.li = b[2];
     o.rb[4] = __longlong_as_double((long long)d[0]); o.rb[5] = __longlong_as_double((long long)d[1]); o.ri = d[2];
 }
+// One node (for the lane-pair kernel: each lane of a pair fetches one child of the sibling pair).
+__device__ __forceinline__ void load_node(const DevNode<float>* __restrict__ p, float (&b)[6], uint32_t& index) {
+    uint32_t a[8];
+    ldg256(p, a);
+    #pragma unroll
+    for (int k = 0; k < 6; ++k) b[k] = __uint_as_float(a[k]);
+    index = a[6];
+}
+__device__ __forceinline__ void load_node(const DevNode<double>* __restrict__ p, double (&b)[6], uint64_t& index) {
+    unsigned long long a[4], c[4];
+    const unsigned char* q = reinterpret_cast<const unsigned char*>(p);
+    ldg256(q, a); ldg256(q + 32, c);
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) b[k] = __longlong_as_double((long long)a[k]);
+    b[4] = __longlong_as_double((long long)c[0]); b[5] = __longlong_as_double((long long)c[1]);
+    index = c[2];
+}
 __device__ __forceinline__ void load_tri(const DevTri<float>* __restrict__ p, DevTri<float>& o) {
     const float4* q = reinterpret_cast<const float4*>(p);
     const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);

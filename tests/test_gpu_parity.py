@@ -31,7 +31,7 @@ def test_lbvh_vs_reference_golden(gpu_lib, name):
     api = gpu_lib
     g = golden(name)
     bvh = api.Bvh.build_triangles(g["tris"])
-    for kernel in (0, api.KERNEL_NO_TMA, api.KERNEL_SIMPLE):
+    for kernel in (0,) + api.KERNELS:
         hits = bvh.intersect_rays(g["rays"], flags=kernel)
         assert_hits_equal(hits_tuple(hits), tuple(g[f"lowest_{k}"] for k in ("ids", "t", "u", "v")), f"{name}/closest/{kernel}")
         hits = bvh.intersect_rays(g["rays"], flags=kernel | api.ROBUST)
@@ -63,7 +63,7 @@ def test_reference_tree_on_gpu(gpu_lib, name):
             assert_hits_equal(hits_tuple(hits), tuple(g[f"{mode}_{k}"] for k in ("ids", "t", "u", "v")), f"{name}/{mode}")
             want = g[f"{mode}_stats"]
             assert (st["inner_steps"] == want[:, 0]).all() and (st["leaves"] == want[:, 1]).all() and (st["prim_tests"] == want[:, 2]).all()
-            for variant in (0, api.KERNEL_NO_TMA):                      # persistent kernels, same answers
+            for variant in (0,) + api.KERNELS[:3]:                    # persistent kernels, same answers
                 hits2 = bvh.intersect_rays(g["rays"], flags=flags | variant)
                 assert_hits_equal(hits_tuple(hits2), hits_tuple(hits), f"{name}/{mode}/persistent/{variant}")
         # save -> byte-identical file
@@ -165,7 +165,7 @@ def test_nan_and_degenerate_rays(gpu_lib, oracle):
     oracle.set_triangles(tree, tris)
     for mode, oflags, flags in modes(api):
         want = oracle.trace(tree, rays, flags=oflags)
-        for variant in (0, api.KERNEL_NO_TMA, api.KERNEL_SIMPLE):
+        for variant in (0,) + api.KERNELS:
             got = hits_tuple(bvh.intersect_rays(rays, flags=flags | variant))
             nan_rays = np.isnan(rays[:, 7])
             assert (got[0] == want[0]).all()
@@ -283,7 +283,7 @@ def test_full_size_properties(gpu_lib, oracle, kind):
     assert (hits["t"][~hit] == rays[~hit, 7]).all() and (hits["t"][hit] > 0).all()
     assert (hits["u"][hit] >= -1e-6).all() and (hits["v"][hit] >= -1e-6).all() and ((hits["u"] + hits["v"])[hit] <= 1 + 1e-5).all()
     # all kernels agree exactly
-    for variant in (api.KERNEL_SIMPLE, api.KERNEL_NO_TMA):
+    for variant in api.KERNELS:
         other = bvh.intersect_rays(rays, flags=variant)
         assert (other.view(np.uint8) == hits.view(np.uint8)).all()
     # nothing lies in front of a reported closest hit: re-trace with tmax just below t as any-hit

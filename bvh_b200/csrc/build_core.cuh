@@ -110,13 +110,30 @@ template <typename K> BVH_HD Delta<K> delta_at(const K* __restrict__ keys, uint3
     return Delta<K>{ (K)(keys[k] ^ keys[k + 1]), k ^ (k + 1) };
 }
 
-template <typename T> struct NodeAux;
-template <> struct alignas(8)  NodeAux<float>  { float cost;  uint32_t depth; };
-template <> struct alignas(16) NodeAux<double> { double cost; uint32_t depth; uint32_t pad; };
+// While the tree is being built, the spare word of a node record carries what the SECOND arrival at the
+// parent needs from the first: the subtree's SAH cost and its depth.  Keeping them in the record itself
+// (instead of a side array) means one 32-byte store and one 32-byte load per node on the critical path.
+// float nodes have a 32-bit spare word: the cost's low 7 mantissa bits are replaced by the depth (<= 127;
+// the cost only feeds the leaf-collapse comparison); double nodes have 64 bits: float cost + depth.
+// The traversal never reads this word and the host mirror drops it.
+template <typename T> struct AuxPack;
+template <> struct AuxPack<float> {
+    static BVH_HD uint32_t pack(float cost, uint32_t depth) {
+        return (Real<float>::bits(cost) & ~0x7Fu) | (depth > 127u ? 127u : depth);
+    }
+    static BVH_HD float cost(uint32_t w) { return Real<float>::from_bits(w & ~0x7Fu); }
+    static BVH_HD uint32_t depth(uint32_t w) { return w & 0x7Fu; }
+};
+template <> struct AuxPack<double> {
+    static BVH_HD uint64_t pack(double cost, uint32_t depth) {
+        return ((uint64_t)Real<float>::bits((float)cost) << 32) | depth;
+    }
+    static BVH_HD double cost(uint64_t w) { return (double)Real<float>::from_bits((uint32_t)(w >> 32)); }
+    static BVH_HD uint32_t depth(uint64_t w) { return (uint32_t)w; }
+};
 
 template <typename T> struct BuildParams {
     DevNode<T>* nodes;            // 2n device slots (slot = reference index + 1)
-    NodeAux<T>* aux;              // 2n, indexed like nodes
     int* flags;                   // n-1, initialised to -1
     uint32_t* info;               // [0] tree depth (max stack entries needed), [1] root split position
     uint32_t n;
@@ -124,10 +141,10 @@ template <typename T> struct BuildParams {
 };
 
 template <typename T> BVH_HD void write_node(DevNode<T>* dst, const T bmin[3], const T bmax[3],
-                                             typename Real<T>::UInt index) {
+                                             typename Real<T>::UInt index, typename Real<T>::UInt pad = 0) {
     DevNode<T> n;
     for (int k = 0; k < 3; ++k) { n.bounds[2 * k] = bmin[k]; n.bounds[2 * k + 1] = bmax[k]; }
-    n.index = index; n.pad = 0;
+    n.index = index; n.pad = pad;
 #if defined(__CUDA_ARCH__)
     // two (float) / four (double) 128-bit stores
     const uint4* s = reinterpret_cast<const uint4*>(&n);
@@ -176,8 +193,11 @@ BVH_HD void build_bottom_up(const BuildParams<T>& p, const K* __restrict__ keys,
             parent = l - 1; side = 1;                       // we are the child covering [parent+1, r]
         }
         const size_t slot = 2 * (size_t)parent + 1 + side + 1;   // reference index 2p+1+side, +1 device shift
-        write_node(p.nodes + slot, bmin, bmax, index);
-        p.aux[slot].cost = cost; p.aux[slot].depth = depth;
+        // the cost travels rounded to what the packed word can hold, so that both arrivals (and the host
+        // emulation) see the same value
+        const U aux = AuxPack<T>::pack(cost, depth);
+        cost = AuxPack<T>::cost(aux);
+        write_node(p.nodes + slot, bmin, bmax, index, aux);
         Sync::fence();
         const int other = Sync::exchange(p.flags + parent, (int)(side == 0 ? l : r));
         if (other < 0) return;                              // first to arrive: the sibling will carry on
@@ -186,7 +206,8 @@ BVH_HD void build_bottom_up(const BuildParams<T>& p, const K* __restrict__ keys,
         // Second to arrive: fetch the sibling's record and merge.
         const size_t sib = 2 * (size_t)parent + 1 + (1 - side) + 1;
         const DevNode<T> sn = Sync::load(p.nodes + sib);
-        const NodeAux<T> sa = Sync::load(p.aux + sib);
+        const T sib_cost = AuxPack<T>::cost(sn.pad);
+        const uint32_t sib_depth = AuxPack<T>::depth(sn.pad);
         T smin[3] = { sn.bounds[0], sn.bounds[2], sn.bounds[4] };
         T smax[3] = { sn.bounds[1], sn.bounds[3], sn.bounds[5] };
         const T own_area = half_area(bmin, bmax), sib_area = half_area(smin, smax);
@@ -195,8 +216,8 @@ BVH_HD void build_bottom_up(const BuildParams<T>& p, const K* __restrict__ keys,
         const bool own_is_left = side == 0;
         const T left_area = own_is_left ? own_area : sib_area, right_area = own_is_left ? sib_area : own_area;
         if (left_area < right_area) {
-            write_node(p.nodes + sib, bmin, bmax, index);
-            write_node(p.nodes + slot, smin, smax, sn.index);
+            write_node(p.nodes + sib, bmin, bmax, index, aux);
+            write_node(p.nodes + slot, smin, smax, sn.index, sn.pad);
         }
 
         if (side == 0) r = (uint32_t)other; else l = (uint32_t)other;
@@ -212,9 +233,9 @@ BVH_HD void build_bottom_up(const BuildParams<T>& p, const K* __restrict__ keys,
 
         const uint32_t count = r - l + 1;
         const T area = half_area(bmin, bmax);
-        const T split_cost = R::add(area, R::add(cost, sa.cost));   // node cost_ratio 1 (split_heuristic.h:18-24)
+        const T split_cost = R::add(area, R::add(cost, sib_cost));   // node cost_ratio 1 (split_heuristic.h:18-24)
         const T leaf_cost = R::mul(area, (T)count);                 // get_leaf_cost, split_heuristic.h:30-33
-        const uint32_t sub_depth = (depth > sa.depth ? depth : sa.depth) + 1;
+        const uint32_t sub_depth = (depth > sib_depth ? depth : sib_depth) + 1;
         if (count <= p.max_leaf && (count <= p.min_leaf || leaf_cost <= split_cost)) {
             index = make_index<U>((U)l, count);             // collapse the subtree into one leaf
             cost = leaf_cost; depth = 0;

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -392,6 +393,7 @@ int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bv
     auto d_stats = static_cast<uint32_t*>(h->d_stats);
     constexpr size_t kMinChunk = 1u << 18;                   // 256K rays = 8 MB of float rays
     size_t chunks = n / kMinChunk;
+    if (const char* e = getenv("BVH_B200_E2E_CHUNKS")) chunks = (size_t)atol(e);      // experiments only
     if (chunks < 1) chunks = 1;
     if (chunks > Handle<T>::kMaxChunks) chunks = Handle<T>::kMaxChunks;
     // the staging buffers may still be in use by earlier work on the handle's stream

@@ -36,12 +36,12 @@ struct DeviceSync {
     }
     // read through L2 (the sibling's record was written by another SM)
     template <typename X> static __device__ __forceinline__ X load(const X* p) {
-        static_assert(sizeof(X) % 8 == 0, "load granularity");
+        static_assert(sizeof(X) % 16 == 0, "load granularity");
         X out;
-        const unsigned long long* s = reinterpret_cast<const unsigned long long*>(p);
-        unsigned long long* d = reinterpret_cast<unsigned long long*>(&out);
+        const uint4* s = reinterpret_cast<const uint4*>(p);
+        uint4* d = reinterpret_cast<uint4*>(&out);
         #pragma unroll
-        for (int k = 0; k < (int)(sizeof(X) / 8); ++k) d[k] = __ldcg(s + k);
+        for (int k = 0; k < (int)(sizeof(X) / 16); ++k) d[k] = __ldcg(s + k);
         return out;
     }
 };
@@ -228,10 +228,10 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     const uint32_t num_tiles = (n + kRsTile - 1) / kRsTile;
 
     MinMax3<T>* partials; K* keys_a; K* keys_b; uint32_t* vals_b; uint32_t* tile_hist; int* flags;
-    NodeAux<T>* aux; uint32_t* info;
+    uint32_t* info;
     if (scratch.alloc(&partials, grid) || scratch.alloc(&keys_a, n) || scratch.alloc(&keys_b, n) ||
         scratch.alloc(&vals_b, n) || scratch.alloc(&tile_hist, (size_t)num_tiles * kRsBins + kRsBins) ||
-        scratch.alloc(&flags, n) || scratch.alloc(&aux, 2 * (size_t)n + 2) || scratch.alloc(&info, 4))
+        scratch.alloc(&flags, n) || scratch.alloc(&info, 4))
         return -1;
 
     out.prim_count = n;
@@ -245,7 +245,7 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     BVH_CUDA_TRY(radix_sort_pairs<K>(keys_a, out.prim_ids, keys_b, vals_b, tile_hist, n, key_bits, stream));
 
     BuildParams<T> p;
-    p.nodes = out.nodes; p.aux = aux; p.flags = flags; p.info = info; p.n = n;
+    p.nodes = out.nodes; p.flags = flags; p.info = info; p.n = n;
     p.min_leaf = options.min_leaf < 1 ? 1 : options.min_leaf;
     p.max_leaf = options.max_leaf > kMaxLeafPrims ? kMaxLeafPrims : (options.max_leaf < 1 ? 1 : options.max_leaf);
     if (p.min_leaf > p.max_leaf) p.min_leaf = p.max_leaf;

@@ -344,7 +344,6 @@ trace_pair_kernel(TraceArgs<T> a) {
     constexpr unsigned kFull = 0xFFFFFFFFu;
     constexpr unsigned kEven = 0x55555555u;
     const unsigned lane = threadIdx.x & 31u, sub = lane & 1u, pair_shift = lane & ~1u;
-    const unsigned pair_mask = 3u << pair_shift;
     const unsigned lt_mask = (1u << pair_shift) - 1u;                  // pairs before this one
     SmemStack<U> stack { reinterpret_cast<U*>(smem_raw) + (threadIdx.x >> 1), kTraceBlock / 2, 0 };
     const bool lowest_id = a.lowest_id != 0;
@@ -398,37 +397,47 @@ trace_pair_kernel(TraceArgs<T> a) {
             continue;
         }
 
-        // ---- inner phase (bounded) --------------------------------------------------------------------
-        if (has_ray) {
+        // ---- inner phase (bounded, WARP-UNIFORM trip count) ----------------------------------------------
+        // Every lane runs every round of this loop so that the pair exchange can use full-mask warp
+        // primitives (a pair-specific mask would make the hardware execute the shuffle once per pair);
+        // lanes that already hold a leaf, or no ray, are predicated off inside a round.
+        {
             uint32_t budget = inner_budget;
-            while (index_count(top) == 0 && budget != 0) {
+            while (budget != 0) {
                 --budget;
-                T b[6]; U my_index;
-                load_node(a.nodes + (size_t)index_first(top) + 1 + sub, b, my_index);
-                T t0, t1;
-                node_test<T, kRobust>(b, r, t0, t1);
-                const bool my_hit = t0 <= t1;
-                const unsigned votes = (__ballot_sync(pair_mask, my_hit) >> pair_shift) & 3u;
-                const T other_t0 = shfl_xor1<T>(pair_mask, t0);
-                const U other_index = shfl_xor1<U>(pair_mask, my_index);
-                const U left_index = sub ? other_index : my_index, right_index = sub ? my_index : other_index;
-                const T l0 = sub ? other_t0 : t0, r0 = sub ? t0 : other_t0;
-                if (votes & 1u) {                                           // hit_left (bvh.h:138-147)
-                    U near_index = left_index;
-                    if (votes & 2u) {
-                        U far_index = right_index;
-                        if (!kAny && l0 > r0) { near_index = right_index; far_index = left_index; }
-                        stack.push(far_index);
+                const bool active = has_ray && index_count(top) == 0;
+                if (__ballot_sync(kFull, active) == 0u) break;
+                T b[6]; U my_index = 0;
+                T t0 = (T)0, t1 = (T)-1;
+                if (active) {
+                    load_node(a.nodes + (size_t)index_first(top) + 1 + sub, b, my_index);
+                    node_test<T, kRobust>(b, r, t0, t1);
+                }
+                const bool my_hit = active && t0 <= t1;
+                const unsigned votes = (__ballot_sync(kFull, my_hit) >> pair_shift) & 3u;
+                const T other_t0 = shfl_xor1<T>(kFull, t0);
+                const U other_index = shfl_xor1<U>(kFull, my_index);
+                if (active) {
+                    const U left_index = sub ? other_index : my_index, right_index = sub ? my_index : other_index;
+                    const T l0 = sub ? other_t0 : t0, r0 = sub ? t0 : other_t0;
+                    if (votes & 1u) {                                       // hit_left (bvh.h:138-147)
+                        U near_index = left_index;
+                        if (votes & 2u) {
+                            U far_index = right_index;
+                            if (!kAny && l0 > r0) { near_index = right_index; far_index = left_index; }
+                            stack.push(far_index);
+                        }
+                        top = near_index;
+                    } else if (votes & 2u) {
+                        top = right_index;
+                    } else if (stack.empty()) {
+                        has_ray = false;
+                        if (sub == 0) store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
+                    } else {
+                        top = stack.pop();
                     }
-                    top = near_index;
-                } else if (votes & 2u) {
-                    top = right_index;
-                } else {
-                    if (stack.empty()) { has_ray = false; break; }
-                    top = stack.pop();
                 }
             }
-            if (!has_ray && sub == 0) store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
         }
         __syncwarp();
 

@@ -50,12 +50,11 @@ uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t 
     std::vector<K> sorted(n);
     for (uint32_t i = 0; i < n; ++i) { sorted[i] = keys[order[i]]; prim_ids[i] = order[i]; }
     // K4: bottom-up, leaves in order (any order is valid: the second arrival continues)
-    std::vector<NodeAux<T>> aux(2 * (size_t)n + 2);
     std::vector<int> flags(n, -1);
     uint32_t info[4] = { 0, 0, 0, 0 };
     std::memset(nodes, 0, 2 * (size_t)n * sizeof(DevNode<T>));
     BuildParams<T> p;
-    p.nodes = nodes; p.aux = aux.data(); p.flags = flags.data(); p.info = info; p.n = n;
+    p.nodes = nodes; p.flags = flags.data(); p.info = info; p.n = n;
     p.min_leaf = min_leaf; p.max_leaf = max_leaf;
     for (uint32_t i = 0; i < n; ++i) {
         T bmin[3], bmax[3];

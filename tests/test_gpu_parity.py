@@ -357,3 +357,29 @@ def test_double_precision_config5(gpu_lib, oracle):
     assert_hits_equal(hits_tuple(hits[sample]), want, "double")
     simple = bvh.intersect_rays(rays, flags=api.KERNEL_SIMPLE)
     assert (simple.view(np.uint8) == hits.view(np.uint8)).all()
+
+
+def test_reference_c_example_runs_unmodified(gpu_lib, tmp_path):
+    """The reference's own test/c_api_example.c (+ load_obj.cpp), compiled UNMODIFIED against this
+    repository's <bvh/v2/c_api/bvh.h> and linked to libbvh_c.so (oracle/Makefile target c_api_example, built
+    where the reference exists; the binary travels in tests/_build/).  It builds with bvh3f_build on the GPU
+    and traces 1024x1024 rays through bvh3f_intersect_ray + its C leaf callback: the reference's ctest
+    known answer is 1 027 152 intersections."""
+    import re
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "c_api_example")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_build/c_api_example was not prebuilt (needs the reference at build time)")
+    tris = golden("kat_cornell")["tris"]
+    obj = tmp_path / "cornell.obj"
+    with open(obj, "w") as f:
+        for t in tris:
+            for k in range(3):
+                f.write("v %.9g %.9g %.9g\n" % tuple(t[3 * k:3 * k + 3]))
+        for i in range(tris.shape[0]):
+            f.write("f %d %d %d\n" % (3 * i + 1, 3 * i + 2, 3 * i + 3))
+    out = subprocess.run([exe, str(obj), "--eye", "0", "1", "2", "--dir", "0", "0", "-1", "--up", "0", "1", "0",
+                          "-o", str(tmp_path / "render.ppm")], capture_output=True, text=True, timeout=600, cwd=tmp_path)
+    assert out.returncode == 0, out.stderr
+    m = re.search(r"(\d+) intersection\(s\) found", out.stdout)
+    assert m and int(m.group(1)) == 1027152, out.stdout

@@ -89,6 +89,8 @@ def lib() -> C.CDLL:
         f("remove_last_node").argtypes = [P]
         f("set_triangles").restype = C.c_int
         f("set_triangles").argtypes = [P, P, SZ, U]
+        f("refit_triangles").restype = C.c_int
+        f("refit_triangles").argtypes = [P, P, SZ, U]
         f("intersect_rays").restype = C.c_int
         f("intersect_rays").argtypes = [P, P, SZ, P, U]
         f("intersect_rays_stats").restype = C.c_int
@@ -204,6 +206,14 @@ class Bvh:
         if isinstance(vertices, np.ndarray):
             vertices = np.ascontiguousarray(vertices, dtype=self.dtype)
         if self._f("set_triangles")(self.handle, _addr(vertices), n, flags):
+            raise BvhError(last_error())
+
+    def refit_triangles(self, vertices, flags: int = 0) -> None:
+        """``bvhNN_refit_triangles``: GPU refit after the vertices moved (same count and order)."""
+        n = vertices.shape[0] if isinstance(vertices, np.ndarray) else self.prim_count
+        if isinstance(vertices, np.ndarray):
+            vertices = np.ascontiguousarray(vertices, dtype=self.dtype)
+        if self._f("refit_triangles")(self.handle, _addr(vertices), n, flags):
             raise BvhError(last_error())
 
     def destroy(self) -> None:

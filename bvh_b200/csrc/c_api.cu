@@ -412,8 +412,7 @@ int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bv
         if (stats) BVH_CUDA_TRY(cudaMemcpyAsync(stats + b, d_stats + 3 * b, (e - b) * sizeof(bvh_ray_stats), cudaMemcpyDeviceToHost, h->copy_out));
     }
     BVH_CUDA_TRY(cudaStreamSynchronize(h->copy_out));
-    BVH_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return 0;
+    return check_trace_status(h->dev, h->stream);
 }
 
 // reference bvh.h:220-242 / node.h:90-102: [node_count][prim_count] nodes (6 bounds + index) prim ids
@@ -575,6 +574,20 @@ BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete p
         BVH_CUDA_TRY(cudaStreamSynchronize(h->stream));                                                            \
         return 0;                                                                                                  \
     }                                                                                                              \
+    BVH_EXPORT int bvh##S##_refit_triangles(struct bvh##S* bvh, const T* vertices, size_t prim_count, unsigned flags) { \
+        auto h = H(T, bvh);                                                                                        \
+        if (!h) { set_error("null handle"); return -1; }                                                           \
+        BVH_CUDA_TRY(cudaSetDevice(h->device));                                                                    \
+        if (ensure_device(*h)) return -1;                                                                          \
+        if (prim_count != h->dev.prim_count) { set_error("refit_triangles: prim_count mismatch"); return -1; }     \
+        DeviceInput<T> dv(h->stream);                                                                              \
+        if (dv.set(vertices, 9 * prim_count, (flags & BVH_DEVICE_POINTERS) != 0)) return -1;                       \
+        if (refit_triangles<T>(h->dev, dv.ptr, h->stream)) return -1;                                              \
+        h->host_valid = false;                   /* the mirror (if any) is stale: re-download on demand */        \
+        h->nodes.clear(); h->prim_ids.clear();                                                                     \
+        BVH_CUDA_TRY(cudaStreamSynchronize(h->stream));                                                            \
+        return 0;                                                                                                  \
+    }                                                                                                              \
     BVH_EXPORT int bvh##S##_intersect_rays(struct bvh##S* bvh, const struct bvh_ray##S* rays, size_t ray_count,    \
             struct bvh_hit##S* hits, unsigned flags) {                                                             \
         return intersect_batch<T>(H(T, bvh), rays, ray_count, hits, nullptr, flags);                               \
@@ -588,8 +601,7 @@ BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete p
         auto h = H(T, bvh);                                                                                        \
         if (!h) { set_error("null handle"); return -1; }                                                           \
         BVH_CUDA_TRY(cudaSetDevice(h->device));                                                                    \
-        BVH_CUDA_TRY(cudaStreamSynchronize(h->stream));                                                            \
-        return 0;                                                                                                  \
+        return check_trace_status(h->dev, h->stream);                                                              \
     }                                                                                                              \
     BVH_EXPORT size_t bvh##S##_get_depth(struct bvh##S* bvh) {                                                     \
         auto h = H(T, bvh);                                                                                        \

@@ -49,7 +49,14 @@ template <typename T> struct DeviceBvh {
     DevTri<T>* tris = nullptr;          // nullptr until triangles are attached
     uint32_t depth = 0;                 // longest chain of inner nodes below the root (stack bound)
     bool compact = false;               // true when every slot 1..node_slots-1 is a live node
+    // two device words owned by the traversal: [0] the persistent kernels' ray cursor, [1] a sticky status
+    // word set by their watchdog (allocated on first use)
+    mutable unsigned long long* scratch = nullptr;
 };
+
+// Reads and clears the traversal status word; returns -1 (with an error message) if a watchdog fired.
+// Synchronises the stream.
+template <typename T> int check_trace_status(const DeviceBvh<T>& bvh, cudaStream_t stream);
 
 // LBVH build.  Exactly one of d_verts (n x 9) or d_bboxes (n x 6 as min3,max3) + d_centers (n x 3)
 // is given; all pointers are device pointers.  With d_verts the BVH-order PrecomputedTri array is
@@ -61,6 +68,11 @@ int build_lbvh(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const T* 
 // Attach triangles to a BVH that was built from boxes/centres or uploaded from a host mirror.
 template <typename T>
 int attach_triangles(DeviceBvh<T>& bvh, const T* d_verts, cudaStream_t stream);
+
+// GPU refit from moved vertices (same topology, same primitive order): new leaf boxes, new BVH-order
+// triangles, inner boxes recomputed bottom-up (reference Bvh::refit, bvh.h:184-218).
+template <typename T>
+int refit_triangles(DeviceBvh<T>& bvh, const T* d_verts, cudaStream_t stream);
 
 template <typename T> void release(DeviceBvh<T>& bvh, cudaStream_t stream);
 

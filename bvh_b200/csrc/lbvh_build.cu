@@ -198,6 +198,74 @@ permute_tris_kernel(const T* __restrict__ verts, const uint32_t* __restrict__ pr
     for (int k = 0; k < (int)(sizeof(DevTri<T>) / 16); ++k) d[k] = s[k];
 }
 
+// ---- GPU refit (reference Bvh::refit, bvh.h:184-218, with the leaf function recomputing the leaf
+// boxes from moved vertices — what an animation loop does every frame) ----------------------------------
+// K_r1: parent[child slot] = parent slot, for every inner node.
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+refit_parents_kernel(const DevNode<T>* __restrict__ nodes, size_t slots, uint32_t* __restrict__ parent, int* __restrict__ flags) {
+    const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x + 1;
+    if (i >= slots) return;
+    flags[i] = 0;
+    const auto index = nodes[i].index;
+    if (index_count(index) == 0) {
+        const size_t first = (size_t)index_first(index) + 1;          // device slot of the left child
+        if (first + 1 < slots) { parent[first] = (uint32_t)i; parent[first + 1] = (uint32_t)i; }
+    }
+    if (i == 1) parent[1] = 0;
+}
+
+// K_r2: one thread per leaf slot: box of its triangles (tri.h:24, in BVH order), BVH-order PrecomputedTri
+// (tri.h:35-37), then climb; the second child to arrive unions the two boxes in the reference's order
+// (left.get_bbox().extend(right.get_bbox()), bvh.h:213-217).
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+refit_leaves_kernel(DevNode<T>* __restrict__ nodes, size_t slots, const uint32_t* __restrict__ parent, int* __restrict__ flags,
+                    const T* __restrict__ verts, const uint32_t* __restrict__ prim_ids, DevTri<T>* __restrict__ tris) {
+    using R = Real<T>;
+    const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x + 1;
+    if (i >= slots) return;
+    const auto index = nodes[i].index;
+    const uint32_t count = index_count(index);
+    if (count == 0) return;
+    const uint32_t first = (uint32_t)index_first(index);
+    T bmin[3] = { R::max(), R::max(), R::max() };
+    T bmax[3] = { R::neg(R::max()), R::neg(R::max()), R::neg(R::max()) };
+    for (uint32_t k = first; k < first + count; ++k) {
+        const uint32_t id = prim_ids[k];
+        T v[9];
+        #pragma unroll
+        for (int j = 0; j < 9; ++j) v[j] = __ldg(verts + 9 * (size_t)id + j);
+        T tmin[3], tmax[3], c[3];
+        tri_bounds_center(v, tmin, tmax, c);
+        #pragma unroll
+        for (int a = 0; a < 3; ++a) { bmin[a] = robust_min(bmin[a], tmin[a]); bmax[a] = robust_max(bmax[a], tmax[a]); }
+        const DevTri<T> t = precompute_tri(v);
+        const uint4* s = reinterpret_cast<const uint4*>(&t);
+        uint4* d = reinterpret_cast<uint4*>(tris + k);
+        #pragma unroll
+        for (int j = 0; j < (int)(sizeof(DevTri<T>) / 16); ++j) d[j] = s[j];
+    }
+    write_node(nodes + i, bmin, bmax, index);
+    size_t node = i;
+    while (node != 1) {
+        const size_t p = parent[node];
+        if (p == 0) return;                                            // dead slot (collapsed subtree)
+        cuda::atomic_ref<int, cuda::thread_scope_device> flag(flags[p]);
+        if (flag.fetch_add(1, cuda::memory_order_acq_rel) == 0) return; // the sibling will carry on
+        const size_t left = (size_t)index_first(nodes[p].index) + 1;
+        const DevNode<T> l = DeviceSync::load(nodes + left), r = DeviceSync::load(nodes + left + 1);
+        T pmin[3], pmax[3];
+        #pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            pmin[a] = robust_min(l.bounds[2 * a], r.bounds[2 * a]);
+            pmax[a] = robust_max(l.bounds[2 * a + 1], r.bounds[2 * a + 1]);
+        }
+        write_node(nodes + p, pmin, pmax, nodes[p].index);
+        node = p;
+    }
+}
+
 struct Scratch {
     cudaStream_t stream;
     void* ptrs[16];
@@ -287,10 +355,26 @@ int attach_triangles(DeviceBvh<T>& bvh, const T* d_verts, cudaStream_t stream) {
     return 0;
 }
 
+template <typename T>
+int refit_triangles(DeviceBvh<T>& bvh, const T* d_verts, cudaStream_t stream) {
+    if (!bvh.nodes) { set_error("refit: no BVH"); return -1; }
+    if (!bvh.tris && device_alloc(reinterpret_cast<void**>(&bvh.tris), (size_t)bvh.prim_count * sizeof(DevTri<T>), stream)) return -1;
+    Scratch scratch(stream);
+    uint32_t* parent; int* flags;
+    if (scratch.alloc(&parent, bvh.node_slots) || scratch.alloc(&flags, bvh.node_slots)) return -1;
+    BVH_CUDA_TRY(cudaMemsetAsync(parent, 0, bvh.node_slots * sizeof(uint32_t), stream));
+    const unsigned blocks = (unsigned)((bvh.node_slots + kBlock - 1) / kBlock);
+    refit_parents_kernel<T><<<blocks, kBlock, 0, stream>>>(bvh.nodes, bvh.node_slots, parent, flags);
+    refit_leaves_kernel<T><<<blocks, kBlock, 0, stream>>>(bvh.nodes, bvh.node_slots, parent, flags, d_verts, bvh.prim_ids, bvh.tris);
+    BVH_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 template <typename T> void release(DeviceBvh<T>& bvh, cudaStream_t stream) {
     device_free(bvh.nodes, stream); bvh.nodes = nullptr;
     device_free(bvh.prim_ids, stream); bvh.prim_ids = nullptr;
     device_free(bvh.tris, stream); bvh.tris = nullptr;
+    device_free(bvh.scratch, stream); bvh.scratch = nullptr;
     bvh.prim_count = 0; bvh.node_slots = 0;
 }
 
@@ -298,6 +382,8 @@ template int build_lbvh<float>(DeviceBvh<float>&, const float*, const float*, co
 template int build_lbvh<double>(DeviceBvh<double>&, const double*, const double*, const double*, uint32_t, const BuildOptions&, cudaStream_t);
 template int attach_triangles<float>(DeviceBvh<float>&, const float*, cudaStream_t);
 template int attach_triangles<double>(DeviceBvh<double>&, const double*, cudaStream_t);
+template int refit_triangles<float>(DeviceBvh<float>&, const float*, cudaStream_t);
+template int refit_triangles<double>(DeviceBvh<double>&, const double*, cudaStream_t);
 template void release<float>(DeviceBvh<float>&, cudaStream_t);
 template void release<double>(DeviceBvh<double>&, cudaStream_t);
 

@@ -5,7 +5,7 @@
 //   rs_scan_bins   one warp per digit: exclusive scan of that digit's counts over the tiles (= keys with
 //                  the same digit in earlier tiles) and the digit's total
 //   rs_scatter     scans the 256 digit totals (= keys with a smaller digit anywhere), re-reads the tile,
-//                  ranks keys of equal digit stably (warp-level multi-split with __match_any_sync, then
+//                  ranks keys of equal digit stably (warp-level multi-split from eight ballots per key, then
 //                  a per-digit prefix across the tile's warps) and scatters
 // A tile is 256 threads x 8 keys = 2048 keys, warp-striped so every load instruction of a warp
 // reads 32 consecutive keys (128 B / 256 B, fully coalesced).  No stage is a single serial block.
@@ -116,7 +116,15 @@ rs_scatter_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ va
         const uint32_t idx = warp_base + j * 32 + lane;
         const bool valid = idx < n;
         const uint32_t d = valid ? ((uint32_t)(key[j] >> shift) & 255u) : 256u;
-        const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+        // lanes holding the same digit: AND of eight ballots (much cheaper than __match_any_sync, which
+        // iterates over the distinct values in the warp — up to 32 of them here)
+        unsigned peers = __ballot_sync(0xFFFFFFFFu, valid);
+        if (!valid) peers = ~peers;
+        #pragma unroll
+        for (int bit = 0; bit < 8; ++bit) {
+            const unsigned vote = __ballot_sync(0xFFFFFFFFu, (d >> bit) & 1u);
+            peers &= ((d >> bit) & 1u) ? vote : ~vote;
+        }
         const uint32_t r = __popc(peers & lt);
         uint32_t base = 0;
         if (valid) base = warp_hist[warp][d];

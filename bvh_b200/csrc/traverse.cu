@@ -17,6 +17,7 @@
 //
 // Both kernels execute the reference's per-ray algorithm exactly (traverse_core.cuh), so on the same
 // tree they visit nodes in the same order as the CPU code and produce bit-identical ids, t, u, v.
+#include <cstdio>
 #include <cstdlib>
 
 #include "engine.h"
@@ -89,6 +90,9 @@ template <typename T> struct TraceArgs {
     int variant;                      // 0/1: one lane per ray (direct / TMA-staged rays), 2: lane-pair kernel
     bool use_tma;                     // persistent kernel: stage ray chunks with cp.async.bulk
     uint32_t inner_budget;            // persistent kernel: inner steps per lane per round (0xFFFFFFFF = unbounded)
+    uint32_t full_mask;               // 0xFFFFFFFF passed at run time (see trace_pair_kernel)
+    uint32_t* status;                 // device word set to 1 when a watchdog fired
+    uint32_t watchdog;                // persistent kernels: trap after this many rounds of one warp (a hang becomes an error)
     int lowest_id;
 };
 
@@ -220,7 +224,12 @@ trace_persistent_kernel(TraceArgs<T> a) {
     T tmax_in = (T)0;
     U top = 0;
 
+    uint32_t rounds = 0;
     for (;;) {
+        if (++rounds > a.watchdog) {                       // a hang becomes an error (see trace_rays)
+            if (lane == 0) atomicExch(a.status, 1u);
+            return;
+        }
         // ---- refill idle lanes from the private chunk (claiming a new chunk when it runs dry) ----
         unsigned idle = __ballot_sync(kFull, !has_ray);
         while (idle != 0u && !exhausted) {
@@ -309,10 +318,11 @@ trace_persistent_kernel(TraceArgs<T> a) {
 }
 
 // Tunables of the persistent kernel; environment overrides exist for experiments only.
-struct Tuning { uint32_t inner_budget; int variant; };
+struct Tuning { uint32_t inner_budget; int variant; uint32_t watchdog; };
 const Tuning& tuning() {
     static const Tuning t = [] {
-        Tuning v { 8u, 2 };
+        Tuning v { 8u, 0, 1u << 26 };
+        if (const char* e = getenv("BVH_B200_WATCHDOG")) v.watchdog = (uint32_t)atol(e);
         if (const char* e = getenv("BVH_B200_INNER_BUDGET")) { long k = atol(e); v.inner_budget = k <= 0 ? 0xFFFFFFFFu : (uint32_t)k; }
         if (const char* e = getenv("BVH_B200_VARIANT")) v.variant = atoi(e);
         return v;
@@ -341,7 +351,12 @@ __global__ void __launch_bounds__(kTraceBlock, sizeof(T) == 4 ? 8 : 4)
 trace_pair_kernel(TraceArgs<T> a) {
     using U = typename Real<T>::UInt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr unsigned kFull = 0xFFFFFFFFu;
+    // The member mask of every warp-synchronous primitive below comes from a kernel argument (always
+    // 0xFFFFFFFF).  With a compile-time full mask ptxas elides the hardware warp barrier wherever it
+    // believes the warp is already converged and keeps the round counter in a uniform register; on B200
+    // that produced occasional hangs of this kernel (a warp split in two that never rejoined, found with
+    // the watchdog below).  A run-time mask forces a real WARPSYNC in front of each vote / shuffle.
+    const unsigned kFull = a.full_mask;
     constexpr unsigned kEven = 0x55555555u;
     const unsigned lane = threadIdx.x & 31u, sub = lane & 1u, pair_shift = lane & ~1u;
     const unsigned lt_mask = (1u << pair_shift) - 1u;                  // pairs before this one
@@ -360,7 +375,15 @@ trace_pair_kernel(TraceArgs<T> a) {
     T tmax_in = (T)0;
     U top = 0;
 
+    // `lane_zero` is 0 for every thread (blocks have 128 threads) but not provably so: adding it keeps the
+    // round counters in ordinary per-lane registers instead of a warp-uniform register shared by the warp.
+    const uint32_t lane_zero = threadIdx.x >> 10;
+    uint32_t rounds = lane_zero;
     for (;;) {
+        if (++rounds > a.watchdog) {                       // a hang becomes an error (see trace_rays)
+            if (lane == 0) atomicExch(a.status, 1u);
+            return;
+        }
         // ---- refill idle pairs -----------------------------------------------------------------------
         unsigned idle = __ballot_sync(kFull, !has_ray) & kEven;
         while (idle != 0u && !exhausted) {
@@ -399,47 +422,41 @@ trace_pair_kernel(TraceArgs<T> a) {
 
         // ---- inner phase (bounded, WARP-UNIFORM trip count) ----------------------------------------------
         // Every lane runs every round of this loop so that the pair exchange can use full-mask warp
-        // primitives (a pair-specific mask would make the hardware execute the shuffle once per pair);
-        // lanes that already hold a leaf, or no ray, are predicated off inside a round.
+        // primitives (a pair-specific mask would make the hardware execute the shuffle once per pair).
+        // The body is written without data-dependent branches: lanes that hold a leaf or no ray fetch the
+        // root pair and discard the result, pushes / pops / retirement are predicated.
         {
-            uint32_t budget = inner_budget;
-            while (budget != 0) {
-                --budget;
+            bool retired = false;
+            for (uint32_t budget = inner_budget + lane_zero; budget != 0; --budget) {
                 const bool active = has_ray && index_count(top) == 0;
                 if (__ballot_sync(kFull, active) == 0u) break;
-                T b[6]; U my_index = 0;
-                T t0 = (T)0, t1 = (T)-1;
-                if (active) {
-                    load_node(a.nodes + (size_t)index_first(top) + 1 + sub, b, my_index);
-                    node_test<T, kRobust>(b, r, t0, t1);
-                }
+                T b[6]; U my_index;
+                const size_t pair_slot = active ? (size_t)index_first(top) + 1 : (size_t)1;
+                load_node(a.nodes + pair_slot + sub, b, my_index);
+                T t0, t1;
+                node_test<T, kRobust>(b, r, t0, t1);
                 const bool my_hit = active && t0 <= t1;
                 const unsigned votes = (__ballot_sync(kFull, my_hit) >> pair_shift) & 3u;
                 const T other_t0 = shfl_xor1<T>(kFull, t0);
                 const U other_index = shfl_xor1<U>(kFull, my_index);
-                if (active) {
-                    const U left_index = sub ? other_index : my_index, right_index = sub ? my_index : other_index;
-                    const T l0 = sub ? other_t0 : t0, r0 = sub ? t0 : other_t0;
-                    if (votes & 1u) {                                       // hit_left (bvh.h:138-147)
-                        U near_index = left_index;
-                        if (votes & 2u) {
-                            U far_index = right_index;
-                            if (!kAny && l0 > r0) { near_index = right_index; far_index = left_index; }
-                            stack.push(far_index);
-                        }
-                        top = near_index;
-                    } else if (votes & 2u) {
-                        top = right_index;
-                    } else if (stack.empty()) {
-                        has_ray = false;
-                        if (sub == 0) store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
-                    } else {
-                        top = stack.pop();
-                    }
-                }
+                const U left_index = sub ? other_index : my_index, right_index = sub ? my_index : other_index;
+                const T l0 = sub ? other_t0 : t0, r0 = sub ? t0 : other_t0;
+                const bool hit_left = (votes & 1u) != 0, hit_right = (votes & 2u) != 0;
+                const bool swap_order = !kAny && l0 > r0;                   // bvh.h:180
+                const U near_index = hit_left ? ((hit_right && swap_order) ? right_index : left_index) : right_index;
+                const U far_index = swap_order ? left_index : right_index;
+                const bool do_push = active && hit_left && hit_right;
+                const bool do_pop = active && !hit_left && !hit_right;
+                if (do_push) stack.push(far_index);
+                U next = near_index;
+                const bool finished = do_pop && stack.empty();
+                if (do_pop && !finished) next = stack.pop();
+                if (active) top = next;
+                if (finished) { has_ray = false; retired = true; }
             }
+            if (retired && sub == 0) store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
         }
-        __syncwarp();
+        __syncwarp(kFull);
 
         // ---- leaf phase (both lanes of the pair run it redundantly) -------------------------------------
         if (has_ray && index_count(top) != 0) {
@@ -528,23 +545,42 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     args.stack_entries = entries;
     args.next_ray = nullptr;
     args.inner_budget = tuning().inner_budget;
+    args.watchdog = tuning().watchdog;
+    args.full_mask = 0xFFFFFFFFu;
     args.variant = (flags & kTracePair) ? 2 : ((flags & (kTraceNoTma | kTraceTma)) ? 0 : tuning().variant);
     args.use_tma = (flags & kTraceTma) ? true : ((flags & kTraceNoTma) ? false : tuning().variant == 1);
     const bool simple = (flags & kTraceSimple) != 0, stats = d_ray_stats != nullptr;
-    void* cursor = nullptr;
-    if (!simple && !stats) {
-        if (device_alloc(&cursor, sizeof(unsigned long long), stream)) return -1;
-        args.next_ray = static_cast<unsigned long long*>(cursor);
+    if (!bvh.scratch) {
+        void* p = nullptr;
+        if (device_alloc(&p, 2 * sizeof(unsigned long long), stream)) return -1;
+        bvh.scratch = static_cast<unsigned long long*>(p);
+        BVH_CUDA_TRY(cudaMemsetAsync(bvh.scratch, 0, 2 * sizeof(unsigned long long), stream));
     }
+    args.next_ray = bvh.scratch;
+    args.status = reinterpret_cast<uint32_t*>(bvh.scratch + 1);
     int rc;
     const bool any = (flags & kTraceAnyHit) != 0, robust = (flags & kTraceRobust) != 0;
     if (any) rc = robust ? launch<T, true, true>(args, simple, stats, bvh.device, stream)
                          : launch<T, true, false>(args, simple, stats, bvh.device, stream);
     else     rc = robust ? launch<T, false, true>(args, simple, stats, bvh.device, stream)
                          : launch<T, false, false>(args, simple, stats, bvh.device, stream);
-    if (cursor) device_free(cursor, stream);
     return rc;
 }
+
+template <typename T> int check_trace_status(const DeviceBvh<T>& bvh, cudaStream_t stream) {
+    if (!bvh.scratch) { BVH_CUDA_TRY(cudaStreamSynchronize(stream)); return 0; }
+    unsigned long long status = 0;
+    BVH_CUDA_TRY(cudaMemcpyAsync(&status, bvh.scratch + 1, sizeof status, cudaMemcpyDeviceToHost, stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (status != 0) {
+        BVH_CUDA_TRY(cudaMemsetAsync(bvh.scratch + 1, 0, sizeof status, stream));
+        set_error("trace: the traversal kernel's watchdog fired (a warp exceeded its round limit); results are incomplete");
+        return -1;
+    }
+    return 0;
+}
+template int check_trace_status<float>(const DeviceBvh<float>&, cudaStream_t);
+template int check_trace_status<double>(const DeviceBvh<double>&, cudaStream_t);
 
 template int trace_rays<float>(const DeviceBvh<float>&, const DevRay<float>*, DevHit<float>*, size_t, unsigned, uint32_t*, cudaStream_t);
 template int trace_rays<double>(const DeviceBvh<double>&, const DevRay<double>*, DevHit<double>*, size_t, unsigned, uint32_t*, cudaStream_t);

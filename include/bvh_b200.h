@@ -80,6 +80,9 @@ BVH_API void bvh_host_free(void* ptr);
     /* Attach triangles (original order) to a BVH made by bvhNN_build / bvhNN_load so that it can be   \
        traced in batches; precomputes and permutes them into BVH order on the device. */                \
     BVH_API int bvh##S##_set_triangles(struct bvh##S* bvh, const T* vertices, size_t prim_count, unsigned flags); \
+    /* Refit on the GPU after the vertices moved (same triangle count and order): recomputes leaf boxes,    \
+       inner boxes (reference Bvh::refit, bvh.h:184-218) and the BVH-order triangles; topology unchanged. */ \
+    BVH_API int bvh##S##_refit_triangles(struct bvh##S* bvh, const T* vertices, size_t prim_count, unsigned flags); \
     /* Intersect ray_count rays; hits[i] answers rays[i]. */                                            \
     BVH_API int bvh##S##_intersect_rays(struct bvh##S* bvh, const struct bvh_ray##S* rays, size_t ray_count, \
                                         struct bvh_hit##S* hits, unsigned flags);                       \

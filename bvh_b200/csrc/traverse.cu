@@ -321,7 +321,7 @@ trace_persistent_kernel(TraceArgs<T> a) {
 struct Tuning { uint32_t inner_budget; int variant; uint32_t watchdog; };
 const Tuning& tuning() {
     static const Tuning t = [] {
-        Tuning v { 8u, 0, 1u << 26 };
+        Tuning v { 12u, 1, 1u << 26 };
         if (const char* e = getenv("BVH_B200_WATCHDOG")) v.watchdog = (uint32_t)atol(e);
         if (const char* e = getenv("BVH_B200_INNER_BUDGET")) { long k = atol(e); v.inner_budget = k <= 0 ? 0xFFFFFFFFu : (uint32_t)k; }
         if (const char* e = getenv("BVH_B200_VARIANT")) v.variant = atoi(e);

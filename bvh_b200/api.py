@@ -24,6 +24,7 @@ KERNEL_SIMPLE = 1 << 8
 KERNEL_NO_TMA = 1 << 9
 KERNEL_TMA = 1 << 10
 KERNEL_PAIR = 1 << 11
+KERNEL_WIDE = 1 << 12
 KERNELS = (KERNEL_PAIR, KERNEL_NO_TMA, KERNEL_TMA, KERNEL_SIMPLE)
 INVALID_ID = 0xFFFFFFFF
 

@@ -73,7 +73,7 @@ template <typename T> struct Handle {
     uint64_t synced_ids_hash = 0;             // hash of prim_ids the device triangles were permuted with
 
     // staging and side streams for host-pointer batches
-    static constexpr size_t kMaxChunks = 16;
+    static constexpr size_t kMaxChunks = 8;       // measured: 8 chunks of a 10M-ray batch overlap best
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t events[1 + 2 * kMaxChunks] = {};
     void* d_rays = nullptr; size_t d_rays_bytes = 0;
@@ -218,6 +218,7 @@ template <typename T> int upload_mirror(Handle<T>& h) {
     BVH_CUDA_TRY(cudaMemcpyAsync(h.dev.nodes, dev_nodes.data(), dev_nodes.size() * sizeof(DevNode<T>), cudaMemcpyHostToDevice, h.stream));
     BVH_CUDA_TRY(cudaMemcpyAsync(h.dev.prim_ids, ids.data(), ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h.stream));
     BVH_CUDA_TRY(cudaStreamSynchronize(h.stream));
+    if (rebuild_wide(h.dev, h.stream)) return -1;
     h.device_valid = true;
     h.maybe_edited = false;
     h.synced_hash = mirror_hash(h);
@@ -373,6 +374,7 @@ int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bv
     if (flags & BVH_KERNEL_NO_TMA) tf |= kTraceNoTma;
     if (flags & BVH_KERNEL_TMA) tf |= kTraceTma;
     if (flags & BVH_KERNEL_PAIR) tf |= kTracePair;
+    if (flags & BVH_KERNEL_WIDE) tf |= kTraceWide;
     if (flags & BVH_DEVICE_POINTERS) {
         return trace_rays<T>(h->dev, reinterpret_cast<const DevRay<T>*>(rays), reinterpret_cast<DevHit<T>*>(hits), n, tf,
                              reinterpret_cast<uint32_t*>(stats), h->stream);
@@ -391,7 +393,7 @@ int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bv
     auto d_rays = static_cast<DevRay<T>*>(h->d_rays);
     auto d_hits = static_cast<DevHit<T>*>(h->d_hits);
     auto d_stats = static_cast<uint32_t*>(h->d_stats);
-    constexpr size_t kMinChunk = 1u << 18;                   // 256K rays = 8 MB of float rays
+    constexpr size_t kMinChunk = 1u << 20;                   // 1M rays = 32 MB of float rays per chunk
     size_t chunks = n / kMinChunk;
     if (const char* e = getenv("BVH_B200_E2E_CHUNKS")) chunks = (size_t)atol(e);      // experiments only
     if (chunks < 1) chunks = 1;

@@ -11,6 +11,8 @@
 
 namespace bvhb200 {
 
+struct WideNode;
+
 // Error plumbing: every engine call returns 0 on success; the message of the last failure on the
 // calling thread is kept for bvh_last_error().
 void set_error(const std::string& msg);
@@ -52,7 +54,14 @@ template <typename T> struct DeviceBvh {
     // two device words owned by the traversal: [0] the persistent kernels' ray cursor, [1] a sticky status
     // word set by their watchdog (allocated on first use)
     mutable unsigned long long* scratch = nullptr;
+    // compressed 4-wide companion tree for the fast traversal path (wide_bvh.cuh); float trees only
+    WideNode* wide = nullptr;
+    uint32_t wide_depth = 0;            // number of wide levels (bounds the fast path's stack)
+    uint32_t wide_count = 0;
 };
+
+// (Re)derives the wide tree from the binary one, e.g. after an upload from the host mirror.
+template <typename T> int rebuild_wide(DeviceBvh<T>& bvh, cudaStream_t stream);
 
 // Reads and clears the traversal status word; returns -1 (with an error message) if a watchdog fired.
 // Synchronises the stream.
@@ -84,6 +93,7 @@ enum TraceFlags : unsigned {
     kTraceNoTma       = 1u << 9,   // persistent one-lane-per-ray kernel, rays read with streaming loads
     kTraceTma         = 1u << 10,  // persistent one-lane-per-ray kernel, ray chunks staged by bulk async copy (TMA)
     kTracePair        = 1u << 11,  // persistent lane-pair kernel (two lanes per ray)
+    kTraceWide        = 1u << 12,  // persistent kernel over the compressed 4-wide tree
 };
 
 // Batched traversal; all pointers are device pointers.  ray_stats (nullable): n x 3 uint32

@@ -11,11 +11,14 @@
 //                             that links parents, unions boxes (bvh.h:213-217), collapses subtrees into
 //                             leaves by SAH (split_heuristic.h:30-38) and stores each node once, in its
 //                             final reference-layout slot.
+#include <cstdlib>
+
 #include <cuda/atomic>
 
 #include "build_core.cuh"
 #include "engine.h"
 #include "radix_sort.cuh"
+#include "wide_bvh.cuh"
 
 namespace bvhb200 {
 
@@ -266,6 +269,73 @@ refit_leaves_kernel(DevNode<T>* __restrict__ nodes, size_t slots, const uint32_t
     }
 }
 
+// ---- collapse of the binary tree into the compressed 4-wide tree (wide_bvh.cuh) ------------------------
+// Level-synchronous: the frontier of level L holds (device slot of a binary inner node, index of the wide
+// node that represents it).  Each item gathers the node's two children, replaces the larger-area inner
+// ones by their own children until four slots are filled, quantises the slot boxes against their union
+// and appends the inner slots to the frontier of level L+1.  counters[0] = next free wide node,
+// counters[1 + L] = size of frontier L, counters[63] = number of non-empty levels.
+constexpr int kWideMaxLevels = 60;
+
+__global__ void __launch_bounds__(kBlock)
+wide_collapse_kernel(const DevNode<float>* __restrict__ nodes, WideNode* __restrict__ wide,
+                     const uint2* __restrict__ frontier_in, uint2* __restrict__ frontier_out,
+                     uint32_t* __restrict__ counters, int level) {
+    const uint32_t count = counters[1 + level];
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= count) return;
+    if (i == 0) atomicMax(&counters[63], (uint32_t)level + 1);
+    const uint2 item = frontier_in[i];
+    uint32_t slot[4];
+    const int used = wide_gather_children(nodes, item.x, slot);
+    WideNode w;
+    bool is_inner[4];
+    wide_encode(nodes, slot, used, w, is_inner);
+    for (int c = 0; c < used; ++c) {
+        if (!is_inner[c]) continue;
+        const uint32_t wide_index = atomicAdd(&counters[0], 1u);
+        w.child[c] = wide_index << kPrimCountBits;
+        frontier_out[atomicAdd(&counters[2 + level], 1u)] = make_uint2(slot[c], wide_index);
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(&w);
+    uint4* dst = reinterpret_cast<uint4*>(wide + item.y);
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = src[k];
+}
+
+__global__ void wide_init_kernel(uint2* frontier, uint32_t* counters) {
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) counters[k] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) { frontier[0] = make_uint2(1u, 0u); counters[0] = 1; counters[1] = 1; }
+}
+
+// Builds (or rebuilds, after a refit) bvh.wide from the binary tree.  `levels` bounds the number of
+// collapse rounds (binary depth + 1 is always enough).  Leaves the number of wide levels in counters[63]
+// of the returned scratch, which the caller reads back together with its other results.
+int build_wide(DeviceBvh<float>& bvh, uint32_t levels, uint32_t* d_counters, uint2* d_frontier_a, uint2* d_frontier_b,
+               cudaStream_t stream) {
+    const uint32_t n = bvh.prim_count;
+    if (!bvh.wide && device_alloc(reinterpret_cast<void**>(&bvh.wide), (size_t)(n ? n : 1) * sizeof(WideNode), stream)) return -1;
+    wide_init_kernel<<<1, 64, 0, stream>>>(d_frontier_a, d_counters);
+    if (levels > (uint32_t)kWideMaxLevels) levels = kWideMaxLevels;
+    uint64_t bound = 1;
+    for (uint32_t level = 0; level < levels; ++level) {
+        const uint64_t items = bound < n ? bound : n;                     // frontier L has at most min(4^L, n) items
+        const unsigned blocks = (unsigned)((items + kBlock - 1) / kBlock);
+        wide_collapse_kernel<<<blocks, kBlock, 0, stream>>>(bvh.nodes, bvh.wide, (level & 1) ? d_frontier_b : d_frontier_a,
+                                                            (level & 1) ? d_frontier_a : d_frontier_b, d_counters, (int)level);
+        if (bound < n) bound *= 4;
+    }
+    BVH_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+inline int build_wide(DeviceBvh<double>&, uint32_t, uint32_t*, uint2*, uint2*, cudaStream_t) { return 0; }
+
+bool wide_enabled() {
+    static const bool on = [] { const char* e = getenv("BVH_B200_WIDE"); return !e || atoi(e) != 0; }();
+    return on;
+}
+
 struct Scratch {
     cudaStream_t stream;
     void* ptrs[16];
@@ -280,6 +350,23 @@ struct Scratch {
         return 0;
     }
 };
+
+// Collapses the binary tree of `bvh` into its wide companion (float trees only) and records the wide
+// depth.  Synchronises the stream.
+template <typename T> int make_wide_tree(DeviceBvh<T>& bvh, cudaStream_t stream) {
+    if (sizeof(T) != 4 || !wide_enabled()) return 0;
+    Scratch scratch(stream);
+    uint32_t* counters; uint2* fa; uint2* fb;
+    const size_t cap = bvh.prim_count ? bvh.prim_count : 1;
+    if (scratch.alloc(&counters, 64) || scratch.alloc(&fa, cap) || scratch.alloc(&fb, cap)) return -1;
+    if (build_wide(bvh, bvh.depth + 1, counters, fa, fb, stream)) return -1;
+    uint32_t host_counters[64];
+    BVH_CUDA_TRY(cudaMemcpyAsync(host_counters, counters, sizeof(host_counters), cudaMemcpyDeviceToHost, stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(stream));
+    bvh.wide_depth = host_counters[63];
+    bvh.wide_count = host_counters[0];
+    return 0;
+}
 
 template <typename T, typename K>
 int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const T* d_centers,
@@ -324,6 +411,7 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     BVH_CUDA_TRY(cudaMemcpyAsync(host_info, info, sizeof(host_info), cudaMemcpyDeviceToHost, stream));
     BVH_CUDA_TRY(cudaStreamSynchronize(stream));
     out.depth = host_info[0];
+    if (make_wide_tree(out, stream)) return -1;
     out.compact = false;
     return 0;
 }
@@ -367,7 +455,7 @@ int refit_triangles(DeviceBvh<T>& bvh, const T* d_verts, cudaStream_t stream) {
     refit_parents_kernel<T><<<blocks, kBlock, 0, stream>>>(bvh.nodes, bvh.node_slots, parent, flags);
     refit_leaves_kernel<T><<<blocks, kBlock, 0, stream>>>(bvh.nodes, bvh.node_slots, parent, flags, d_verts, bvh.prim_ids, bvh.tris);
     BVH_CUDA_TRY(cudaGetLastError());
-    return 0;
+    return make_wide_tree(bvh, stream);
 }
 
 template <typename T> void release(DeviceBvh<T>& bvh, cudaStream_t stream) {
@@ -375,6 +463,7 @@ template <typename T> void release(DeviceBvh<T>& bvh, cudaStream_t stream) {
     device_free(bvh.prim_ids, stream); bvh.prim_ids = nullptr;
     device_free(bvh.tris, stream); bvh.tris = nullptr;
     device_free(bvh.scratch, stream); bvh.scratch = nullptr;
+    device_free(bvh.wide, stream); bvh.wide = nullptr;
     bvh.prim_count = 0; bvh.node_slots = 0;
 }
 
@@ -382,6 +471,9 @@ template int build_lbvh<float>(DeviceBvh<float>&, const float*, const float*, co
 template int build_lbvh<double>(DeviceBvh<double>&, const double*, const double*, const double*, uint32_t, const BuildOptions&, cudaStream_t);
 template int attach_triangles<float>(DeviceBvh<float>&, const float*, cudaStream_t);
 template int attach_triangles<double>(DeviceBvh<double>&, const double*, cudaStream_t);
+template <typename T> int rebuild_wide(DeviceBvh<T>& bvh, cudaStream_t stream) { return make_wide_tree(bvh, stream); }
+template int rebuild_wide<float>(DeviceBvh<float>&, cudaStream_t);
+template int rebuild_wide<double>(DeviceBvh<double>&, cudaStream_t);
 template int refit_triangles<float>(DeviceBvh<float>&, const float*, cudaStream_t);
 template int refit_triangles<double>(DeviceBvh<double>&, const double*, cudaStream_t);
 template void release<float>(DeviceBvh<float>&, cudaStream_t);

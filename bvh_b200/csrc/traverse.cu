@@ -22,6 +22,7 @@
 
 #include "engine.h"
 #include "traverse_core.cuh"
+#include "wide_bvh.cuh"
 
 namespace bvhb200 {
 
@@ -87,6 +88,8 @@ template <typename T> struct TraceArgs {
     unsigned long long* next_ray;     // persistent kernel: global ray cursor
     uint32_t* ray_stats;              // statistics variant: n x 3
     uint32_t stack_entries;
+    const WideNode* wide;             // compressed 4-wide tree (float only) or nullptr
+    uint32_t wide_entries;            // stack entries per thread for the wide kernel
     int variant;                      // 0/1: one lane per ray (direct / TMA-staged rays), 2: lane-pair kernel
     bool use_tma;                     // persistent kernel: stage ray chunks with cp.async.bulk
     uint32_t inner_budget;            // persistent kernel: inner steps per lane per round (0xFFFFFFFF = unbounded)
@@ -318,10 +321,11 @@ trace_persistent_kernel(TraceArgs<T> a) {
 }
 
 // Tunables of the persistent kernel; environment overrides exist for experiments only.
-struct Tuning { uint32_t inner_budget; int variant; uint32_t watchdog; };
+struct Tuning { uint32_t inner_budget; int variant; uint32_t watchdog; bool use_wide; };
 const Tuning& tuning() {
     static const Tuning t = [] {
-        Tuning v { 12u, 1, 1u << 26 };
+        Tuning v { 12u, 1, 1u << 26, false };
+        if (const char* e = getenv("BVH_B200_USE_WIDE")) v.use_wide = atoi(e) != 0;
         if (const char* e = getenv("BVH_B200_WATCHDOG")) v.watchdog = (uint32_t)atol(e);
         if (const char* e = getenv("BVH_B200_INNER_BUDGET")) { long k = atol(e); v.inner_budget = k <= 0 ? 0xFFFFFFFFu : (uint32_t)k; }
         if (const char* e = getenv("BVH_B200_VARIANT")) v.variant = atoi(e);
@@ -473,11 +477,136 @@ trace_pair_kernel(TraceArgs<T> a) {
 }
 
 
+// ---- wide kernel: persistent traversal of the compressed 4-wide tree (wide_bvh.cuh) -------------------
+// One lane per ray, same refill / bounded-round structure as trace_persistent_kernel.  An inner step
+// fetches ONE 64-byte node (two 256-bit loads from the same line), dequantises four child boxes straight
+// into ray-parameter space (t = q * (cell * inv_dir) + (origin - org) * inv_dir, far planes with the
+// padded inverse direction so that rounding can only enlarge a box), visits the hit children nearest
+// first and pushes the others far-to-near.  Leaves are the binary tree's leaves: same BVH-order triangle
+// array, same exact triangle test and canonical tie-break as every other kernel.
+template <bool kAny>
+__global__ void __launch_bounds__(kTraceBlock, 8)
+trace_wide_kernel(TraceArgs<float> a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    SmemStack<uint32_t> stack { reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x, kTraceBlock, 0 };
+    const uint32_t inner_budget = a.inner_budget;
+
+    unsigned long long chunk_pos = 0, chunk_end = 0;
+    bool exhausted = false;
+    bool has_ray = false;
+    unsigned long long ray_index = 0;
+    RayCtx<float> r;                   // aux = padded inverse direction (far planes)
+    HitState<float> hit;
+    float tmax_in = 0.f;
+    uint32_t top = 0;
+
+    uint32_t rounds = 0;
+    for (;;) {
+        if (++rounds > a.watchdog) {
+            if (lane == 0) atomicExch(a.status, 1u);
+            return;
+        }
+        unsigned idle = __ballot_sync(kFull, !has_ray);
+        while (idle != 0u && !exhausted) {
+            if (chunk_pos == chunk_end) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.next_ray, (unsigned long long)kChunkRays);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= a.n) { exhausted = true; break; }
+                chunk_pos = base;
+                chunk_end = base + kChunkRays < a.n ? base + kChunkRays : a.n;
+            }
+            const unsigned avail = (unsigned)(chunk_end - chunk_pos), want = __popc(idle);
+            const unsigned take = want < avail ? want : avail;
+            const unsigned rank = __popc(idle & lt_mask);
+            if (!has_ray && rank < take) {
+                ray_index = chunk_pos + rank;
+                load_ray(a.rays, ray_index, r);
+                tmax_in = r.tmax;
+                hit.slot = kInvalidId; hit.t = r.tmax; hit.u = 0.f; hit.v = 0.f;
+                if (ray_interval_is_nan(r)) {
+                    store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
+                } else {
+                    wide_ray_setup(r);
+                    top = 0;                                    // wide node 0, inner
+                    stack.sp = 0;
+                    has_ray = true;
+                }
+            }
+            chunk_pos += take;
+            idle = __ballot_sync(kFull, !has_ray);
+        }
+        if (__ballot_sync(kFull, has_ray) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---- inner phase ----------------------------------------------------------------------------
+        if (has_ray) {
+            uint32_t budget = inner_budget;
+            while (index_count(top) == 0 && budget != 0) {
+                --budget;
+                uint32_t w[16];
+                {
+                    uint32_t w0[8], w1[8];
+                    const WideNode* node = a.wide + (top >> kPrimCountBits);
+                    ldg256(node, w0);
+                    ldg256(reinterpret_cast<const unsigned char*>(node) + 32, w1);
+                    #pragma unroll
+                    for (int k = 0; k < 8; ++k) { w[k] = w0[k]; w[8 + k] = w1[k]; }
+                }
+                if (!wide_step<kAny>(w, r, top, stack)) { has_ray = false; break; }
+            }
+            if (!has_ray) store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
+        }
+        __syncwarp();
+
+        // ---- leaf phase -----------------------------------------------------------------------------
+        if (has_ray && index_count(top) != 0) {
+            leaf_step<float>(a.tris, a.prim_ids, true, top, r, hit, nullptr);
+            if ((kAny && hit.slot != kInvalidId) || stack.empty()) {
+                store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
+                has_ray = false;
+            } else {
+                top = stack.pop();
+            }
+        }
+        __syncwarp();
+    }
+}
+
+
 template <typename KernelT>
 int configure_smem(KernelT kernel, size_t smem_bytes) {
     if (smem_bytes > 48 * 1024)
         BVH_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     return 0;
+}
+
+template <typename T, bool kAny>
+int launch_wide(const TraceArgs<T>& args, int device, cudaStream_t stream) {
+    if constexpr (sizeof(T) == 4) {
+        auto kernel = trace_wide_kernel<kAny>;
+        const size_t smem = (size_t)args.wide_entries * kTraceBlock * sizeof(uint32_t);
+        if (smem > 200 * 1024) { set_error("trace: wide tree too deep for the shared-memory stack"); return -1; }
+        if (configure_smem(kernel, smem)) return -1;
+        int sm_count = 148, per_sm = 1;
+        BVH_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceBlock, smem));
+        if (per_sm < 1) per_sm = 1;
+        unsigned long long grid = (unsigned long long)sm_count * per_sm;
+        const unsigned long long max_useful = (args.n + 31) / 32 / (kTraceBlock / 32) + 1;
+        if (grid > max_useful) grid = max_useful;
+        BVH_CUDA_TRY(cudaMemsetAsync(args.next_ray, 0, sizeof(unsigned long long), stream));
+        kernel<<<(unsigned)grid, kTraceBlock, smem, stream>>>(args);
+        return 0;
+    } else {
+        set_error("trace: the wide kernel is float-only");
+        return -1;
+    }
 }
 
 template <typename T, bool kAny, bool kRobust>
@@ -495,6 +624,8 @@ int launch(const TraceArgs<T>& args, bool simple, bool stats, int device, cudaSt
             if (configure_smem(trace_simple_kernel<T, kAny, kRobust, false>, smem)) return -1;
             trace_simple_kernel<T, kAny, kRobust, false><<<(unsigned)blocks, kTraceBlock, smem, stream>>>(args);
         }
+    } else if (args.variant == 3) {
+        if (launch_wide<T, kAny>(args, device, stream)) return -1;
     } else if (args.variant == 2) {
         auto kernel = trace_pair_kernel<T, kAny, kRobust>;
         const size_t pair_smem = smem / 2;                                     // one stack per lane pair
@@ -548,6 +679,18 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     args.watchdog = tuning().watchdog;
     args.full_mask = 0xFFFFFFFFu;
     args.variant = (flags & kTracePair) ? 2 : ((flags & (kTraceNoTma | kTraceTma)) ? 0 : tuning().variant);
+    // the wide (compressed 4-wide) path: float, canonical tie-break, fast slab test, no statistics
+    args.wide = nullptr; args.wide_entries = 0;
+    if constexpr (sizeof(T) == 4) {
+        const bool explicit_binary = (flags & (kTracePair | kTraceNoTma | kTraceTma | kTraceSimple)) != 0;
+        const bool order_sensitive = (flags & (kTraceLastVisited | kTraceRobust)) != 0 || d_ray_stats != nullptr;
+        if (bvh.wide && !order_sensitive && ((flags & kTraceWide) || (!explicit_binary && tuning().use_wide))) {
+            args.wide = bvh.wide;
+            uint32_t e = 3 * bvh.wide_depth + 2;
+            args.wide_entries = (e + 7u) & ~7u;
+            args.variant = 3;
+        }
+    }
     args.use_tma = (flags & kTraceTma) ? true : ((flags & kTraceNoTma) ? false : tuning().variant == 1);
     const bool simple = (flags & kTraceSimple) != 0, stats = d_ray_stats != nullptr;
     if (!bvh.scratch) {

@@ -21,11 +21,7 @@ template <typename T> struct NodePair {
     typename Real<T>::UInt li, ri;
 };
 
-#if defined(__CUDA_ARCH__)
-// sm_100 has 256-bit global loads (SASS LDG.E.256): a node is ONE load, a sibling pair two, from one
-// naturally aligned 64-byte (float) / 128-byte (double) block, through the read-only path.  Halving the
-// number of load instructions matters because with divergent rays every load costs one L1 tag lookup per
-// distinct line touched by the warp (profiles/: the traversal is L1-tag bound, not DRAM bound).
+#if defined(__CUDACC__)
 __device__ __forceinline__ void ldg256(const void* p, uint32_t (&w)[8]) {
     asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
@@ -33,6 +29,13 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&w)[8]) {
 __device__ __forceinline__ void ldg256(const void* p, unsigned long long (&w)[4]) {
     asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(p));
 }
+#endif
+
+#if defined(__CUDA_ARCH__)
+// sm_100 has 256-bit global loads (SASS LDG.E.256): a node is ONE load, a sibling pair two, from one
+// naturally aligned 64-byte (float) / 128-byte (double) block, through the read-only path.  Halving the
+// number of load instructions matters because with divergent rays every load costs one L1 tag lookup per
+// distinct line touched by the warp (profiles/: the traversal is L1-tag bound, not DRAM bound).
 __device__ __forceinline__ void load_pair(const DevNode<float>* __restrict__ p, NodePair<float>& o) {
     uint32_t a[8], b[8];
     ldg256(p, a);

@@ -50,6 +50,9 @@ class HostEmul:
             getattr(L, f"emul_trace{s}").argtypes = [P, P, P, P, C.c_size_t, C.c_uint, P, P, P, P, P]
             getattr(L, f"emul_from_reference{s}").argtypes = [P, P, C.c_size_t, P]
             getattr(L, f"emul_precompute{s}").argtypes = [P, P, C.c_size_t, P]
+        L.emul_wide_build.restype = C.c_size_t
+        L.emul_wide_build.argtypes = [P, P, C.c_size_t, P]
+        L.emul_wide_trace.argtypes = [P, P, P, P, C.c_size_t, C.c_uint, P, P, P, P, P]
         L.emul_morton30.restype = C.c_uint32
         L.emul_morton30.argtypes = [C.c_uint32] * 3
         L.emul_morton63.restype = C.c_uint64
@@ -91,6 +94,25 @@ class HostEmul:
         dtris = aligned_zeros((ids.shape[0], 12), dtype)
         getattr(self.lib, f"emul_precompute{s}")(_ptr(np.ascontiguousarray(tris)), _ptr(ids), ids.shape[0], _ptr(dtris))
         return dict(nodes=nodes, prim_ids=ids, tris=dtris, depth=None, dtype=dtype, n=ids.shape[0])
+
+    def wide_build(self, tree):
+        """Collapse the (float) binary tree into the compressed 4-wide tree; returns (wide nodes, levels)."""
+        n = tree["n"]
+        wide = aligned_zeros((max(n, 1), 16), np.uint32)
+        levels = C.c_uint32(0)
+        count = self.lib.emul_wide_build(_ptr(tree["nodes"]), _ptr(wide), wide.shape[0], C.byref(levels))
+        assert count <= wide.shape[0]
+        return wide[:count], levels.value
+
+    def wide_trace(self, tree, wide, rays, flags):
+        rays = np.ascontiguousarray(rays, dtype=np.float32)
+        m = rays.shape[0]
+        ids = np.zeros(m, np.uint32)
+        t, u, v = (np.zeros(m, np.float32) for _ in range(3))
+        steps = np.zeros(m, np.uint32)
+        self.lib.emul_wide_trace(_ptr(wide), _ptr(tree["tris"]), _ptr(tree["prim_ids"]), _ptr(rays), m, flags,
+                                 _ptr(ids), _ptr(t), _ptr(u), _ptr(v), _ptr(steps))
+        return ids, t, u, v, steps
 
     def trace(self, tree, rays, flags):
         dtype = tree["dtype"]

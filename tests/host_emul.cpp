@@ -13,6 +13,7 @@
 
 #include "build_core.cuh"
 #include "traverse_core.cuh"
+#include "wide_bvh.cuh"
 
 using namespace bvhb200;
 
@@ -139,6 +140,70 @@ void emul_from_reference(const T* bounds, const uint64_t* index_values, size_t n
     }
 }
 
+// wide tree: the same collapse the device runs level by level (lbvh_build.cu wide_collapse_kernel), sequentially
+size_t emul_wide_build_impl(const DevNode<float>* nodes, WideNode* wide, size_t cap, uint32_t* levels_out) {
+    std::vector<std::pair<uint32_t, uint32_t>> frontier { { 1u, 0u } }, next;
+    uint32_t count = 1, levels = 0;
+    while (!frontier.empty()) {
+        ++levels;
+        next.clear();
+        for (auto [slot_self, wide_index] : frontier) {
+            uint32_t slot[4];
+            const int used = wide_gather_children(nodes, slot_self, slot);
+            WideNode w;
+            bool is_inner[4];
+            wide_encode(nodes, slot, used, w, is_inner);
+            for (int c = 0; c < used; ++c) {
+                if (!is_inner[c]) continue;
+                const uint32_t idx = count++;
+                w.child[c] = idx << kPrimCountBits;
+                next.emplace_back(slot[c], idx);
+            }
+            if (wide_index < cap) wide[wide_index] = w;
+        }
+        frontier.swap(next);
+    }
+    *levels_out = levels;
+    return count;
+}
+
+void emul_wide_trace_impl(const WideNode* wide, const DevTri<float>* tris, const uint32_t* prim_ids, const float* rays, size_t m,
+                          unsigned flags, uint32_t* ids, float* ts, float* us, float* vs, uint32_t* steps) {
+    const bool any = flags & 1u;
+    for (size_t i = 0; i < m; ++i) {
+        RayCtx<float> r;
+        for (int k = 0; k < 3; ++k) { r.org[k] = rays[8 * i + k]; r.dir[k] = rays[8 * i + 3 + k]; }
+        r.tmin = rays[8 * i + 6]; r.tmax = rays[8 * i + 7];
+        const float tmax_in = r.tmax;
+        HitState<float> hit { kInvalidId, r.tmax, 0.f, 0.f };
+        uint32_t n_steps = 0;
+        if (!ray_interval_is_nan(r)) {
+            wide_ray_setup(r);
+            HostStack<uint32_t> stack;
+            uint32_t top = 0;
+            for (;;) {
+                bool alive = true;
+                while (index_count(top) == 0) {
+                    uint32_t w[16];
+                    std::memcpy(w, wide + (top >> kPrimCountBits), 64);
+                    ++n_steps;
+                    const bool ok = any ? wide_step<true>(w, r, top, stack) : wide_step<false>(w, r, top, stack);
+                    if (!ok) { alive = false; break; }
+                }
+                if (!alive) break;
+                leaf_step<float>(tris, prim_ids, true, top, r, hit, nullptr);
+                if (any && hit.slot != kInvalidId) break;
+                if (stack.empty()) break;
+                top = stack.pop();
+            }
+        }
+        const bool was_hit = hit.slot != kInvalidId;
+        ids[i] = was_hit ? prim_ids[hit.slot] : kInvalidId;
+        ts[i] = was_hit ? hit.t : tmax_in; us[i] = was_hit ? hit.u : 0.f; vs[i] = was_hit ? hit.v : 0.f;
+        if (steps) steps[i] = n_steps;
+    }
+}
+
 } // namespace
 
 #define EMUL_API(T, S) \
@@ -157,6 +222,13 @@ void emul_from_reference(const T* bounds, const uint64_t* index_values, size_t n
         for (size_t i = 0; i < n; ++i) ((DevTri<T>*)tris)[i] = precompute_tri(verts + 9 * (size_t)prim_ids[i]); }
 
 extern "C" {
+size_t emul_wide_build(const void* nodes, void* wide, size_t cap, uint32_t* levels) {
+    return emul_wide_build_impl((const DevNode<float>*)nodes, (WideNode*)wide, cap, levels);
+}
+void emul_wide_trace(const void* wide, const void* tris, const uint32_t* prim_ids, const float* rays, size_t m, unsigned flags,
+                     uint32_t* ids, float* ts, float* us, float* vs, uint32_t* steps) {
+    emul_wide_trace_impl((const WideNode*)wide, (const DevTri<float>*)tris, prim_ids, rays, m, flags, ids, ts, us, vs, steps);
+}
 EMUL_API(float, 3f)
 EMUL_API(double, 3d)
 uint32_t emul_morton30(uint32_t x, uint32_t y, uint32_t z) { return MortonTraits<uint32_t>::encode(x, y, z); }

@@ -34,6 +34,16 @@ def test_lbvh_vs_reference_golden(gpu_lib, name):
     for kernel in (0,) + api.KERNELS:
         hits = bvh.intersect_rays(g["rays"], flags=kernel)
         assert_hits_equal(hits_tuple(hits), tuple(g[f"lowest_{k}"] for k in ("ids", "t", "u", "v")), f"{name}/closest/{kernel}")
+    if g["tris"].dtype == np.float32:
+        # the compressed 4-wide path is conservative: where the reference's fast slab test is not watertight
+        # (rays lying exactly in a box face; fast and robust golden answers differ) it agrees with robust
+        hits = hits_tuple(bvh.intersect_rays(g["rays"], flags=api.KERNEL_WIDE))
+        degenerate = g["lowest_ids"] != g["robust_ids"]
+        want = tuple(np.where(degenerate, g[f"robust_{k}"], g[f"lowest_{k}"]) for k in ("ids", "t", "u", "v"))
+        assert_hits_equal(hits, want, f"{name}/closest/wide")
+        occl = bvh.intersect_rays(g["rays"], flags=api.KERNEL_WIDE | api.ANY_HIT)
+        assert (((occl["prim_id"] != INVALID) == (g["any_ids"] != INVALID)) | degenerate).all()
+    for kernel in (0,) + api.KERNELS:
         hits = bvh.intersect_rays(g["rays"], flags=kernel | api.ROBUST)
         assert_hits_equal(hits_tuple(hits), tuple(g[f"robust_{k}"] for k in ("ids", "t", "u", "v")), f"{name}/robust/{kernel}")
         occl = bvh.intersect_rays(g["rays"], flags=kernel | api.ANY_HIT)
@@ -282,10 +292,10 @@ def test_full_size_properties(gpu_lib, oracle, kind):
     assert (ids[hit] < n).all()
     assert (hits["t"][~hit] == rays[~hit, 7]).all() and (hits["t"][hit] > 0).all()
     assert (hits["u"][hit] >= -1e-6).all() and (hits["v"][hit] >= -1e-6).all() and ((hits["u"] + hits["v"])[hit] <= 1 + 1e-5).all()
-    # all kernels agree exactly
-    for variant in api.KERNELS:
+    # all kernels agree exactly (the compressed 4-wide path included)
+    for variant in api.KERNELS + (api.KERNEL_WIDE,):
         other = bvh.intersect_rays(rays, flags=variant)
-        assert (other.view(np.uint8) == hits.view(np.uint8)).all()
+        assert (other.view(np.uint8) == hits.view(np.uint8)).all(), variant
     # nothing lies in front of a reported closest hit: re-trace with tmax just below t as any-hit
     sel = np.nonzero(hit)[0][:: max(1, int(hit.sum()) // 200_000)]
     shortened = rays[sel].copy()
@@ -328,9 +338,13 @@ def test_incoherent_any_hit_full_size(gpu_lib, oracle):
     tris = scenes.soup(1_000_000)
     bvh = api.Bvh.build_triangles(tris)
     rays = scenes.incoherent_rays(tris, 2_000_000)
-    occl = bvh.intersect_rays(rays, flags=api.ANY_HIT)
-    closest = bvh.intersect_rays(rays)
+    occl = bvh.intersect_rays(rays, flags=api.ANY_HIT | api.KERNEL_TMA)
+    closest = bvh.intersect_rays(rays, flags=api.KERNEL_TMA)
     assert ((occl["prim_id"] != INVALID) == (closest["prim_id"] != INVALID)).all()
+    wide_occl = bvh.intersect_rays(rays, flags=api.ANY_HIT | api.KERNEL_WIDE)
+    wide_closest = bvh.intersect_rays(rays, flags=api.KERNEL_WIDE)
+    assert ((wide_occl["prim_id"] != INVALID) == (occl["prim_id"] != INVALID)).all()
+    assert (wide_closest.view(np.uint8) == closest.view(np.uint8)).all()
     hit = occl["prim_id"] != INVALID
     assert (occl["t"][hit] <= rays[hit, 7]).all() and (occl["t"][hit] >= closest["t"][hit]).all()
     sample = np.arange(0, rays.shape[0], 100)

@@ -161,3 +161,54 @@ def test_leaf_size_config(emul, oracle):
         assert counts.max() <= max_leaf
         if max_leaf == 1:
             assert index_values.shape[0] == 2 * tris.shape[0] - 1
+
+
+@pytest.mark.parametrize("kind,n", [("soup", 1), ("soup", 2), ("soup", 5), ("soup", 20000), ("grid", 20000), ("box12", 12)])
+def test_wide_tree_is_conservative_and_equivalent(emul, oracle, kind, n):
+    """The compressed 4-wide tree derived from the binary one: every child box contains the binary box it
+    was quantised from, and traversing it gives the binary traversal's canonical closest hit bit for bit
+    (and the same occlusion answer), in about half as many inner steps."""
+    tris = scenes.make_mesh(kind, n)
+    tree = emul.build(tris=tris)
+    wide, levels = emul.wide_build(tree)
+    assert 1 <= levels <= tree["depth"] + 1
+    # decode every child box and compare with the binary node it came from (walk both trees together)
+    nodes = tree["nodes"]
+    words = wide.view(np.uint32)
+    def decode(w, c):
+        origin = w[0:3].view(np.float32)
+        exps = [(int(w[3]) >> (8 * k)) & 0xFF for k in range(3)]
+        cell = np.array([np.uint32(e << 23) for e in exps], np.uint32).view(np.float32)
+        lo = np.array([origin[a] + np.float32((int(w[4 + a]) >> (8 * c)) & 0xFF) * cell[a] for a in range(3)], np.float32)
+        hi = np.array([origin[a] + np.float32((int(w[7 + a]) >> (8 * c)) & 0xFF) * cell[a] for a in range(3)], np.float32)
+        return lo, hi
+    checked = 0
+    rng = np.random.RandomState(0)
+    for wi in rng.choice(words.shape[0], size=min(300, words.shape[0]), replace=False):
+        w = words[wi]
+        count = (int(w[3]) >> 24) & 0xFF
+        assert 1 <= count <= 4
+        for c in range(count):
+            ref = int(w[10 + c])
+            lo, hi = decode(w, c)
+            if ref & 15:      # leaf: find the binary leaf with the same index value and check containment
+                match = np.nonzero(nodes.view(np.uint32)[:, 6] == ref)[0]
+                assert match.size >= 1
+                b = nodes[match[0]][:6]
+                assert (lo <= b[0::2]).all() and (hi >= b[1::2]).all()
+                checked += 1
+    assert checked > 0 or n <= 2
+    rays = scenes.make_primary(kind, 97, 95)          # odd sizes: no ray lies exactly in a vertex plane
+    binary = emul.trace(tree, rays, TIE_LOWEST_ID)
+    got = emul.wide_trace(tree, wide, rays, 0)
+    assert_hits_equal(got[:4], binary[:4], f"wide/{kind}/{n}")
+    # rays lying exactly in box faces (even image width: the centre column has dir.x == 0 on a vertex plane):
+    # the wide test is conservative, so it must agree with the watertight ROBUST binary traversal
+    rays_d = scenes.make_primary(kind, 96, 96)
+    assert_hits_equal(emul.wide_trace(tree, wide, rays_d, 0)[:4], emul.trace(tree, rays_d, ROBUST | TIE_LOWEST_ID)[:4], "wide degenerate")
+    occl = emul.wide_trace(tree, wide, rays, 1)
+    assert ((occl[0] != INVALID) == (binary[0] != INVALID)).all()
+    if n >= 1000:
+        assert got[4].mean() < 0.75 * binary[4][:, 0].mean()      # fewer node fetches per ray
+    rays2 = scenes.incoherent_rays(tris, 3000) if n >= 5 else rays
+    assert_hits_equal(emul.wide_trace(tree, wide, rays2, 0)[:4], emul.trace(tree, rays2, TIE_LOWEST_ID)[:4], "wide incoherent")

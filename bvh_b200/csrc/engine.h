@@ -61,7 +61,9 @@ template <typename T> struct DeviceBvh {
 };
 
 // (Re)derives the wide tree from the binary one, e.g. after an upload from the host mirror.
-template <typename T> int rebuild_wide(DeviceBvh<T>& bvh, cudaStream_t stream);
+// force = false: only if the tree already has one (refresh) or the environment asks for it at build time;
+// force = true: always (first use by a trace).
+template <typename T> int rebuild_wide(DeviceBvh<T>& bvh, cudaStream_t stream, bool force = false);
 
 // Reads and clears the traversal status word; returns -1 (with an error message) if a watchdog fired.
 // Synchronises the stream.

@@ -331,8 +331,10 @@ int build_wide(DeviceBvh<float>& bvh, uint32_t levels, uint32_t* d_counters, uin
 }
 inline int build_wide(DeviceBvh<double>&, uint32_t, uint32_t*, uint2*, uint2*, cudaStream_t) { return 0; }
 
+// The wide tree is derived lazily, the first time a trace asks for it (trace_rays), unless the
+// environment asks for it at build time (experiments: BVH_B200_USE_WIDE=1 makes it the default path).
 bool wide_enabled() {
-    static const bool on = [] { const char* e = getenv("BVH_B200_WIDE"); return !e || atoi(e) != 0; }();
+    static const bool on = [] { const char* e = getenv("BVH_B200_USE_WIDE"); return e && atoi(e) != 0; }();
     return on;
 }
 
@@ -353,8 +355,9 @@ struct Scratch {
 
 // Collapses the binary tree of `bvh` into its wide companion (float trees only) and records the wide
 // depth.  Synchronises the stream.
-template <typename T> int make_wide_tree(DeviceBvh<T>& bvh, cudaStream_t stream) {
-    if (sizeof(T) != 4 || !wide_enabled()) return 0;
+template <typename T> int make_wide_tree(DeviceBvh<T>& bvh, cudaStream_t stream, bool force = false) {
+    if (sizeof(T) != 4) return 0;
+    if (!force && !wide_enabled() && !bvh.wide) return 0;        // not wanted yet (a stale one is always refreshed)
     Scratch scratch(stream);
     uint32_t* counters; uint2* fa; uint2* fb;
     const size_t cap = bvh.prim_count ? bvh.prim_count : 1;
@@ -471,9 +474,9 @@ template int build_lbvh<float>(DeviceBvh<float>&, const float*, const float*, co
 template int build_lbvh<double>(DeviceBvh<double>&, const double*, const double*, const double*, uint32_t, const BuildOptions&, cudaStream_t);
 template int attach_triangles<float>(DeviceBvh<float>&, const float*, cudaStream_t);
 template int attach_triangles<double>(DeviceBvh<double>&, const double*, cudaStream_t);
-template <typename T> int rebuild_wide(DeviceBvh<T>& bvh, cudaStream_t stream) { return make_wide_tree(bvh, stream); }
-template int rebuild_wide<float>(DeviceBvh<float>&, cudaStream_t);
-template int rebuild_wide<double>(DeviceBvh<double>&, cudaStream_t);
+template <typename T> int rebuild_wide(DeviceBvh<T>& bvh, cudaStream_t stream, bool force) { return make_wide_tree(bvh, stream, force); }
+template int rebuild_wide<float>(DeviceBvh<float>&, cudaStream_t, bool);
+template int rebuild_wide<double>(DeviceBvh<double>&, cudaStream_t, bool);
 template int refit_triangles<float>(DeviceBvh<float>&, const float*, cudaStream_t);
 template int refit_triangles<double>(DeviceBvh<double>&, const double*, cudaStream_t);
 template void release<float>(DeviceBvh<float>&, cudaStream_t);

@@ -684,7 +684,11 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     if constexpr (sizeof(T) == 4) {
         const bool explicit_binary = (flags & (kTracePair | kTraceNoTma | kTraceTma | kTraceSimple)) != 0;
         const bool order_sensitive = (flags & (kTraceLastVisited | kTraceRobust)) != 0 || d_ray_stats != nullptr;
-        if (bvh.wide && !order_sensitive && ((flags & kTraceWide) || (!explicit_binary && tuning().use_wide))) {
+        const bool want_wide = !order_sensitive && ((flags & kTraceWide) || (!explicit_binary && tuning().use_wide));
+        if (want_wide && !bvh.wide) {                       // derived on first use
+            if (rebuild_wide(const_cast<DeviceBvh<T>&>(bvh), stream, true)) return -1;
+        }
+        if (bvh.wide && want_wide) {
             args.wide = bvh.wide;
             uint32_t e = 3 * bvh.wide_depth + 2;
             args.wide_entries = (e + 7u) & ~7u;

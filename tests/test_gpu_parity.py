@@ -292,10 +292,19 @@ def test_full_size_properties(gpu_lib, oracle, kind):
     assert (ids[hit] < n).all()
     assert (hits["t"][~hit] == rays[~hit, 7]).all() and (hits["t"][hit] > 0).all()
     assert (hits["u"][hit] >= -1e-6).all() and (hits["v"][hit] >= -1e-6).all() and ((hits["u"] + hits["v"])[hit] <= 1 + 1e-5).all()
-    # all kernels agree exactly (the compressed 4-wide path included)
-    for variant in api.KERNELS + (api.KERNEL_WIDE,):
+    # all binary kernels agree exactly
+    for variant in api.KERNELS:
         other = bvh.intersect_rays(rays, flags=variant)
         assert (other.view(np.uint8) == hits.view(np.uint8)).all(), variant
+    # the compressed 4-wide path is conservative: it may only differ from the fast binary traversal where
+    # the fast slab test is not watertight (a ray grazing a box face exactly), and there it must agree with
+    # the watertight ROBUST binary traversal
+    wide = bvh.intersect_rays(rays, flags=api.KERNEL_WIDE)
+    differs = (wide.view(np.uint8).reshape(m, 16) != hits.view(np.uint8).reshape(m, 16)).any(axis=1)
+    assert differs.mean() < 1e-5, int(differs.sum())
+    if differs.any():
+        robust = bvh.intersect_rays(rays[differs], flags=api.ROBUST)
+        assert (robust.view(np.uint8) == wide[differs].view(np.uint8)).all()
     # nothing lies in front of a reported closest hit: re-trace with tmax just below t as any-hit
     sel = np.nonzero(hit)[0][:: max(1, int(hit.sum()) // 200_000)]
     shortened = rays[sel].copy()

@@ -49,7 +49,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel", default="persistent", choices=["persistent", "simple"])
-    ap.add_argument("--chunks", type=int, default=4, help="gather chunks per step when N > 1")
+    ap.add_argument("--chunks", type=int, default=4, help="NCCL gather chunks per step when N > 1")
+    ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "peer", "nccl"],
+                    help="N > 1: fused peer-memory gather (multicast / peer stores) or NCCL all-gather")
     return ap.parse_args()
 
 
@@ -287,7 +289,24 @@ def main():
         if api.lib().bvh3f_intersect_rays(bvh.handle, rays.data_ptr() + 32 * b, e - b, out.data_ptr(), api.DEVICE_POINTERS | kflag):
             raise SystemExit(api.last_error())
 
-    tracer = ShardedTracer(n_rays, 4, torch.int32, device, trace, chunks=args.chunks if world > 1 else 1)
+    tracer, gather_desc = None, None
+    if world > 1 and args.gather != "nccl":
+        try:
+            from bvh_b200.multi_gpu import FusedGatherTracer
+            tracer = FusedGatherTracer(bvh, rays, 4, flags=api.DEVICE_POINTERS | kflag, mode=args.gather)
+            gather_desc = (f"fused in the traversal kernel: every hit record stored into all {world} ranks' symmetric-memory "
+                           f"buffers ({'one multimem store via the NVSwitch multicast address' if tracer.mode == 'multicast' else 'one NVLink peer store per rank'}), "
+                           "symmetric-memory barrier per step")
+        except Exception as exc:                 # no symmetric memory on this box: NCCL all-gather instead
+            if args.gather != "auto":
+                raise
+            if rank == 0:
+                print(f"[bench] fused gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+            tracer = None
+    if tracer is None:
+        tracer = ShardedTracer(n_rays, 4, torch.int32, device, trace, chunks=args.chunks if world > 1 else 1)
+        if world > 1:
+            gather_desc = f"NCCL all_gather_into_tensor of hit records, {args.chunks} chunks overlapped with traversal"
     for _ in range(max(3, args.warmup)):
         tracer.step()
     barrier()
@@ -315,6 +334,11 @@ def main():
         g = tracer.global_hits()
         assert g.shape[0] == world * n_rays
         assert torch.equal(g[rank * n_rays:(rank + 1) * n_rays], tracer.local), "gathered hits do not match the local shard"
+        # every rank must hold every other rank's shard: compare per-shard checksums across ranks
+        sums = g.view(world, n_rays, 4)[:, :, 0].to(torch.int64).sum(dim=1)
+        ref_sums = sums.clone()
+        dist.broadcast(ref_sums, src=0)
+        assert torch.equal(sums, ref_sums), "ranks disagree on the gathered hit records"
 
     # ---- e2e through the C ABI with pinned host buffers ----------------------------------------------
     e2e = None
@@ -360,7 +384,7 @@ def main():
                        "kernel": args.kernel, "tie_break": "lowest original id (canonical)",
                        "l2": "inputs larger than L2: 320 MB of rays + 160 MB of hits streamed per step, no flush needed",
                        "hit_fraction": hit_frac, "inner_steps_per_ray": s_inner, "leaves_per_ray": s_leaves, "tri_tests_per_ray": s_tri,
-                       "gather": None if world == 1 else f"NCCL all_gather_into_tensor of hit records, {args.chunks} chunks overlapped with traversal",
+                       "gather": gather_desc,
                        "hits_checksum": checksum},
             "roofline": {"bound": "hbm", "kernel": f"trace_{args.kernel}_kernel<float>", "achieved": achieved, "peak": peak_gbs,
                          "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,

@@ -94,6 +94,8 @@ def lib() -> C.CDLL:
         f("refit_triangles").argtypes = [P, P, SZ, U]
         f("intersect_rays").restype = C.c_int
         f("intersect_rays").argtypes = [P, P, SZ, P, U]
+        f("intersect_rays_gather").restype = C.c_int
+        f("intersect_rays_gather").argtypes = [P, P, SZ, P, C.POINTER(C.c_void_p), C.c_int, SZ, P, U]
         f("intersect_rays_stats").restype = C.c_int
         f("intersect_rays_stats").argtypes = [P, P, SZ, P, P, U]
         f("sync").restype = C.c_int
@@ -246,6 +248,17 @@ class Bvh:
         if rc:
             raise BvhError(last_error())
         return (hits, st) if stats else hits
+
+    def intersect_rays_gather(self, rays_ptr: int, count: int, gathered_ptrs, shard_offset: int, hits_ptr: int = 0,
+                              multicast_ptr: int = 0, flags: int = 0) -> None:
+        """``bvhNN_intersect_rays_gather``: trace a device-resident shard and let the kernel store each hit
+        record into the gathered array of every rank (``gathered_ptrs[r]``: that array as mapped here)."""
+        arr = (C.c_void_p * len(gathered_ptrs))(*[int(p) for p in gathered_ptrs])
+        rc = self._f("intersect_rays_gather")(self.handle, C.c_void_p(int(rays_ptr)), count,
+                                              C.c_void_p(int(hits_ptr)) if hits_ptr else None, arr, len(gathered_ptrs),
+                                              shard_offset, C.c_void_p(int(multicast_ptr)) if multicast_ptr else None, flags)
+        if rc:
+            raise BvhError(last_error())
 
     def sync(self) -> None:
         if self._f("sync")(self.handle):

@@ -359,13 +359,7 @@ template <typename T> int ensure_staging(Handle<T>& h, void** buf, size_t* cap, 
     return 0;
 }
 
-template <typename T, typename RayPod, typename HitPod>
-int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bvh_ray_stats* stats, unsigned flags) {
-    static_assert(sizeof(RayPod) == sizeof(DevRay<T>) && sizeof(HitPod) == sizeof(DevHit<T>), "POD layouts");
-    if (!h) { set_error("null handle"); return -1; }
-    if (n == 0) return 0;
-    BVH_CUDA_TRY(cudaSetDevice(h->device));
-    if (ensure_device(*h)) return -1;
+static unsigned translate_flags(unsigned flags) {
     unsigned tf = 0;
     if (flags & BVH_ANY_HIT) tf |= kTraceAnyHit;
     if (flags & BVH_ROBUST) tf |= kTraceRobust;
@@ -375,6 +369,17 @@ int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bv
     if (flags & BVH_KERNEL_TMA) tf |= kTraceTma;
     if (flags & BVH_KERNEL_PAIR) tf |= kTracePair;
     if (flags & BVH_KERNEL_WIDE) tf |= kTraceWide;
+    return tf;
+}
+
+template <typename T, typename RayPod, typename HitPod>
+int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bvh_ray_stats* stats, unsigned flags) {
+    static_assert(sizeof(RayPod) == sizeof(DevRay<T>) && sizeof(HitPod) == sizeof(DevHit<T>), "POD layouts");
+    if (!h) { set_error("null handle"); return -1; }
+    if (n == 0) return 0;
+    BVH_CUDA_TRY(cudaSetDevice(h->device));
+    if (ensure_device(*h)) return -1;
+    const unsigned tf = translate_flags(flags);
     if (flags & BVH_DEVICE_POINTERS) {
         return trace_rays<T>(h->dev, reinterpret_cast<const DevRay<T>*>(rays), reinterpret_cast<DevHit<T>*>(hits), n, tf,
                              reinterpret_cast<uint32_t*>(stats), h->stream);
@@ -593,6 +598,20 @@ BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete p
     BVH_EXPORT int bvh##S##_intersect_rays(struct bvh##S* bvh, const struct bvh_ray##S* rays, size_t ray_count,    \
             struct bvh_hit##S* hits, unsigned flags) {                                                             \
         return intersect_batch<T>(H(T, bvh), rays, ray_count, hits, nullptr, flags);                               \
+    }                                                                                                              \
+    BVH_EXPORT int bvh##S##_intersect_rays_gather(struct bvh##S* bvh, const struct bvh_ray##S* rays, size_t ray_count, \
+            struct bvh_hit##S* hits, void* const* gathered_hits, int world_size, size_t shard_offset,              \
+            void* multicast_hits, unsigned flags) {                                                                \
+        auto h = H(T, bvh);                                                                                        \
+        if (!h) { set_error("null handle"); return -1; }                                                           \
+        if (!gathered_hits || world_size < 1 || world_size > 8) { set_error("gather: need 1..8 gathered arrays"); return -1; } \
+        BVH_CUDA_TRY(cudaSetDevice(h->device));                                                                    \
+        if (ensure_device(*h)) return -1;                                                                          \
+        GatherTargets g;                                                                                           \
+        for (int r = 0; r < 8; ++r) g.peer[r] = r < world_size ? gathered_hits[r] : nullptr;                      \
+        g.count = world_size; g.multicast = multicast_hits; g.offset = shard_offset;                               \
+        return trace_rays<T>(h->dev, reinterpret_cast<const DevRay<T>*>(rays), reinterpret_cast<DevHit<T>*>(hits), \
+                             ray_count, translate_flags(flags), nullptr, h->stream, &g);                           \
     }                                                                                                              \
     BVH_EXPORT int bvh##S##_intersect_rays_stats(struct bvh##S* bvh, const struct bvh_ray##S* rays, size_t ray_count, \
             struct bvh_hit##S* hits, struct bvh_ray_stats* stats, unsigned flags) {                                \

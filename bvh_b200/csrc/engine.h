@@ -98,10 +98,21 @@ enum TraceFlags : unsigned {
     kTraceWide        = 1u << 12,  // persistent kernel over the compressed 4-wide tree
 };
 
+// Fused multi-GPU gather: besides (or instead of) the local hit array, every finished ray's record is
+// stored at element `offset + i` of the gathered hit array of each rank — peer[] holds that array's address
+// on every rank (peer-mapped device pointers, own rank included); multicast, when non-null, is the NVSwitch
+// multicast alias of the same array and replaces the per-peer stores by one multimem store.
+struct GatherTargets {
+    void* peer[8];
+    int count;
+    void* multicast;
+    size_t offset;
+};
+
 // Batched traversal; all pointers are device pointers.  ray_stats (nullable): n x 3 uint32
 // {inner steps, leaves, triangle tests}; it selects the statistics variant of the kernel.
 template <typename T>
 int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hits, size_t n,
-               unsigned flags, uint32_t* d_ray_stats, cudaStream_t stream);
+               unsigned flags, uint32_t* d_ray_stats, cudaStream_t stream, const GatherTargets* gather = nullptr);
 
 } // namespace bvhb200

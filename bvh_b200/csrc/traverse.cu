@@ -54,8 +54,24 @@ __device__ __forceinline__ void load_ray(const DevRay<double>* __restrict__ rays
     r.dir[1] = c.x; r.dir[2] = c.y; r.tmin = d.x; r.tmax = d.y;
 }
 
+// Where a finished ray's hit record goes: the caller's local array and, in the fused multi-GPU mode, the
+// gathered array of EVERY rank (peer stores over NVLink, or one multimem store through the NVSwitch
+// multicast address).  See trace_rays_gather / DESIGN.md "Multi-GPU".
+constexpr int kMaxPeers = 8;
+template <typename T> struct HitSinks {
+    DevHit<T>* local;                 // may be null in gather mode
+    DevHit<T>* peer[kMaxPeers];       // gathered arrays (own rank included), already offset to this shard
+    int peer_count;
+    DevHit<T>* multicast;             // multicast alias of the gathered array (offset to this shard) or null
+};
+
+__device__ __forceinline__ void multimem_store_v4(void* p, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
+
 // A miss reports id = all ones (BVH_INVALID_PRIM_ID), t = the ray's tmax, u = v = 0.
-__device__ __forceinline__ void store_hit(DevHit<float>* __restrict__ hits, size_t i, const HitState<float>& h,
+__device__ __forceinline__ void store_hit(const HitSinks<float>& sinks, size_t i, const HitState<float>& h,
                                           float tmax, const uint32_t* __restrict__ prim_ids) {
     uint4 o;
     const bool was_hit = h.slot != kInvalidId;
@@ -63,9 +79,11 @@ __device__ __forceinline__ void store_hit(DevHit<float>* __restrict__ hits, size
     o.y = __float_as_uint(was_hit ? h.t : tmax);
     o.z = __float_as_uint(was_hit ? h.u : 0.f);
     o.w = __float_as_uint(was_hit ? h.v : 0.f);
-    __stcs(reinterpret_cast<uint4*>(hits + i), o);
+    if (sinks.local) __stcs(reinterpret_cast<uint4*>(sinks.local + i), o);
+    if (sinks.multicast) multimem_store_v4(sinks.multicast + i, o);
+    else for (int p = 0; p < sinks.peer_count; ++p) *reinterpret_cast<uint4*>(sinks.peer[p] + i) = o;
 }
-__device__ __forceinline__ void store_hit(DevHit<double>* __restrict__ hits, size_t i, const HitState<double>& h,
+__device__ __forceinline__ void store_hit(const HitSinks<double>& sinks, size_t i, const HitState<double>& h,
                                           double tmax, const uint32_t* __restrict__ prim_ids) {
     const bool was_hit = h.slot != kInvalidId;
     ulonglong2 a, b;
@@ -73,9 +91,15 @@ __device__ __forceinline__ void store_hit(DevHit<double>* __restrict__ hits, siz
     a.y = (unsigned long long)__double_as_longlong(was_hit ? h.t : tmax);
     b.x = (unsigned long long)__double_as_longlong(was_hit ? h.u : 0.0);
     b.y = (unsigned long long)__double_as_longlong(was_hit ? h.v : 0.0);
-    ulonglong2* d = reinterpret_cast<ulonglong2*>(hits + i);
-    __stcs(d, a);
-    __stcs(d + 1, b);
+    if (sinks.local) {
+        ulonglong2* d = reinterpret_cast<ulonglong2*>(sinks.local + i);
+        __stcs(d, a);
+        __stcs(d + 1, b);
+    }
+    for (int p = 0; p < sinks.peer_count; ++p) {
+        ulonglong2* d = reinterpret_cast<ulonglong2*>(sinks.peer[p] + i);
+        d[0] = a; d[1] = b;
+    }
 }
 
 template <typename T> struct TraceArgs {
@@ -83,7 +107,7 @@ template <typename T> struct TraceArgs {
     const DevTri<T>* tris;
     const uint32_t* prim_ids;
     const DevRay<T>* rays;
-    DevHit<T>* hits;
+    HitSinks<T> hits;
     unsigned long long n;
     unsigned long long* next_ray;     // persistent kernel: global ray cursor
     uint32_t* ray_stats;              // statistics variant: n x 3
@@ -662,12 +686,23 @@ int launch(const TraceArgs<T>& args, bool simple, bool stats, int device, cudaSt
 
 template <typename T>
 int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hits, size_t n,
-               unsigned flags, uint32_t* d_ray_stats, cudaStream_t stream) {
+               unsigned flags, uint32_t* d_ray_stats, cudaStream_t stream, const GatherTargets* gather) {
     if (n == 0) return 0;
     if (!bvh.nodes || !bvh.tris) { set_error("trace: the BVH has no triangles attached (bvhNN_set_triangles)"); return -1; }
     TraceArgs<T> args;
     args.nodes = bvh.nodes; args.tris = bvh.tris; args.prim_ids = bvh.prim_ids;
-    args.rays = d_rays; args.hits = d_hits; args.n = n;
+    args.rays = d_rays; args.n = n;
+    args.hits.local = d_hits; args.hits.peer_count = 0; args.hits.multicast = nullptr;
+    for (int p = 0; p < kMaxPeers; ++p) args.hits.peer[p] = nullptr;
+    if (gather) {
+        if (gather->count < 0 || gather->count > kMaxPeers) { set_error("trace: at most 8 gather targets"); return -1; }
+        for (int p = 0; p < gather->count; ++p) args.hits.peer[p] = static_cast<DevHit<T>*>(gather->peer[p]) + gather->offset;
+        args.hits.peer_count = gather->count;
+        if (gather->multicast) {
+            if (sizeof(T) != 4) { set_error("trace: multicast gather is float-only"); return -1; }
+            args.hits.multicast = static_cast<DevHit<T>*>(gather->multicast) + gather->offset;
+        }
+    } else if (!d_hits) { set_error("trace: no hit array"); return -1; }
     args.ray_stats = d_ray_stats;
     args.lowest_id = (flags & kTraceLastVisited) ? 0 : 1;
     uint32_t entries = bvh.depth + 1;
@@ -729,7 +764,7 @@ template <typename T> int check_trace_status(const DeviceBvh<T>& bvh, cudaStream
 template int check_trace_status<float>(const DeviceBvh<float>&, cudaStream_t);
 template int check_trace_status<double>(const DeviceBvh<double>&, cudaStream_t);
 
-template int trace_rays<float>(const DeviceBvh<float>&, const DevRay<float>*, DevHit<float>*, size_t, unsigned, uint32_t*, cudaStream_t);
-template int trace_rays<double>(const DeviceBvh<double>&, const DevRay<double>*, DevHit<double>*, size_t, unsigned, uint32_t*, cudaStream_t);
+template int trace_rays<float>(const DeviceBvh<float>&, const DevRay<float>*, DevHit<float>*, size_t, unsigned, uint32_t*, cudaStream_t, const GatherTargets*);
+template int trace_rays<double>(const DeviceBvh<double>&, const DevRay<double>*, DevHit<double>*, size_t, unsigned, uint32_t*, cudaStream_t, const GatherTargets*);
 
 } // namespace bvhb200

@@ -79,3 +79,43 @@ class ShardedTracer:
         views = [g.view(self.world, e - b, -1) for g, (b, e) in zip(self.gathered, self.bounds)]
         per_rank = [torch.cat([v[r] for v in views], dim=0) for r in range(self.world)]
         return torch.cat(per_rank, dim=0)
+
+
+class FusedGatherTracer:
+    """Traversal fused with the all-gather of its hit records over NVLink peer memory.
+
+    The gathered hit array lives in symmetric memory (``torch.distributed._symmetric_memory``): every rank
+    holds the same (world * local_count, words) buffer and knows the address of each peer's copy.  One
+    launch of the traversal kernel (``bvhNN_intersect_rays_gather``) traces this rank's shard and stores
+    each finished ray's 16-byte record straight into the shard's slot of EVERY rank's buffer — one multimem
+    store through the NVSwitch multicast address when the fabric offers it, otherwise one peer store per
+    rank — so the transfer rides along with the traversal instead of following it as an NCCL call.  A
+    symmetric-memory barrier at the end of the step orders the remote stores before anyone reads.
+    """
+
+    def __init__(self, bvh, rays: torch.Tensor, hit_words: int, group=None, flags: int = 0, mode: str = "auto"):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.bvh, self.rays, self.flags = bvh, rays, flags
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.local_count = rays.shape[0]
+        self.gathered = symm_mem.empty((self.world * self.local_count, hit_words), dtype=torch.int32, device=rays.device)
+        self.handle = symm_mem.rendezvous(self.gathered, self.group)
+        self.peers = [int(p) for p in self.handle.buffer_ptrs]
+        multicast = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        if mode == "peer":
+            multicast = 0
+        if mode == "multicast" and not multicast:
+            raise RuntimeError("no multicast address for the symmetric buffer on this fabric")
+        self.multicast = multicast
+        self.mode = "multicast" if multicast else "peer"
+        self.bounds = [(0, self.local_count)]
+        self.local = self.gathered[self.rank * self.local_count:(self.rank + 1) * self.local_count]
+
+    def step(self) -> None:
+        self.bvh.intersect_rays_gather(self.rays.data_ptr(), self.local_count, self.peers,
+                                       self.rank * self.local_count, multicast_ptr=self.multicast, flags=self.flags)
+        self.handle.barrier(channel=0)
+
+    def global_hits(self) -> torch.Tensor:
+        return self.gathered

@@ -88,6 +88,16 @@ BVH_API void bvh_host_free(void* ptr);
     /* Intersect ray_count rays; hits[i] answers rays[i]. */                                            \
     BVH_API int bvh##S##_intersect_rays(struct bvh##S* bvh, const struct bvh_ray##S* rays, size_t ray_count, \
                                         struct bvh_hit##S* hits, unsigned flags);                       \
+    /* Fused traversal + all-gather for a ray batch sharded over several GPUs (device pointers only, stream-  \
+       ordered).  This rank traces its shard and the kernel itself stores every hit record at element         \
+       `shard_offset + i` of the gathered hit array of EVERY rank: gathered_hits[r] is that array's address on  \
+       rank r as mapped into this process (peer / symmetric memory, own rank included); multicast_hits, when    \
+       non-NULL, is the NVSwitch multicast alias of the same array (one multimem store instead of world_size   \
+       stores; float only).  hits may be NULL.  The caller orders a cross-rank barrier after the call before    \
+       anyone reads the gathered arrays. */                                                                   \
+    BVH_API int bvh##S##_intersect_rays_gather(struct bvh##S* bvh, const struct bvh_ray##S* rays, size_t ray_count, \
+                                               struct bvh_hit##S* hits, void* const* gathered_hits, int world_size, \
+                                               size_t shard_offset, void* multicast_hits, unsigned flags);     \
     /* Same, also returning the per-ray traversal counters (statistics kernel). */                      \
     BVH_API int bvh##S##_intersect_rays_stats(struct bvh##S* bvh, const struct bvh_ray##S* rays, size_t ray_count, \
                                               struct bvh_hit##S* hits, struct bvh_ray_stats* stats, unsigned flags); \

@@ -165,90 +165,169 @@ struct HostSync {
     static inline void store_max(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
 };
 
-// The bottom-up pass for sorted leaf `i` whose box is [bmin, bmax].  Called once per leaf; the
-// thread that arrives SECOND at an internal node continues upwards with the merged node.
+// ---- the bottom-up pass, in pieces -----------------------------------------------------------------
+// State of a node on its way up: the range of sorted primitives it covers, its box, its packed index
+// (leaf or inner), SAH cost and depth.
+template <typename T> struct ClimbState {
+    uint32_t l, r;
+    T bmin[3], bmax[3];
+    typename Real<T>::UInt index;
+    T cost;
+    uint32_t depth;
+};
+
+template <typename T> BVH_HD void climb_init(ClimbState<T>& s, uint32_t i, const T bmin[3], const T bmax[3]) {
+    using U = typename Real<T>::UInt;
+    s.l = s.r = i;
+    for (int k = 0; k < 3; ++k) { s.bmin[k] = bmin[k]; s.bmax[k] = bmax[k]; }
+    s.index = make_index<U>((U)i, 1);                       // Index::make_leaf(i, 1)
+    s.cost = half_area(bmin, bmax);                         // leaf cost = half_area * prim_count
+    s.depth = 0;
+}
+
+// Choose the parent: merge across the more similar boundary (ties -> left boundary).  side 0: the node is
+// the child covering [l, parent]; side 1: the child covering [parent+1, r].
+template <typename K> BVH_HD void choose_parent(const K* __restrict__ keys, uint32_t n, uint32_t l, uint32_t r,
+                                                uint32_t& parent, uint32_t& side) {
+    if (l == 0 || (r != n - 1 && delta_less(delta_at(keys, r), delta_at(keys, l - 1)))) { parent = r; side = 0; }
+    else { parent = l - 1; side = 1; }
+}
+
+// Device slot of child `side` of internal node `parent` (reference index 2p+1+side, +1 device shift).
+BVH_HD size_t child_slot(uint32_t parent, uint32_t side) { return 2 * (size_t)parent + 1 + side + 1; }
+
+// Publishes the node as child `side` of `parent`: its final record goes to its final slot.  Returns the
+// record (the cost travels rounded to what the packed word holds, so both arrivals see the same value).
+template <typename T> BVH_HD DevNode<T> publish_child(const BuildParams<T>& p, ClimbState<T>& s, uint32_t parent, uint32_t side) {
+    using U = typename Real<T>::UInt;
+    const U aux = AuxPack<T>::pack(s.cost, s.depth);
+    s.cost = AuxPack<T>::cost(aux);
+    DevNode<T> rec;
+    for (int k = 0; k < 3; ++k) { rec.bounds[2 * k] = s.bmin[k]; rec.bounds[2 * k + 1] = s.bmax[k]; }
+    rec.index = s.index; rec.pad = aux;
+    write_node(p.nodes + child_slot(parent, side), s.bmin, s.bmax, s.index, aux);
+    return rec;
+}
+
+// The second arrival at `parent` merges with its sibling's record `sn` (whose far range boundary is
+// `other`): SATO swap of the two records if needed, box union in memory order, SAH leaf-collapse decision.
+// Returns true when the merged node is the root (its record is then written to reference index 0).
+template <typename T> BVH_HD bool merge_into_parent(const BuildParams<T>& p, ClimbState<T>& s, uint32_t parent, uint32_t side,
+                                                    const DevNode<T>& own, const DevNode<T>& sn, uint32_t other) {
+    using R = Real<T>;
+    using U = typename R::UInt;
+    const T sib_cost = AuxPack<T>::cost(sn.pad);
+    const uint32_t sib_depth = AuxPack<T>::depth(sn.pad);
+    T smin[3] = { sn.bounds[0], sn.bounds[2], sn.bounds[4] };
+    T smax[3] = { sn.bounds[1], sn.bounds[3], sn.bounds[5] };
+    const T own_area = half_area(s.bmin, s.bmax), sib_area = half_area(smin, smax);
+
+    // SATO: the child with the larger half-area must be the LEFT one (top_down_sah_builder.h:101-108).
+    const bool own_is_left = side == 0;
+    const T left_area = own_is_left ? own_area : sib_area, right_area = own_is_left ? sib_area : own_area;
+    const bool swap = left_area < right_area;
+    if (swap) {
+        write_node(p.nodes + child_slot(parent, 1 - side), s.bmin, s.bmax, own.index, own.pad);
+        write_node(p.nodes + child_slot(parent, side), smin, smax, sn.index, sn.pad);
+    }
+    if (side == 0) s.r = other; else s.l = other;
+    // parent box = left.get_bbox().extend(right.get_bbox()) (bvh.h:213-217), left/right as they now sit in memory
+    const bool own_first = swap ? !own_is_left : own_is_left;
+    for (int k = 0; k < 3; ++k) {
+        const T a_min = own_first ? s.bmin[k] : smin[k], b_min = own_first ? smin[k] : s.bmin[k];
+        const T a_max = own_first ? s.bmax[k] : smax[k], b_max = own_first ? smax[k] : s.bmax[k];
+        s.bmin[k] = robust_min(a_min, b_min);
+        s.bmax[k] = robust_max(a_max, b_max);
+    }
+    const uint32_t count = s.r - s.l + 1;
+    const T area = half_area(s.bmin, s.bmax);
+    const T split_cost = R::add(area, R::add(s.cost, sib_cost));   // node cost_ratio 1 (split_heuristic.h:18-24)
+    const T leaf_cost = R::mul(area, (T)count);                   // get_leaf_cost, split_heuristic.h:30-33
+    const uint32_t sub_depth = (s.depth > sib_depth ? s.depth : sib_depth) + 1;
+    if (count <= p.max_leaf && (count <= p.min_leaf || leaf_cost <= split_cost)) {
+        s.index = make_index<U>((U)s.l, count);             // collapse the subtree into one leaf
+        s.cost = leaf_cost; s.depth = 0;
+    } else {
+        s.index = make_index<U>((U)(2 * (size_t)parent + 1), 0);   // Index::make_inner(first child)
+        s.cost = split_cost; s.depth = sub_depth;
+    }
+    if (s.l == 0 && s.r == p.n - 1) {                       // this is the root: reference index 0
+        write_node(p.nodes + 1, s.bmin, s.bmax, s.index);
+        p.info[0] = s.depth; p.info[1] = parent;
+        return true;
+    }
+    return false;
+}
+
+// Climb through GLOBAL memory from a node that has just been published as child `side` of `parent` (record
+// `own`): exchange the arrival flag; the first arrival stops, the second merges and goes on.
+template <typename T, typename K, typename Sync>
+BVH_HD void climb_global(const BuildParams<T>& p, const K* __restrict__ keys, ClimbState<T>& s,
+                         uint32_t parent, uint32_t side, DevNode<T> own) {
+    for (;;) {
+        Sync::fence();
+        const int other = Sync::exchange(p.flags + parent, (int)(side == 0 ? s.l : s.r));
+        if (other < 0) return;                              // first to arrive: the sibling will carry on
+        Sync::fence();
+        const DevNode<T> sn = Sync::load(p.nodes + child_slot(parent, 1 - side));
+        if (merge_into_parent(p, s, parent, side, own, sn, (uint32_t)other)) return;
+        choose_parent(keys, p.n, s.l, s.r, parent, side);
+        own = publish_child(p, s, parent, side);
+    }
+}
+
+// The whole pass for sorted leaf `i` through global memory only (host emulation; reference formulation).
 template <typename T, typename K, typename Sync>
 BVH_HD void build_bottom_up(const BuildParams<T>& p, const K* __restrict__ keys, uint32_t i,
                             T bmin[3], T bmax[3]) {
-    using R = Real<T>;
-    using U = typename R::UInt;
-    const uint32_t n = p.n;
-    uint32_t l = i, r = i;
-    U index = make_index<U>((U)i, 1);                       // Index::make_leaf(i, 1)
-    T cost = half_area(bmin, bmax);                         // leaf cost = half_area * prim_count
-    uint32_t depth = 0;
-
-    if (n == 1) {                                           // the root is a leaf (bvh.h:128 handles it)
-        write_node(p.nodes + 1, bmin, bmax, index);
+    ClimbState<T> s;
+    climb_init(s, i, bmin, bmax);
+    if (p.n == 1) {                                         // the root is a leaf (bvh.h:128 handles it)
+        write_node(p.nodes + 1, bmin, bmax, s.index);
         p.info[0] = 0; p.info[1] = 0;
         return;
     }
+    uint32_t parent, side;
+    choose_parent(keys, p.n, s.l, s.r, parent, side);
+    const DevNode<T> own = publish_child(p, s, parent, side);
+    climb_global<T, K, Sync>(p, keys, s, parent, side, own);
+}
 
+// ---- block-local first phase -------------------------------------------------------------------------
+// A block of consecutive sorted leaves [i0, iend) first merges, through SHARED memory, every pair of nodes
+// that meets at a boundary strictly inside the block (the merges of the final tree whose both children lie
+// in the block — about 95 % of all merges for 256-leaf blocks); only nodes whose parent boundary is a block
+// wall, or whose sibling never showed up locally, continue through global memory (climb_global).  The tree
+// is the same as with the global-only pass: the same merges happen, only where the two arrivals meet differs.
+template <typename T> struct LocalSlots {
+    DevNode<T>* nodes;      // [2 * block_leaves]: record of child `side` of boundary p at 2 * (p - i0) + side
+    int* flags;             // [block_leaves]: -1, or the far boundary of the first arrival
+    int* matched;           // [block_leaves]: set by the second arrival
+};
+
+enum ClimbOutcome : int { kClimbDone = 0, kClimbGlobal = 1, kClimbWaiting = 2 };
+
+// Runs the local phase for one leaf.  On return `parent`/`side`/`own` describe where the node stands:
+// kClimbDone    — finished (it was a second... no further work: first arrival matched later, or root written)
+// kClimbGlobal  — its parent boundary is a block wall: continue with climb_global
+// kClimbWaiting — it is the first arrival at a local boundary; after the block barrier, if nobody matched it,
+//                 it must continue with climb_global (its record is already in global memory)
+template <typename T, typename K, typename LocalSync>
+BVH_HD int climb_local(const BuildParams<T>& p, const K* __restrict__ keys, ClimbState<T>& s, const LocalSlots<T>& loc,
+                       uint32_t i0, uint32_t iend, uint32_t& parent, uint32_t& side, DevNode<T>& own) {
     for (;;) {
-        // Choose the parent: merge across the more similar boundary (ties -> left boundary).
-        uint32_t parent; uint32_t side;
-        if (l == 0 || (r != n - 1 && delta_less(delta_at(keys, r), delta_at(keys, l - 1)))) {
-            parent = r; side = 0;                           // we are the child covering [l, parent]
-        } else {
-            parent = l - 1; side = 1;                       // we are the child covering [parent+1, r]
-        }
-        const size_t slot = 2 * (size_t)parent + 1 + side + 1;   // reference index 2p+1+side, +1 device shift
-        // the cost travels rounded to what the packed word can hold, so that both arrivals (and the host
-        // emulation) see the same value
-        const U aux = AuxPack<T>::pack(cost, depth);
-        cost = AuxPack<T>::cost(aux);
-        write_node(p.nodes + slot, bmin, bmax, index, aux);
-        Sync::fence();
-        const int other = Sync::exchange(p.flags + parent, (int)(side == 0 ? l : r));
-        if (other < 0) return;                              // first to arrive: the sibling will carry on
-        Sync::fence();
-
-        // Second to arrive: fetch the sibling's record and merge.
-        const size_t sib = 2 * (size_t)parent + 1 + (1 - side) + 1;
-        const DevNode<T> sn = Sync::load(p.nodes + sib);
-        const T sib_cost = AuxPack<T>::cost(sn.pad);
-        const uint32_t sib_depth = AuxPack<T>::depth(sn.pad);
-        T smin[3] = { sn.bounds[0], sn.bounds[2], sn.bounds[4] };
-        T smax[3] = { sn.bounds[1], sn.bounds[3], sn.bounds[5] };
-        const T own_area = half_area(bmin, bmax), sib_area = half_area(smin, smax);
-
-        // SATO: the child with the larger half-area must be the LEFT one (top_down_sah_builder.h:101-108).
-        const bool own_is_left = side == 0;
-        const T left_area = own_is_left ? own_area : sib_area, right_area = own_is_left ? sib_area : own_area;
-        if (left_area < right_area) {
-            write_node(p.nodes + sib, bmin, bmax, index, aux);
-            write_node(p.nodes + slot, smin, smax, sn.index, sn.pad);
-        }
-
-        if (side == 0) r = (uint32_t)other; else l = (uint32_t)other;
-        // parent box = left.get_bbox().extend(right.get_bbox()) (bvh.h:213-217) with left/right as
-        // they now sit in memory
-        const bool own_first = (left_area < right_area) ? !own_is_left : own_is_left;
-        for (int k = 0; k < 3; ++k) {
-            const T a_min = own_first ? bmin[k] : smin[k], b_min = own_first ? smin[k] : bmin[k];
-            const T a_max = own_first ? bmax[k] : smax[k], b_max = own_first ? smax[k] : bmax[k];
-            bmin[k] = robust_min(a_min, b_min);
-            bmax[k] = robust_max(a_max, b_max);
-        }
-
-        const uint32_t count = r - l + 1;
-        const T area = half_area(bmin, bmax);
-        const T split_cost = R::add(area, R::add(cost, sib_cost));   // node cost_ratio 1 (split_heuristic.h:18-24)
-        const T leaf_cost = R::mul(area, (T)count);                 // get_leaf_cost, split_heuristic.h:30-33
-        const uint32_t sub_depth = (depth > sib_depth ? depth : sib_depth) + 1;
-        if (count <= p.max_leaf && (count <= p.min_leaf || leaf_cost <= split_cost)) {
-            index = make_index<U>((U)l, count);             // collapse the subtree into one leaf
-            cost = leaf_cost; depth = 0;
-        } else {
-            index = make_index<U>((U)(2 * (size_t)parent + 1), 0);   // Index::make_inner(first child)
-            cost = split_cost; depth = sub_depth;
-        }
-
-        if (l == 0 && r == n - 1) {                         // this is the root: reference index 0
-            write_node(p.nodes + 1, bmin, bmax, index);
-            p.info[0] = depth; p.info[1] = parent;
-            return;
-        }
+        choose_parent(keys, p.n, s.l, s.r, parent, side);
+        own = publish_child(p, s, parent, side);
+        if (parent < i0 || parent + 1 >= iend) return kClimbGlobal;       // the boundary is a block wall
+        const uint32_t q = parent - i0;
+        loc.nodes[2 * q + side] = own;
+        LocalSync::fence();
+        const int other = LocalSync::exchange(loc.flags + q, (int)(side == 0 ? s.l : s.r));
+        if (other < 0) return kClimbWaiting;
+        LocalSync::fence();
+        loc.matched[q] = 1;
+        const DevNode<T> sn = loc.nodes[2 * q + (1 - side)];
+        if (merge_into_parent(p, s, parent, side, own, sn, (uint32_t)other)) return kClimbDone;
     }
 }
 

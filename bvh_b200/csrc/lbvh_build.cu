@@ -154,34 +154,70 @@ morton_kernel(const T* __restrict__ src, uint32_t n, int mode, const MinMax3<T>*
     }
 }
 
+// Shared-memory meeting point of the block-local phase: plain shared accesses ordered by block-scope fences
+// around a shared-memory exchange (nobody ever waits, so divergent lanes of one warp cannot deadlock).
+struct BlockSync {
+    static __device__ __forceinline__ void fence() { __threadfence_block(); }
+    static __device__ __forceinline__ int exchange(int* p, int v) { return atomicExch(p, v); }
+};
+
 // K4.  leaf_mode 0: verts (n x 9), also writes BVH-order triangles; 1: bboxes (n x 6, min3 max3).
+// Two phases (build_core.cuh): merges whose two children lie inside this block's kBlock consecutive leaves
+// meet in shared memory; after one block barrier, whatever reached a block wall or was not matched locally
+// carries on through the global arrival flags.
 template <typename T, typename K>
 __global__ void __launch_bounds__(kBlock)
 hierarchy_kernel(BuildParams<T> p, const K* __restrict__ keys, const uint32_t* __restrict__ vals,
                  const T* __restrict__ leaf_src, int leaf_mode, DevTri<T>* __restrict__ tris) {
-    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= p.n) return;
-    const uint32_t id = vals[i];
+    __shared__ DevNode<T> s_nodes[2 * kBlock];
+    __shared__ int s_flags[kBlock];
+    __shared__ int s_matched[kBlock];
+    s_flags[threadIdx.x] = -1;
+    s_matched[threadIdx.x] = 0;
+    const uint32_t i0 = blockIdx.x * kBlock;
+    const uint32_t iend = min(i0 + (uint32_t)kBlock, p.n);
+    const uint32_t i = i0 + threadIdx.x;
+    const bool active = i < p.n;
     T bmin[3], bmax[3];
-    if (leaf_mode == 0) {
-        T v[9];
-        #pragma unroll
-        for (int k = 0; k < 9; ++k) v[k] = __ldg(leaf_src + 9 * (size_t)id + k);
-        T c[3];
-        tri_bounds_center(v, bmin, bmax, c);
-        const DevTri<T> t = precompute_tri(v);
-        const uint4* s = reinterpret_cast<const uint4*>(&t);
-        uint4* d = reinterpret_cast<uint4*>(tris + i);
-        #pragma unroll
-        for (int k = 0; k < (int)(sizeof(DevTri<T>) / 16); ++k) d[k] = s[k];
-    } else {
-        #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            bmin[k] = __ldg(leaf_src + 6 * (size_t)id + k);
-            bmax[k] = __ldg(leaf_src + 6 * (size_t)id + 3 + k);
+    if (active) {
+        const uint32_t id = vals[i];
+        if (leaf_mode == 0) {
+            T v[9];
+            #pragma unroll
+            for (int k = 0; k < 9; ++k) v[k] = __ldg(leaf_src + 9 * (size_t)id + k);
+            T c[3];
+            tri_bounds_center(v, bmin, bmax, c);
+            const DevTri<T> t = precompute_tri(v);
+            const uint4* s = reinterpret_cast<const uint4*>(&t);
+            uint4* d = reinterpret_cast<uint4*>(tris + i);
+            #pragma unroll
+            for (int k = 0; k < (int)(sizeof(DevTri<T>) / 16); ++k) d[k] = s[k];
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                bmin[k] = __ldg(leaf_src + 6 * (size_t)id + k);
+                bmax[k] = __ldg(leaf_src + 6 * (size_t)id + 3 + k);
+            }
         }
     }
-    build_bottom_up<T, K, DeviceSync>(p, keys, i, bmin, bmax);
+    if (p.n == 1) {
+        if (active) build_bottom_up<T, K, DeviceSync>(p, keys, i, bmin, bmax);
+        return;
+    }
+    __syncthreads();
+    ClimbState<T> st;
+    uint32_t parent = 0, side = 0;
+    DevNode<T> own;
+    int outcome = kClimbDone;
+    if (active) {
+        climb_init(st, i, bmin, bmax);
+        const LocalSlots<T> loc { s_nodes, s_flags, s_matched };
+        outcome = climb_local<T, K, BlockSync>(p, keys, st, loc, i0, iend, parent, side, own);
+    }
+    __syncthreads();
+    if (outcome == kClimbDone) return;
+    if (outcome == kClimbWaiting && s_matched[parent - i0]) return;
+    climb_global<T, K, DeviceSync>(p, keys, st, parent, side, own);
 }
 
 template <typename T>

@@ -53,6 +53,7 @@ class HostEmul:
         L.emul_wide_build.restype = C.c_size_t
         L.emul_wide_build.argtypes = [P, P, C.c_size_t, P]
         L.emul_wide_trace.argtypes = [P, P, P, P, C.c_size_t, C.c_uint, P, P, P, P, P]
+        L.emul_set_block.argtypes = [C.c_int, C.c_int]
         L.emul_morton30.restype = C.c_uint32
         L.emul_morton30.argtypes = [C.c_uint32] * 3
         L.emul_morton63.restype = C.c_uint64
@@ -74,6 +75,10 @@ class HostEmul:
         getattr(self.lib, f"emul_build{s}")(_ptr(tris), _ptr(bboxes), _ptr(centers), n, min_leaf, max_leaf, morton_bits,
                                             _ptr(nodes), _ptr(ids), _ptr(dtris), C.byref(depth))
         return dict(nodes=nodes, prim_ids=ids, tris=dtris, depth=depth.value, dtype=dtype, n=n)
+
+    def set_block(self, leaves=0, order=0):
+        """0 leaves: every merge through the global flags; else the device kernel's block-local first phase."""
+        self.lib.emul_set_block(leaves, order)
 
     def compact(self, tree):
         n, dtype = tree["n"], tree["dtype"]

@@ -27,6 +27,8 @@ template <typename U> struct HostStack {
     bool empty() const { return sp == 0; }
 };
 
+static int g_block_leaves = 0, g_block_order = 0;
+
 template <typename T, typename K>
 uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t n, uint32_t min_leaf, uint32_t max_leaf,
                     DevNode<T>* nodes /* 2n slots */, uint32_t* prim_ids, DevTri<T>* tris, uint32_t* depth_out) {
@@ -57,8 +59,7 @@ uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t 
     BuildParams<T> p;
     p.nodes = nodes; p.flags = flags.data(); p.info = info; p.n = n;
     p.min_leaf = min_leaf; p.max_leaf = max_leaf;
-    for (uint32_t i = 0; i < n; ++i) {
-        T bmin[3], bmax[3];
+    auto leaf_box = [&] (uint32_t i, T bmin[3], T bmax[3]) {
         const uint32_t id = order[i];
         if (verts) {
             T c[3];
@@ -67,7 +68,44 @@ uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t 
         } else {
             for (int k = 0; k < 3; ++k) { bmin[k] = bboxes[6 * (size_t)id + k]; bmax[k] = bboxes[6 * (size_t)id + 3 + k]; }
         }
-        build_bottom_up<T, K, HostSync>(p, sorted.data(), i, bmin, bmax);
+    };
+    if (g_block_leaves <= 0 || n == 1) {
+        for (uint32_t i = 0; i < n; ++i) {
+            T bmin[3], bmax[3];
+            leaf_box(i, bmin, bmax);
+            build_bottom_up<T, K, HostSync>(p, sorted.data(), i, bmin, bmax);
+        }
+    } else {
+        // the device kernel's two phases (block-local merges, then global), one "block" at a time; within a
+        // block the leaves run in the order g_block_order selects (0 ascending, 1 descending, 2 interleaved)
+        const uint32_t B = (uint32_t)g_block_leaves;
+        std::vector<DevNode<T>> lnodes(2 * (size_t)B);
+        std::vector<int> lflags(B), lmatched(B);
+        struct Pending { ClimbState<T> s; uint32_t parent, side; DevNode<T> own; int outcome; };
+        std::vector<Pending> pend(B);
+        for (uint32_t i0 = 0; i0 < n; i0 += B) {
+            const uint32_t iend = i0 + B < n ? i0 + B : n;
+            std::fill(lflags.begin(), lflags.end(), -1);
+            std::fill(lmatched.begin(), lmatched.end(), 0);
+            LocalSlots<T> loc { lnodes.data(), lflags.data(), lmatched.data() };
+            const uint32_t m = iend - i0;
+            for (uint32_t k = 0; k < m; ++k) {
+                uint32_t j = k;
+                if (g_block_order == 1) j = m - 1 - k;
+                else if (g_block_order == 2) j = (k & 1) ? m - 1 - k / 2 : k / 2;
+                T bmin[3], bmax[3];
+                leaf_box(i0 + j, bmin, bmax);
+                Pending& q = pend[j];
+                climb_init(q.s, i0 + j, bmin, bmax);
+                q.outcome = climb_local<T, K, HostSync>(p, sorted.data(), q.s, loc, i0, iend, q.parent, q.side, q.own);
+            }
+            for (uint32_t j = 0; j < m; ++j) {
+                Pending& q = pend[j];
+                if (q.outcome == kClimbDone) continue;
+                if (q.outcome == kClimbWaiting && lmatched[q.parent - i0]) continue;
+                climb_global<T, K, HostSync>(p, sorted.data(), q.s, q.parent, q.side, q.own);
+            }
+        }
     }
     *depth_out = info[0];
     return info[1];
@@ -231,6 +269,7 @@ void emul_wide_trace(const void* wide, const void* tris, const uint32_t* prim_id
 }
 EMUL_API(float, 3f)
 EMUL_API(double, 3d)
+void emul_set_block(int leaves, int order) { g_block_leaves = leaves; g_block_order = order; }
 uint32_t emul_morton30(uint32_t x, uint32_t y, uint32_t z) { return MortonTraits<uint32_t>::encode(x, y, z); }
 uint64_t emul_morton63(uint64_t x, uint64_t y, uint64_t z) { return MortonTraits<uint64_t>::encode(x, y, z); }
 size_t emul_sizeof_node(int is_double) { return is_double ? sizeof(DevNode<double>) : sizeof(DevNode<float>); }

@@ -212,3 +212,22 @@ def test_wide_tree_is_conservative_and_equivalent(emul, oracle, kind, n):
         assert got[4].mean() < 0.75 * binary[4][:, 0].mean()      # fewer node fetches per ray
     rays2 = scenes.incoherent_rays(tris, 3000) if n >= 5 else rays
     assert_hits_equal(emul.wide_trace(tree, wide, rays2, 0)[:4], emul.trace(tree, rays2, TIE_LOWEST_ID)[:4], "wide incoherent")
+
+
+@pytest.mark.parametrize("kind,n,dtype", [("soup", 5000, np.float32), ("grid", 4232, np.float32), ("soup", 1777, np.float64)])
+def test_block_local_phase_builds_the_same_tree(emul, kind, n, dtype):
+    """The hierarchy kernel merges inside a block of consecutive leaves through shared memory first and only
+    then through global memory; every schedule must give the same nodes, bit for bit."""
+    tris = (scenes.soup(n, seed=5) if kind == "soup" else scenes.grid(46)).astype(dtype)
+    try:
+        emul.set_block(0, 0)
+        ref = emul.build(tris=tris)
+        for leaves in (2, 3, 32, 256, 1 << 20):
+            for order in (0, 1, 2):
+                emul.set_block(leaves, order)
+                got = emul.build(tris=tris)
+                assert got["depth"] == ref["depth"]
+                assert np.array_equal(got["nodes"].view(np.uint8), ref["nodes"].view(np.uint8)), (leaves, order)
+                assert np.array_equal(got["prim_ids"], ref["prim_ids"])
+    finally:
+        emul.set_block(0, 0)

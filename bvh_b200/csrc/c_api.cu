@@ -238,25 +238,25 @@ template <typename T> int ensure_device(Handle<T>& h) {
 
 // ---- reference semantics on the mirror ---------------------------------------------------------
 // Bvh::refit with no leaf function (reference bvh.h:184-218; c_api/bvh_impl.h:218-221).
-template <typename T> void refit_mirror(Handle<T>& h) {
-    const size_t n = h.nodes.size();
+template <typename T, int kDim, typename NodeVec> void refit_nodes(NodeVec& nodes) {
+    const size_t n = nodes.size();
     std::vector<size_t> parents(n, 0);
     std::vector<unsigned char> seen(n, 0);
     for (size_t i = 0; i < n; ++i) {
-        if (index_count(h.nodes[i].index) != 0) continue;
-        const size_t first = (size_t)index_first(h.nodes[i].index);
+        if (index_count(nodes[i].index) != 0) continue;
+        const size_t first = (size_t)index_first(nodes[i].index);
         if (first + 1 < n) { parents[first] = i; parents[first + 1] = i; }
     }
     for (size_t i = n; i-- > 0;) {
-        if (index_count(h.nodes[i].index) == 0) continue;
+        if (index_count(nodes[i].index) == 0) continue;
         seen[i] = 1;
         for (size_t j = parents[i];; j = parents[j]) {
-            auto& node = h.nodes[j];
+            auto& node = nodes[j];
             const size_t first = (size_t)index_first(node.index);
             if (seen[j] || index_count(node.index) != 0 || first + 1 >= n || !seen[first] || !seen[first + 1]) break;
-            const auto& l = h.nodes[first];
-            const auto& r = h.nodes[first + 1];
-            for (int k = 0; k < 3; ++k) {
+            const auto& l = nodes[first];
+            const auto& r = nodes[first + 1];
+            for (int k = 0; k < kDim; ++k) {
                 node.bounds[2 * k]     = robust_min(l.bounds[2 * k], r.bounds[2 * k]);
                 node.bounds[2 * k + 1] = robust_max(l.bounds[2 * k + 1], r.bounds[2 * k + 1]);
             }
@@ -265,26 +265,29 @@ template <typename T> void refit_mirror(Handle<T>& h) {
         }
     }
 }
+template <typename T> void refit_mirror(Handle<T>& h) { refit_nodes<T, 3>(h.nodes); }
 
 // Bvh::intersect for one ray with a host callback (reference bvh.h:124-182, c_api/bvh_impl.h:235-250).
-template <typename T, bool kAny, bool kRobust, typename Callback>
-void intersect_mirror(const Handle<T>& h, const T* ray8, const Callback* cb) {
+// `nodes` is the mirror in the reference layout (Node<T, kDim>), `ray` = org[kDim] dir[kDim] tmin tmax.
+template <typename T, bool kAny, bool kRobust, int kDim, typename NodeVec, typename Callback>
+void intersect_nodes(const NodeVec& nodes, const T* ray, const Callback* cb) {
     using U = typename Real<T>::UInt;
     RayCtx<T> r;
-    for (int k = 0; k < 3; ++k) { r.org[k] = ray8[k]; r.dir[k] = ray8[3 + k]; }
-    r.tmin = ray8[6]; r.tmax = ray8[7];
-    ray_prologue<T, kRobust>(r);
+    for (int k = 0; k < 3; ++k) { r.org[k] = 0; r.dir[k] = 0; r.inv_dir[k] = 0; r.aux[k] = 0; }
+    for (int k = 0; k < kDim; ++k) { r.org[k] = ray[k]; r.dir[k] = ray[kDim + k]; }
+    r.tmin = ray[2 * kDim]; r.tmax = ray[2 * kDim + 1];
+    ray_prologue<T, kRobust, kDim>(r);
     U stack[64];                                           // SmallStack<Index, 64>, bvh_impl.h:241
     unsigned sp = 0;
-    U top = h.nodes[0].index;
+    U top = nodes[0].index;
     for (;;) {
         bool alive = true;
         while (index_count(top) == 0) {
-            const auto& left = h.nodes[(size_t)index_first(top)];
-            const auto& right = h.nodes[(size_t)index_first(top) + 1];
+            const auto& left = nodes[(size_t)index_first(top)];
+            const auto& right = nodes[(size_t)index_first(top) + 1];
             T l0, l1, r0, r1;
-            node_test<T, kRobust>(left.bounds, r, l0, l1);
-            node_test<T, kRobust>(right.bounds, r, r0, r1);
+            node_test<T, kRobust, kDim>(left.bounds, r, l0, l1);
+            node_test<T, kRobust, kDim>(right.bounds, r, r0, r1);
             const bool hl = l0 <= l1, hr = r0 <= r1;
             if (hl) {
                 U near_i = left.index;
@@ -304,6 +307,11 @@ void intersect_mirror(const Handle<T>& h, const T* ray8, const Callback* cb) {
         if (sp == 0) break;
         top = stack[--sp];
     }
+}
+
+template <typename T, bool kAny, bool kRobust, typename Callback>
+void intersect_mirror(const Handle<T>& h, const T* ray8, const Callback* cb) {
+    intersect_nodes<T, kAny, kRobust, 3>(h.nodes, ray8, cb);
 }
 
 template <typename T> BuildOptions translate_config(const bvh_build_config* config) {
@@ -449,6 +457,68 @@ template <typename T> Handle<T>* load_mirror(FILE* file) {
     for (auto& id : h->prim_ids) { U v = 0; if (fread(&v, sizeof(U), 1, file) != 1) v = 0; id = (size_t)v; }
     h->host_valid = true;
     h->device_valid = false;
+    return h;
+}
+
+// ---- 2-D suffixes (reference c_api/bvh.cpp:7-25 instantiates bvh2f / bvh2d next to the 3-D ones) ----------
+// The reference has no 2-D primitive type: leaves are intersected by the caller's callback, one ray per call,
+// so there is no batched device traversal to offer here.  What the GPU does is the BUILD: the boxes are lifted
+// to z = 0, the LBVH pipeline runs as for 3-D (the z bits of the Morton keys are all zero, so the order is the
+// 2-D Z-curve), and the result comes back as a host tree of the reference's Node<T, 2> (4 bounds + index,
+// 20 / 40 bytes) on which every other entry point works exactly as the reference's does.
+template <typename T> struct HostNode2 { T bounds[4]; typename Real<T>::UInt index; };
+static_assert(sizeof(HostNode2<float>) == 20 && sizeof(HostNode2<double>) == 40, "reference Node<T,2> layout");
+
+template <typename T> struct Handle2 {
+    std::vector<HostNode2<T>> nodes;
+    std::vector<size_t> prim_ids;
+};
+
+template <typename T>
+Handle2<T>* build_handle2(const T* bboxes4, const T* centers2, size_t n, const bvh_build_config* config) {
+    if (n == 0) { set_error("build: prim_count out of range"); return nullptr; }
+    std::vector<T> boxes(6 * n), centers(3 * n);
+    for (size_t i = 0; i < n; ++i) {                       // bvh_bbox2 = {min.x, min.y, max.x, max.y}
+        boxes[6 * i + 0] = bboxes4[4 * i + 0]; boxes[6 * i + 1] = bboxes4[4 * i + 1]; boxes[6 * i + 2] = 0;
+        boxes[6 * i + 3] = bboxes4[4 * i + 2]; boxes[6 * i + 4] = bboxes4[4 * i + 3]; boxes[6 * i + 5] = 0;
+        centers[3 * i + 0] = centers2[2 * i + 0]; centers[3 * i + 1] = centers2[2 * i + 1]; centers[3 * i + 2] = 0;
+    }
+    Handle<T>* lifted = build_handle<T>(nullptr, boxes.data(), centers.data(), n, config, false);
+    if (!lifted) return nullptr;
+    if (download_mirror(*lifted)) { destroy_handle(lifted); return nullptr; }
+    auto h = new Handle2<T>();
+    h->nodes.resize(lifted->nodes.size());
+    for (size_t i = 0; i < h->nodes.size(); ++i) {
+        std::memcpy(h->nodes[i].bounds, lifted->nodes[i].bounds, 4 * sizeof(T));
+        h->nodes[i].index = lifted->nodes[i].index;
+    }
+    h->prim_ids = lifted->prim_ids;
+    destroy_handle(lifted);
+    return h;
+}
+
+template <typename T> void save_nodes2(const Handle2<T>& h, FILE* file) {
+    using U = typename Real<T>::UInt;
+    U v = (U)h.nodes.size(); fwrite(&v, sizeof v, 1, file);
+    v = (U)h.prim_ids.size(); fwrite(&v, sizeof v, 1, file);
+    for (const auto& n : h.nodes) { fwrite(n.bounds, sizeof(T), 4, file); fwrite(&n.index, sizeof(U), 1, file); }
+    for (size_t id : h.prim_ids) { v = (U)id; fwrite(&v, sizeof v, 1, file); }
+}
+
+template <typename T> Handle2<T>* load_nodes2(FILE* file) {
+    using U = typename Real<T>::UInt;
+    auto h = new Handle2<T>();
+    U node_count = 0, prim_count = 0;
+    if (fread(&node_count, sizeof(U), 1, file) != 1) node_count = 0;
+    if (fread(&prim_count, sizeof(U), 1, file) != 1) prim_count = 0;
+    h->nodes.resize((size_t)node_count);
+    h->prim_ids.resize((size_t)prim_count);
+    for (auto& n : h->nodes) {
+        std::memset(&n, 0, sizeof n);
+        if (fread(n.bounds, sizeof(T), 4, file) != 4) std::memset(n.bounds, 0, sizeof n.bounds);
+        if (fread(&n.index, sizeof(U), 1, file) != 1) n.index = 0;
+    }
+    for (auto& id : h->prim_ids) { U v = 0; if (fread(&v, sizeof(U), 1, file) != 1) v = 0; id = (size_t)v; }
     return h;
 }
 
@@ -633,36 +703,63 @@ BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete p
 BVH_IMPL_3D(float, 3f, bvh_intersect_callbackf)
 BVH_IMPL_3D(double, 3d, bvh_intersect_callbackd)
 
-// 2-D suffixes: part of the reference ABI (c_api/bvh.cpp:7-25) but outside this round's hot path
-// (SURVEY.md §8(f) rank 4).  The symbols exist so that callers link; they report "not implemented".
-#define BVH_STUB_2D(T, S, CALLBACK)                                                                                \
-    static void not_impl##S() { set_error("bvh" #S ": 2-D instantiation is not implemented in this build"); }      \
-    BVH_EXPORT struct bvh##S* bvh##S##_build(struct bvh_thread_pool*, const struct bvh_bbox##S*, const struct bvh_vec##S*, \
-            size_t, const struct bvh_build_config*) { not_impl##S(); return nullptr; }                             \
-    BVH_EXPORT void bvh##S##_destroy(struct bvh##S*) {}                                                            \
-    BVH_EXPORT void bvh##S##_save(const struct bvh##S*, FILE*) { not_impl##S(); }                                  \
-    BVH_EXPORT struct bvh##S* bvh##S##_load(FILE*) { not_impl##S(); return nullptr; }                              \
-    BVH_EXPORT struct bvh_node##S* bvh##S##_get_node(struct bvh##S*, size_t) { not_impl##S(); return nullptr; }    \
-    BVH_EXPORT size_t bvh##S##_get_prim_id(const struct bvh##S*, size_t) { not_impl##S(); return BVH_INVALID_PRIM_ID; } \
-    BVH_EXPORT size_t bvh##S##_get_prim_count(const struct bvh##S*) { not_impl##S(); return 0; }                   \
-    BVH_EXPORT size_t bvh##S##_get_node_count(const struct bvh##S*) { not_impl##S(); return 0; }                   \
-    BVH_EXPORT bool bvh_node##S##_is_leaf(const struct bvh_node##S*) { not_impl##S(); return true; }               \
-    BVH_EXPORT size_t bvh_node##S##_get_prim_count(const struct bvh_node##S*) { not_impl##S(); return 0; }         \
-    BVH_EXPORT void bvh_node##S##_set_prim_count(struct bvh_node##S*, size_t) { not_impl##S(); }                   \
-    BVH_EXPORT size_t bvh_node##S##_get_first_id(const struct bvh_node##S*) { not_impl##S(); return 0; }           \
-    BVH_EXPORT void bvh_node##S##_set_first_id(struct bvh_node##S*, size_t) { not_impl##S(); }                     \
-    BVH_EXPORT struct bvh_bbox##S bvh_node##S##_get_bbox(const struct bvh_node##S*) { not_impl##S(); return bvh_bbox##S {}; } \
-    BVH_EXPORT void bvh_node##S##_set_bbox(struct bvh_node##S*, const struct bvh_bbox##S*) { not_impl##S(); }      \
-    BVH_EXPORT void bvh##S##_append_node(struct bvh##S*) { not_impl##S(); }                                        \
-    BVH_EXPORT void bvh##S##_remove_last_node(struct bvh##S*) { not_impl##S(); }                                   \
-    BVH_EXPORT void bvh##S##_refit(struct bvh##S*) { not_impl##S(); }                                              \
-    BVH_EXPORT void bvh##S##_optimize(struct bvh_thread_pool*, struct bvh##S*) { not_impl##S(); }                  \
-    BVH_EXPORT void bvh##S##_intersect_ray_any(const struct bvh##S*, const struct bvh_ray##S*, const struct CALLBACK*) { not_impl##S(); } \
-    BVH_EXPORT void bvh##S##_intersect_ray_any_robust(const struct bvh##S*, const struct bvh_ray##S*, const struct CALLBACK*) { not_impl##S(); } \
-    BVH_EXPORT void bvh##S##_intersect_ray(const struct bvh##S*, const struct bvh_ray##S*, const struct CALLBACK*) { not_impl##S(); } \
-    BVH_EXPORT void bvh##S##_intersect_ray_robust(const struct bvh##S*, const struct bvh_ray##S*, const struct CALLBACK*) { not_impl##S(); }
+#define H2(T, bvh) (reinterpret_cast<Handle2<T>*>(bvh))
+#define HC2(T, bvh) (reinterpret_cast<const Handle2<T>*>(bvh))
+#define N2(T, node) (reinterpret_cast<HostNode2<T>*>(node))
+#define NC2(T, node) (reinterpret_cast<const HostNode2<T>*>(node))
 
-BVH_STUB_2D(float, 2f, bvh_intersect_callbackf)
-BVH_STUB_2D(double, 2d, bvh_intersect_callbackd)
+#define BVH_IMPL_2D(T, S, CALLBACK)                                                                                \
+    BVH_EXPORT struct bvh##S* bvh##S##_build(struct bvh_thread_pool*, const struct bvh_bbox##S* bboxes,            \
+            const struct bvh_vec##S* centers, size_t prim_count, const struct bvh_build_config* config) {          \
+        return reinterpret_cast<bvh##S*>(build_handle2<T>(reinterpret_cast<const T*>(bboxes),                      \
+            reinterpret_cast<const T*>(centers), prim_count, config));                                             \
+    }                                                                                                              \
+    BVH_EXPORT void bvh##S##_destroy(struct bvh##S* bvh) { delete H2(T, bvh); }                                    \
+    BVH_EXPORT void bvh##S##_save(const struct bvh##S* bvh, FILE* file) { save_nodes2(*HC2(T, bvh), file); }       \
+    BVH_EXPORT struct bvh##S* bvh##S##_load(FILE* file) { return reinterpret_cast<bvh##S*>(load_nodes2<T>(file)); } \
+    BVH_EXPORT struct bvh_node##S* bvh##S##_get_node(struct bvh##S* bvh, size_t node_id) {                         \
+        auto h = H2(T, bvh);                                                                                       \
+        return node_id < h->nodes.size() ? reinterpret_cast<bvh_node##S*>(&h->nodes[node_id]) : nullptr;           \
+    }                                                                                                              \
+    BVH_EXPORT size_t bvh##S##_get_prim_id(const struct bvh##S* bvh, size_t i) {                                   \
+        auto h = HC2(T, bvh);                                                                                      \
+        return i < h->prim_ids.size() ? h->prim_ids[i] : BVH_INVALID_PRIM_ID;                                      \
+    }                                                                                                              \
+    BVH_EXPORT size_t bvh##S##_get_prim_count(const struct bvh##S* bvh) { return HC2(T, bvh)->prim_ids.size(); }   \
+    BVH_EXPORT size_t bvh##S##_get_node_count(const struct bvh##S* bvh) { return HC2(T, bvh)->nodes.size(); }      \
+    BVH_EXPORT bool bvh_node##S##_is_leaf(const struct bvh_node##S* node) { return index_count(NC2(T, node)->index) != 0; } \
+    BVH_EXPORT size_t bvh_node##S##_get_prim_count(const struct bvh_node##S* node) { return index_count(NC2(T, node)->index); } \
+    BVH_EXPORT void bvh_node##S##_set_prim_count(struct bvh_node##S* node, size_t count) {                         \
+        using U = Real<T>::UInt;                                                                                   \
+        N2(T, node)->index = make_index<U>(index_first(N2(T, node)->index), (uint32_t)(count & kMaxLeafPrims));    \
+    }                                                                                                              \
+    BVH_EXPORT size_t bvh_node##S##_get_first_id(const struct bvh_node##S* node) { return (size_t)index_first(NC2(T, node)->index); } \
+    BVH_EXPORT void bvh_node##S##_set_first_id(struct bvh_node##S* node, size_t first_id) {                        \
+        using U = Real<T>::UInt;                                                                                   \
+        N2(T, node)->index = make_index<U>((U)first_id, index_count(N2(T, node)->index));                          \
+    }                                                                                                              \
+    BVH_EXPORT struct bvh_bbox##S bvh_node##S##_get_bbox(const struct bvh_node##S* node) {                         \
+        const T* b = NC2(T, node)->bounds;                                                                         \
+        return bvh_bbox##S { { b[0], b[2] }, { b[1], b[3] } };                                                     \
+    }                                                                                                              \
+    BVH_EXPORT void bvh_node##S##_set_bbox(struct bvh_node##S* node, const struct bvh_bbox##S* bbox) {             \
+        T* b = N2(T, node)->bounds;                                                                                \
+        b[0] = bbox->min.x; b[1] = bbox->max.x; b[2] = bbox->min.y; b[3] = bbox->max.y;                            \
+    }                                                                                                              \
+    BVH_EXPORT void bvh##S##_append_node(struct bvh##S* bvh) { H2(T, bvh)->nodes.emplace_back(); }                 \
+    BVH_EXPORT void bvh##S##_remove_last_node(struct bvh##S* bvh) { if (!H2(T, bvh)->nodes.empty()) H2(T, bvh)->nodes.pop_back(); } \
+    BVH_EXPORT void bvh##S##_refit(struct bvh##S* bvh) { refit_nodes<T, 2>(H2(T, bvh)->nodes); }                   \
+    BVH_EXPORT void bvh##S##_optimize(struct bvh_thread_pool*, struct bvh##S*) {}                                  \
+    BVH_EXPORT void bvh##S##_intersect_ray_any(const struct bvh##S* bvh, const struct bvh_ray##S* ray, const struct CALLBACK* cb) { \
+        intersect_nodes<T, true, false, 2>(HC2(T, bvh)->nodes, reinterpret_cast<const T*>(ray), cb); }            \
+    BVH_EXPORT void bvh##S##_intersect_ray_any_robust(const struct bvh##S* bvh, const struct bvh_ray##S* ray, const struct CALLBACK* cb) { \
+        intersect_nodes<T, true, true, 2>(HC2(T, bvh)->nodes, reinterpret_cast<const T*>(ray), cb); }             \
+    BVH_EXPORT void bvh##S##_intersect_ray(const struct bvh##S* bvh, const struct bvh_ray##S* ray, const struct CALLBACK* cb) { \
+        intersect_nodes<T, false, false, 2>(HC2(T, bvh)->nodes, reinterpret_cast<const T*>(ray), cb); }           \
+    BVH_EXPORT void bvh##S##_intersect_ray_robust(const struct bvh##S* bvh, const struct bvh_ray##S* ray, const struct CALLBACK* cb) { \
+        intersect_nodes<T, false, true, 2>(HC2(T, bvh)->nodes, reinterpret_cast<const T*>(ray), cb); }
+
+BVH_IMPL_2D(float, 2f, bvh_intersect_callbackf)
+BVH_IMPL_2D(double, 2d, bvh_intersect_callbackd)
 
 } // extern "C"

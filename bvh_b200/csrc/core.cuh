@@ -199,10 +199,10 @@ template <typename T> struct RayCtx {
 };
 
 // reference bvh.h:161-165
-template <typename T, bool kRobust> BVH_HD void ray_prologue(RayCtx<T>& r) {
+template <typename T, bool kRobust, int kDim = 3> BVH_HD void ray_prologue(RayCtx<T>& r) {
     using R = Real<T>;
     r.oct = 0;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < kDim; ++i) {
         // ray.h:29-34: get_inv_dir<SafeInverse = !IsRobust>
         r.inv_dir[i] = kRobust ? R::div((T)1, r.dir[i]) : safe_inverse(r.dir[i]);
         if (kRobust) r.aux[i] = add_ulp_magnitude(r.inv_dir[i], 2);           // ray.h:46-48
@@ -232,10 +232,11 @@ template <typename T> inline T acc_min(T tf, T t1) { return robust_min(tf, t1); 
 template <typename T> BVH_HD bool ray_interval_is_nan(const RayCtx<T>& r) { return r.tmin != r.tmin || r.tmax != r.tmax; }
 
 // reference node.h:68-88 + make_intersection_result (:105-117).  b = [minx,maxx,miny,maxy,minz,maxz]
-template <typename T, bool kRobust> BVH_HD void node_test(const T b[6], const RayCtx<T>& r, T& t0, T& t1) {
+// (kDim = 2: [minx,maxx,miny,maxy], the reference's Node<T, 2>)
+template <typename T, bool kRobust, int kDim = 3> BVH_HD void node_test(const T* b, const RayCtx<T>& r, T& t0, T& t1) {
     using R = Real<T>;
     t0 = r.tmin; t1 = r.tmax;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < kDim; ++i) {
         const bool neg = (r.oct >> i) & 1u;
         const T bnear = neg ? b[2 * i + 1] : b[2 * i];       // get_min_bounds(octant), :59-61
         const T bfar  = neg ? b[2 * i] : b[2 * i + 1];       // get_max_bounds(octant), :63-65

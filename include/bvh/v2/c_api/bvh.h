@@ -12,8 +12,9 @@
  *   3d      double  3     struct bvh3d  struct bvh_node3d  bvh_intersect_callbackd
  *
  * Semantics that differ from the reference are listed in INTEGRATION.md; in short: bvhNN_build
- * builds on the GPU (the thread pool argument is ignored), bvhNN_optimize keeps the tree as is,
- * the 2-D suffixes are not implemented yet (they return NULL / do nothing and set bvh_last_error()).
+ * builds on the GPU (the thread pool argument is ignored), bvhNN_optimize keeps the tree as is.
+ * The 2-D suffixes build on the GPU as well (boxes lifted to z = 0) and then live on the host: the
+ * reference has no 2-D primitive type, leaves are intersected by the caller's callback one ray per call.
  * The batched GPU entry points live in <bvh_b200.h>.
  */
 #ifndef BVH_V2_C_API_BVH_H

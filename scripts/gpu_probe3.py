@@ -9,6 +9,7 @@ from bvh_b200 import scenes
 
 W = H = 3163
 tris = scenes.soup(1_000_000)
+api.lib().bvh_cuda_set_stream(None)          # legacy default stream: torch events then bracket the kernels
 bvh = api.Bvh.build_triangles(tris)
 
 def timed(fn, reps=20, warm=3):
@@ -21,7 +22,6 @@ def timed(fn, reps=20, warm=3):
         times.append(a.elapsed_time(b))
     return float(np.median(times))
 
-api.lib().bvh_cuda_set_stream(None)
 rays_np = scenes.make_primary("soup", W, H)
 x, y = np.meshgrid(np.arange(W), np.arange(H))          # row-major pixel coordinates
 x = x.ravel(); y = y.ravel()

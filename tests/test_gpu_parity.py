@@ -296,15 +296,19 @@ def test_full_size_properties(gpu_lib, oracle, kind):
     for variant in api.KERNELS:
         other = bvh.intersect_rays(rays, flags=variant)
         assert (other.view(np.uint8) == hits.view(np.uint8)).all(), variant
-    # the compressed 4-wide path is conservative: it may only differ from the fast binary traversal where
-    # the fast slab test is not watertight (a ray grazing a box face exactly), and there it must agree with
-    # the watertight ROBUST binary traversal
+    # the compressed 4-wide path is conservative: every ray / triangle pair the fast binary traversal tests is
+    # tested here too, so it may only differ where the fast slab test is not watertight (a hit point exactly on
+    # a box face: the leaf holding the other triangle of a shared edge is culled by one ulp), and there it can
+    # only report a closer hit, or the same distance with a lower id — and that hit must be a real one
     wide = bvh.intersect_rays(rays, flags=api.KERNEL_WIDE)
-    differs = (wide.view(np.uint8).reshape(m, 16) != hits.view(np.uint8).reshape(m, 16)).any(axis=1)
-    assert differs.mean() < 1e-5, int(differs.sum())
-    if differs.any():
-        robust = bvh.intersect_rays(rays[differs], flags=api.ROBUST)
-        assert (robust.view(np.uint8) == wide[differs].view(np.uint8)).all()
+    differs = np.nonzero((wide.view(np.uint8).reshape(m, 16) != hits.view(np.uint8).reshape(m, 16)).any(axis=1))[0]
+    assert differs.size < 1e-5 * m, differs.size
+    for i in differs:
+        w, h = wide[i], hits[i]
+        assert w["prim_id"] != INVALID
+        assert w["t"] < h["t"] or (w["t"] == h["t"] and w["prim_id"] < h["prim_id"])
+        one = oracle.brute_force(tris[w["prim_id"]:w["prim_id"] + 1], rays[i:i + 1])
+        assert one[0][0] == 0 and one[1][0] == w["t"] and one[2][0] == w["u"] and one[3][0] == w["v"]
     # nothing lies in front of a reported closest hit: re-trace with tmax just below t as any-hit
     sel = np.nonzero(hit)[0][:: max(1, int(hit.sum()) // 200_000)]
     shortened = rays[sel].copy()

@@ -162,22 +162,39 @@ struct BlockSync {
 };
 
 // K4.  leaf_mode 0: verts (n x 9), also writes BVH-order triangles; 1: bboxes (n x 6, min3 max3).
-// Two phases (build_core.cuh): merges whose two children lie inside this block's kBlock consecutive leaves
-// meet in shared memory; after one block barrier, whatever reached a block wall or was not matched locally
-// carries on through the global arrival flags.
+// One block per kLeaves consecutive sorted leaves, two phases (build_core.cuh): merges whose two children lie
+// inside the block meet in shared memory, in rounds over a compacted work list; then the nodes that reached
+// a block wall or were not matched locally are compacted once more and carry on through the global arrival
+// flags.  Keys of the block (plus one neighbour on each side) are staged in shared memory for the delta tests.
+template <typename T> struct HierarchyCfg { static constexpr int kLeaves = sizeof(T) == 4 ? 256 : 128; };
+
 template <typename T, typename K>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(HierarchyCfg<T>::kLeaves)
 hierarchy_kernel(BuildParams<T> p, const K* __restrict__ keys, const uint32_t* __restrict__ vals,
                  const T* __restrict__ leaf_src, int leaf_mode, DevTri<T>* __restrict__ tris) {
-    __shared__ DevNode<T> s_nodes[2 * kBlock];
-    __shared__ int s_flags[kBlock];
-    __shared__ int s_matched[kBlock];
-    s_flags[threadIdx.x] = -1;
-    s_matched[threadIdx.x] = 0;
-    const uint32_t i0 = blockIdx.x * kBlock;
-    const uint32_t iend = min(i0 + (uint32_t)kBlock, p.n);
-    const uint32_t i = i0 + threadIdx.x;
+    constexpr int B = HierarchyCfg<T>::kLeaves;
+    __shared__ DevNode<T> s_nodes[2 * B];
+    __shared__ ClimbItem<T> s_items[B];          // rounds: two lists of B/2; afterwards: the global climbers
+    __shared__ ClimbItem<T> s_walls[2];
+    __shared__ int s_flags[B];
+    __shared__ int s_info[B];
+    __shared__ K s_keys[B + 2];
+    __shared__ int s_count[3];
+    __shared__ int s_wall_count, s_global_count;
+    const uint32_t t = threadIdx.x;
+    const uint32_t i0 = blockIdx.x * B;
+    const uint32_t iend = min(i0 + (uint32_t)B, p.n);
+    const uint32_t m = iend - i0;
+    const uint32_t i = i0 + t;
     const bool active = i < p.n;
+    s_flags[t] = -1;
+    s_info[t] = 0;
+    if (t < 3) s_count[t] = 0;
+    if (t == 0) { s_wall_count = 0; s_global_count = 0; }
+    for (uint32_t j = t; j < m + 2; j += B) {               // s_keys[j] = keys[i0 - 1 + j]
+        const int64_t src = (int64_t)i0 - 1 + j;
+        if (src >= 0 && src < (int64_t)p.n) s_keys[j] = keys[src];
+    }
     T bmin[3], bmax[3];
     if (active) {
         const uint32_t id = vals[i];
@@ -187,8 +204,8 @@ hierarchy_kernel(BuildParams<T> p, const K* __restrict__ keys, const uint32_t* _
             for (int k = 0; k < 9; ++k) v[k] = __ldg(leaf_src + 9 * (size_t)id + k);
             T c[3];
             tri_bounds_center(v, bmin, bmax, c);
-            const DevTri<T> t = precompute_tri(v);
-            const uint4* s = reinterpret_cast<const uint4*>(&t);
+            const DevTri<T> tri = precompute_tri(v);
+            const uint4* s = reinterpret_cast<const uint4*>(&tri);
             uint4* d = reinterpret_cast<uint4*>(tris + i);
             #pragma unroll
             for (int k = 0; k < (int)(sizeof(DevTri<T>) / 16); ++k) d[k] = s[k];
@@ -205,19 +222,41 @@ hierarchy_kernel(BuildParams<T> p, const K* __restrict__ keys, const uint32_t* _
         return;
     }
     __syncthreads();
-    ClimbState<T> st;
-    uint32_t parent = 0, side = 0;
-    DevNode<T> own;
-    int outcome = kClimbDone;
-    if (active) {
-        climb_init(st, i, bmin, bmax);
-        const LocalSlots<T> loc { s_nodes, s_flags, s_matched };
-        outcome = climb_local<T, K, BlockSync>(p, keys, st, loc, i0, iend, parent, side, own);
+
+    const LocalSlots<T> loc { s_nodes, s_flags, s_info };
+    const K* local_keys = s_keys + 1 - (ptrdiff_t)i0;         // local_keys[i] = keys[i] for i in [i0 - 1, iend]
+    uint32_t count = m;
+    for (uint32_t round = 0; count > 0; ++round) {
+        ClimbItem<T>* in = s_items + (round & 1u) * (B / 2);
+        ClimbItem<T>* out = s_items + ((round + 1) & 1u) * (B / 2);
+        if (t == 0) s_count[(round + 2) % 3] = 0;
+        if (t < count) {
+            ClimbState<T> st;
+            if (round == 0) climb_init(st, i, bmin, bmax);
+            else st = in[t].s;
+            uint32_t parent, side;
+            const int outcome = local_step<T, K, BlockSync>(p, local_keys, st, loc, i0, iend, parent, side);
+            if (outcome == kStepCarry) out[atomicAdd(&s_count[(round + 1) % 3], 1)].s = st;
+            else if (outcome == kStepWall) {
+                ClimbItem<T>& w = s_walls[atomicAdd(&s_wall_count, 1)];
+                w.s = st; w.parent = parent; w.side = side;
+            }
+        }
+        __syncthreads();
+        count = (uint32_t)s_count[(round + 1) % 3];
     }
+
+    // whatever must go on globally, compacted: first arrivals nobody matched, and the (at most two) wall nodes
+    if (t + 1 < m) {
+        ClimbItem<T> item; DevNode<T> own;
+        if (unmatched_first(loc, i0, t, item, own)) s_items[atomicAdd(&s_global_count, 1)] = item;
+    }
+    if ((int)t < s_wall_count) s_items[atomicAdd(&s_global_count, 1)] = s_walls[t];
     __syncthreads();
-    if (outcome == kClimbDone) return;
-    if (outcome == kClimbWaiting && s_matched[parent - i0]) return;
-    climb_global<T, K, DeviceSync>(p, keys, st, parent, side, own);
+    for (uint32_t k = t; k < (uint32_t)s_global_count; k += B) {
+        ClimbItem<T> item = s_items[k];
+        climb_global<T, K, DeviceSync>(p, keys, item.s, item.parent, item.side, published_record(item.s));
+    }
 }
 
 template <typename T>
@@ -443,7 +482,10 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     p.min_leaf = options.min_leaf < 1 ? 1 : options.min_leaf;
     p.max_leaf = options.max_leaf > kMaxLeafPrims ? kMaxLeafPrims : (options.max_leaf < 1 ? 1 : options.max_leaf);
     if (p.min_leaf > p.max_leaf) p.min_leaf = p.max_leaf;
-    hierarchy_kernel<T, K><<<blocks_needed, kBlock, 0, stream>>>(p, keys_a, out.prim_ids, leaf_src, mode, out.tris);
+    {
+        constexpr uint32_t leaves = HierarchyCfg<T>::kLeaves;
+        hierarchy_kernel<T, K><<<(n + leaves - 1) / leaves, leaves, 0, stream>>>(p, keys_a, out.prim_ids, leaf_src, mode, out.tris);
+    }
     BVH_CUDA_TRY(cudaGetLastError());
 
     uint32_t host_info[4] = { 0, 0, 0, 0 };

@@ -296,28 +296,24 @@ BVH_HD void build_bottom_up(const BuildParams<T>& p, const K* __restrict__ keys,
 // ---- block-local first phase -------------------------------------------------------------------------
 // A block of consecutive sorted leaves [i0, iend) first merges, through SHARED memory, every pair of nodes
 // that meets at a boundary strictly inside the block (the merges of the final tree whose both children lie
-// in the block — about 95 % of all merges for 256-leaf blocks).  The phase runs in ROUNDS over a compacted
-// work list: round 0 holds the leaves, every merge appends the merged node to the next round's list, so the
-// lanes of a warp stay busy (a thread-per-leaf climb leaves 7 of 32 lanes active on average).  Nodes whose
-// parent boundary is a block wall, and first arrivals nobody matched locally, are collected afterwards and
-// continue through global memory (climb_global), again compacted.  The tree is the same as with the
-// global-only pass: the same merges happen, only where the two arrivals meet differs.
-template <typename T> struct ClimbItem { ClimbState<T> s; uint32_t parent, side; };
-
+// in the block — about 95 % of all merges for 128-leaf blocks); only nodes whose parent boundary is a block
+// wall, or whose sibling never showed up locally, continue through global memory (climb_global).  The tree
+// is the same as with the global-only pass: the same merges happen, only where the two arrivals meet differs.
 template <typename T> struct LocalSlots {
     DevNode<T>* nodes;      // [2 * block_leaves]: record of child `side` of boundary p at 2 * (p - i0) + side
     int* flags;             // [block_leaves]: -1, or the far boundary of the first arrival
-    int* info;              // [block_leaves]: bit 0 = side of the first arrival, bit 1 = matched by a second one
+    int* info;              // [block_leaves]: non-zero once a second arrival has matched the first
 };
 
 enum StepOutcome : int { kStepRetired = 0, kStepCarry = 1, kStepWall = 2 };
 
 // One step of one node in the local phase: choose the parent, publish, meet the sibling if it is there.
-//   kStepRetired  first arrival at a local boundary (its record waits in loc.nodes), or the root was written
-//   kStepCarry    merged with its sibling: `s` is the parent node, to be stepped again in the next round
-//   kStepWall     the chosen boundary is a block wall: (s, parent, side) continues with climb_global; its
-//                 record is already published in global memory
-// `keys` may point to a shared-memory copy of keys[i0 - 1 .. iend] (biased so that keys[i] works).
+//   kStepRetired  first arrival at a local boundary (its record waits in loc.nodes; after the block barrier
+//                 loc.info[parent - i0] tells whether a sibling came), or the root was written
+//   kStepCarry    merged with its sibling: `s` is now the parent node, to be stepped again
+//   kStepWall     the chosen boundary is a block wall: (s, parent, side) continues with climb_global
+// In the last two cases and for an unmatched first arrival the node's record is already published in global
+// memory and equals published_record(s).
 template <typename T, typename K, typename LocalSync>
 BVH_HD int local_step(const BuildParams<T>& p, const K* keys, ClimbState<T>& s, const LocalSlots<T>& loc,
                       uint32_t i0, uint32_t iend, uint32_t& parent, uint32_t& side) {
@@ -326,36 +322,16 @@ BVH_HD int local_step(const BuildParams<T>& p, const K* keys, ClimbState<T>& s, 
     if (parent < i0 || parent + 1 >= iend) return kStepWall;
     const uint32_t q = parent - i0;
     loc.nodes[2 * q + side] = own;
-    LocalSync::fence();
+    LocalSync::fence();                                     // record before flag (release) ...
     const int other = LocalSync::exchange(loc.flags + q, (int)(side == 0 ? s.l : s.r));
     if (other < 0) return kStepRetired;
-    LocalSync::fence();
+    LocalSync::fence();                                     // ... flag before the sibling's record (acquire)
     loc.info[q] = 2;
     const DevNode<T> sn = loc.nodes[2 * q + (1 - side)];
     return merge_into_parent(p, s, parent, side, own, sn, (uint32_t)other) ? kStepRetired : kStepCarry;
 }
 
-// After the rounds: is local boundary q (parent = i0 + q) held by a first arrival nobody matched?  If so,
-// rebuilds that node's state from what it left in the slots.  The side is recovered from the range: the far
-// boundary it exchanged is its l (<= parent, side 0) or its r (> parent, side 1).
-template <typename T>
-BVH_HD bool unmatched_first(const LocalSlots<T>& loc, uint32_t i0, uint32_t q, ClimbItem<T>& item, DevNode<T>& own) {
-    const int far = loc.flags[q];
-    if (far < 0 || loc.info[q] != 0) return false;
-    const uint32_t parent = i0 + q;
-    const uint32_t side = (uint32_t)far <= parent ? 0u : 1u;
-    own = loc.nodes[2 * q + side];
-    item.parent = parent; item.side = side;
-    item.s.l = side == 0 ? (uint32_t)far : parent + 1;
-    item.s.r = side == 0 ? parent : (uint32_t)far;
-    for (int k = 0; k < 3; ++k) { item.s.bmin[k] = own.bounds[2 * k]; item.s.bmax[k] = own.bounds[2 * k + 1]; }
-    item.s.index = own.index;
-    item.s.cost = AuxPack<T>::cost(own.pad);
-    item.s.depth = AuxPack<T>::depth(own.pad);
-    return true;
-}
-
-// The record a node has published as child `side` of `parent` (what publish_child returned).
+// The record a node has published as child `side` of `parent` (what publish_child wrote).
 template <typename T> BVH_HD DevNode<T> published_record(const ClimbState<T>& s) {
     DevNode<T> rec;
     for (int k = 0; k < 3; ++k) { rec.bounds[2 * k] = s.bmin[k]; rec.bounds[2 * k + 1] = s.bmax[k]; }

@@ -12,6 +12,7 @@
 //                             leaves by SAH (split_heuristic.h:30-38) and stores each node once, in its
 //                             final reference-layout slot.
 #include <cstdlib>
+#include <string>
 
 #include <cuda/atomic>
 
@@ -162,101 +163,98 @@ struct BlockSync {
 };
 
 // K4.  leaf_mode 0: verts (n x 9), also writes BVH-order triangles; 1: bboxes (n x 6, min3 max3).
-// One block per kLeaves consecutive sorted leaves, two phases (build_core.cuh): merges whose two children lie
-// inside the block meet in shared memory, in rounds over a compacted work list; then the nodes that reached
-// a block wall or were not matched locally are compacted once more and carry on through the global arrival
-// flags.  Keys of the block (plus one neighbour on each side) are staged in shared memory for the delta tests.
-template <typename T> struct HierarchyCfg { static constexpr int kLeaves = sizeof(T) == 4 ? 256 : 128; };
+// Leaf stage shared by the hierarchy kernel variants: the leaf's box (and its BVH-order triangle record).
+template <typename T>
+__device__ __forceinline__ void hierarchy_leaf(uint32_t i, const uint32_t* __restrict__ vals, const T* __restrict__ leaf_src,
+                                               int leaf_mode, DevTri<T>* __restrict__ tris, T bmin[3], T bmax[3]) {
+    const uint32_t id = vals[i];
+    if (leaf_mode == 0) {
+        T v[9];
+        #pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = __ldg(leaf_src + 9 * (size_t)id + k);
+        T c[3];
+        tri_bounds_center(v, bmin, bmax, c);
+        const DevTri<T> tri = precompute_tri(v);
+        const uint4* s = reinterpret_cast<const uint4*>(&tri);
+        uint4* d = reinterpret_cast<uint4*>(tris + i);
+        #pragma unroll
+        for (int k = 0; k < (int)(sizeof(DevTri<T>) / 16); ++k) d[k] = s[k];
+    } else {
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            bmin[k] = __ldg(leaf_src + 6 * (size_t)id + k);
+            bmax[k] = __ldg(leaf_src + 6 * (size_t)id + 3 + k);
+        }
+    }
+}
 
+// Variant G: one thread per leaf, every merge through the global arrival flags.
 template <typename T, typename K>
-__global__ void __launch_bounds__(HierarchyCfg<T>::kLeaves)
-hierarchy_kernel(BuildParams<T> p, const K* __restrict__ keys, const uint32_t* __restrict__ vals,
-                 const T* __restrict__ leaf_src, int leaf_mode, DevTri<T>* __restrict__ tris) {
-    constexpr int B = HierarchyCfg<T>::kLeaves;
+__global__ void __launch_bounds__(kBlock)
+hierarchy_global_kernel(BuildParams<T> p, const K* __restrict__ keys, const uint32_t* __restrict__ vals,
+                        const T* __restrict__ leaf_src, int leaf_mode, DevTri<T>* __restrict__ tris) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= p.n) return;
+    T bmin[3], bmax[3];
+    hierarchy_leaf(i, vals, leaf_src, leaf_mode, tris, bmin, bmax);
+    build_bottom_up<T, K, DeviceSync>(p, keys, i, bmin, bmax);
+}
+
+// Variant T: one thread per leaf; merges whose two children lie inside the block's B consecutive leaves meet
+// in shared memory; after one block barrier, whatever reached a block wall or was not matched locally carries
+// on through the global arrival flags.
+template <typename T, typename K, int B>
+__global__ void __launch_bounds__(B)
+hierarchy_thread_kernel(BuildParams<T> p, const K* __restrict__ keys, const uint32_t* __restrict__ vals,
+                        const T* __restrict__ leaf_src, int leaf_mode, DevTri<T>* __restrict__ tris) {
     __shared__ DevNode<T> s_nodes[2 * B];
-    __shared__ ClimbItem<T> s_items[B];          // rounds: two lists of B/2; afterwards: the global climbers
-    __shared__ ClimbItem<T> s_walls[2];
     __shared__ int s_flags[B];
     __shared__ int s_info[B];
-    __shared__ K s_keys[B + 2];
-    __shared__ int s_count[3];
-    __shared__ int s_wall_count, s_global_count;
     const uint32_t t = threadIdx.x;
     const uint32_t i0 = blockIdx.x * B;
     const uint32_t iend = min(i0 + (uint32_t)B, p.n);
-    const uint32_t m = iend - i0;
     const uint32_t i = i0 + t;
     const bool active = i < p.n;
     s_flags[t] = -1;
     s_info[t] = 0;
-    if (t < 3) s_count[t] = 0;
-    if (t == 0) { s_wall_count = 0; s_global_count = 0; }
-    for (uint32_t j = t; j < m + 2; j += B) {               // s_keys[j] = keys[i0 - 1 + j]
-        const int64_t src = (int64_t)i0 - 1 + j;
-        if (src >= 0 && src < (int64_t)p.n) s_keys[j] = keys[src];
-    }
     T bmin[3], bmax[3];
-    if (active) {
-        const uint32_t id = vals[i];
-        if (leaf_mode == 0) {
-            T v[9];
-            #pragma unroll
-            for (int k = 0; k < 9; ++k) v[k] = __ldg(leaf_src + 9 * (size_t)id + k);
-            T c[3];
-            tri_bounds_center(v, bmin, bmax, c);
-            const DevTri<T> tri = precompute_tri(v);
-            const uint4* s = reinterpret_cast<const uint4*>(&tri);
-            uint4* d = reinterpret_cast<uint4*>(tris + i);
-            #pragma unroll
-            for (int k = 0; k < (int)(sizeof(DevTri<T>) / 16); ++k) d[k] = s[k];
-        } else {
-            #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                bmin[k] = __ldg(leaf_src + 6 * (size_t)id + k);
-                bmax[k] = __ldg(leaf_src + 6 * (size_t)id + 3 + k);
-            }
-        }
-    }
+    if (active) hierarchy_leaf(i, vals, leaf_src, leaf_mode, tris, bmin, bmax);
     if (p.n == 1) {
         if (active) build_bottom_up<T, K, DeviceSync>(p, keys, i, bmin, bmax);
         return;
     }
     __syncthreads();
-
     const LocalSlots<T> loc { s_nodes, s_flags, s_info };
-    const K* local_keys = s_keys + 1 - (ptrdiff_t)i0;         // local_keys[i] = keys[i] for i in [i0 - 1, iend]
-    uint32_t count = m;
-    for (uint32_t round = 0; count > 0; ++round) {
-        ClimbItem<T>* in = s_items + (round & 1u) * (B / 2);
-        ClimbItem<T>* out = s_items + ((round + 1) & 1u) * (B / 2);
-        if (t == 0) s_count[(round + 2) % 3] = 0;
-        if (t < count) {
-            ClimbState<T> st;
-            if (round == 0) climb_init(st, i, bmin, bmax);
-            else st = in[t].s;
-            uint32_t parent, side;
-            const int outcome = local_step<T, K, BlockSync>(p, local_keys, st, loc, i0, iend, parent, side);
-            if (outcome == kStepCarry) out[atomicAdd(&s_count[(round + 1) % 3], 1)].s = st;
-            else if (outcome == kStepWall) {
-                ClimbItem<T>& w = s_walls[atomicAdd(&s_wall_count, 1)];
-                w.s = st; w.parent = parent; w.side = side;
-            }
-        }
-        __syncthreads();
-        count = (uint32_t)s_count[(round + 1) % 3];
+    ClimbState<T> st;
+    uint32_t parent = 0, side = 0;
+    int outcome = kStepRetired;
+    if (active) {
+        climb_init(st, i, bmin, bmax);
+        do outcome = local_step<T, K, BlockSync>(p, keys, st, loc, i0, iend, parent, side); while (outcome == kStepCarry);
     }
-
-    // whatever must go on globally, compacted: first arrivals nobody matched, and the (at most two) wall nodes
-    if (t + 1 < m) {
-        ClimbItem<T> item; DevNode<T> own;
-        if (unmatched_first(loc, i0, t, item, own)) s_items[atomicAdd(&s_global_count, 1)] = item;
-    }
-    if ((int)t < s_wall_count) s_items[atomicAdd(&s_global_count, 1)] = s_walls[t];
     __syncthreads();
-    for (uint32_t k = t; k < (uint32_t)s_global_count; k += B) {
-        ClimbItem<T> item = s_items[k];
-        climb_global<T, K, DeviceSync>(p, keys, item.s, item.parent, item.side, published_record(item.s));
-    }
+    if (!active) return;
+    if (outcome == kStepRetired && (parent < i0 || s_info[parent - i0] != 0)) return;     // matched, or the root
+    climb_global<T, K, DeviceSync>(p, keys, st, parent, side, published_record(st));
+}
+
+// Variant selection.  Measured on B200 (1M-triangle soup, whole build, median of 25; profiles/r01_build_variants.txt):
+// global 313 us, thread64 301, thread128 303, thread256 314-320 — the pass is bound by the dependent chain of the
+// top levels and the vertex gather of the leaf stage, which all variants share, so the spread is small.
+// BVH_B200_HIERARCHY=global|thread64|thread128|thread256 overrides the default for experiments; all variants
+// build the same tree (tests/test_host_emulation.py::test_block_local_phase_builds_the_same_tree).
+template <typename T, typename K>
+void launch_hierarchy(const BuildParams<T>& p, const K* keys, const uint32_t* vals, const T* leaf_src, int mode,
+                      DevTri<T>* tris, cudaStream_t stream) {
+    const char* e = std::getenv("BVH_B200_HIERARCHY");
+    const std::string v = e ? e : "thread128";
+    const uint32_t n = p.n;
+#define BVH_LAUNCH_H(B) hierarchy_thread_kernel<T, K, B><<<(n + B - 1) / B, B, 0, stream>>>(p, keys, vals, leaf_src, mode, tris)
+    if (v == "global") hierarchy_global_kernel<T, K><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(p, keys, vals, leaf_src, mode, tris);
+    else if (v == "thread64") BVH_LAUNCH_H(64);
+    else if (v == "thread256" && sizeof(T) == 4) BVH_LAUNCH_H((sizeof(T) == 4 ? 256 : 128));
+    else BVH_LAUNCH_H(128);
+#undef BVH_LAUNCH_H
 }
 
 template <typename T>
@@ -482,10 +480,7 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     p.min_leaf = options.min_leaf < 1 ? 1 : options.min_leaf;
     p.max_leaf = options.max_leaf > kMaxLeafPrims ? kMaxLeafPrims : (options.max_leaf < 1 ? 1 : options.max_leaf);
     if (p.min_leaf > p.max_leaf) p.min_leaf = p.max_leaf;
-    {
-        constexpr uint32_t leaves = HierarchyCfg<T>::kLeaves;
-        hierarchy_kernel<T, K><<<(n + leaves - 1) / leaves, leaves, 0, stream>>>(p, keys_a, out.prim_ids, leaf_src, mode, out.tris);
-    }
+    launch_hierarchy<T, K>(p, keys_a, out.prim_ids, leaf_src, mode, out.tris, stream);
     BVH_CUDA_TRY(cudaGetLastError());
 
     uint32_t host_info[4] = { 0, 0, 0, 0 };
@@ -507,6 +502,7 @@ int build_lbvh(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const T* 
     // first_id must fit Index<32,4>: 2n-1 <= 2^28-1 for float (index.h:39)
     if (sizeof(T) == 4 && 2 * (uint64_t)n > ((uint64_t)1 << 28)) { set_error("build: too many primitives for a 32-bit index"); return -1; }
     int bits = options.morton_bits;
+    if (const char* e = std::getenv("BVH_B200_MORTON_BITS")) bits = std::atoi(e);      // test hook: 30 or 63
     if (bits == 0) bits = n >= (1u << 22) ? 63 : 30;
     int rc;
     if (bits <= 30) rc = build_with_key<T, uint32_t>(out, d_verts, d_bboxes, d_centers, n, options, 30, stream);

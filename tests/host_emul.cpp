@@ -76,45 +76,35 @@ uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t 
             build_bottom_up<T, K, HostSync>(p, sorted.data(), i, bmin, bmax);
         }
     } else {
-        // the device kernel's two phases (block-local merges in rounds over a compacted list, then global), one
-        // "block" at a time; within a round the items run in the order g_block_order selects (0 ascending,
-        // 1 descending, 2 interleaved), which changes who arrives first at every boundary
+        // the device kernel's two phases (block-local merges through "shared" slots, then global), one block at a
+        // time; within a block the leaves run in the order g_block_order selects (0 ascending, 1 descending,
+        // 2 interleaved), which changes who arrives first at every boundary
         const uint32_t B = (uint32_t)g_block_leaves;
         std::vector<DevNode<T>> lnodes(2 * (size_t)B);
         std::vector<int> lflags(B), linfo(B);
+        struct Pending { ClimbState<T> s; uint32_t parent, side; int outcome; };
+        std::vector<Pending> pend(B);
         for (uint32_t i0 = 0; i0 < n; i0 += B) {
             const uint32_t iend = i0 + B < n ? i0 + B : n;
             std::fill(lflags.begin(), lflags.end(), -1);
             std::fill(linfo.begin(), linfo.end(), 0);
             LocalSlots<T> loc { lnodes.data(), lflags.data(), linfo.data() };
             const uint32_t m = iend - i0;
-            std::vector<ClimbState<T>> cur(m), next;
-            std::vector<ClimbItem<T>> walls;
-            for (uint32_t j = 0; j < m; ++j) {
+            for (uint32_t k = 0; k < m; ++k) {
+                uint32_t j = k;
+                if (g_block_order == 1) j = m - 1 - k;
+                else if (g_block_order == 2) j = (k & 1) ? m - 1 - k / 2 : k / 2;
                 T bmin[3], bmax[3];
                 leaf_box(i0 + j, bmin, bmax);
-                climb_init(cur[j], i0 + j, bmin, bmax);
+                Pending& q = pend[j];
+                climb_init(q.s, i0 + j, bmin, bmax);
+                do q.outcome = local_step<T, K, HostSync>(p, sorted.data(), q.s, loc, i0, iend, q.parent, q.side); while (q.outcome == kStepCarry);
             }
-            while (!cur.empty()) {
-                next.clear();
-                const size_t c = cur.size();
-                for (size_t k = 0; k < c; ++k) {
-                    size_t j = k;
-                    if (g_block_order == 1) j = c - 1 - k;
-                    else if (g_block_order == 2) j = (k & 1) ? c - 1 - k / 2 : k / 2;
-                    ClimbItem<T> it;
-                    it.s = cur[j];
-                    const int outcome = local_step<T, K, HostSync>(p, sorted.data(), it.s, loc, i0, iend, it.parent, it.side);
-                    if (outcome == kStepCarry) next.push_back(it.s);
-                    else if (outcome == kStepWall) walls.push_back(it);
-                }
-                cur.swap(next);
+            for (uint32_t j = 0; j < m; ++j) {                 // after the block barrier
+                Pending& q = pend[j];
+                if (q.outcome == kStepRetired && linfo[q.parent - i0] != 0) continue;     // matched, or the root
+                climb_global<T, K, HostSync>(p, sorted.data(), q.s, q.parent, q.side, published_record(q.s));
             }
-            for (uint32_t q = 0; q + 1 < m; ++q) {
-                ClimbItem<T> it; DevNode<T> own;
-                if (unmatched_first(loc, i0, q, it, own)) climb_global<T, K, HostSync>(p, sorted.data(), it.s, it.parent, it.side, own);
-            }
-            for (auto& it : walls) climb_global<T, K, HostSync>(p, sorted.data(), it.s, it.parent, it.side, published_record(it.s));
         }
     }
     *depth_out = info[0];

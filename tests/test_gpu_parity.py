@@ -115,6 +115,47 @@ def test_gpu_tree_is_a_valid_reference_bvh(gpu_lib, oracle, emul, kind, n, dtype
     assert_hits_equal(hits_tuple(bvh.intersect_rays(rays)), oracle.trace(tree, rays, flags=O_LOWEST)[:4], "after refit")
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_wide_morton_keys_match_the_emulation(gpu_lib, emul, monkeypatch, dtype):
+    """The 63-bit Morton path (64-bit keys, 8 radix passes; the automatic choice from 2^22 primitives on),
+    forced at a size the host emulation handles: same tree node for node."""
+    monkeypatch.setenv("BVH_B200_MORTON_BITS", "63")
+    tris = scenes.soup(30000, seed=9).astype(dtype)
+    bvh = gpu_lib.Bvh.build_triangles(tris)
+    monkeypatch.delenv("BVH_B200_MORTON_BITS")
+    bounds, index_values, prim_ids = bvh.arrays()
+    etree = emul.build(tris=tris, morton_bits=63)
+    eb, ei = emul.compact(etree)
+    assert eb.shape == bounds.shape and (eb == bounds).all() and (ei == index_values).all()
+    assert (etree["prim_ids"] == prim_ids).all()
+    narrow = gpu_lib.Bvh.build_triangles(tris)
+    rays = scenes.make_primary("soup", 200, 200, dtype=dtype)
+    assert_hits_equal(hits_tuple(bvh.intersect_rays(rays)), hits_tuple(narrow.intersect_rays(rays)), "63-bit vs 30-bit tree")
+
+
+def test_ten_million_triangles_config4(gpu_lib, oracle):
+    """BASELINE config 4's mesh size on one GPU: 10M triangles (64-bit Morton keys, 20M node slots), a 4M-ray
+    primary batch; structure invariants on the downloaded tree, hit properties, and an exact check of a
+    sample against the reference algorithm on the same tree."""
+    api = gpu_lib
+    n = 10_000_000
+    tris = scenes.soup(n)
+    bvh = api.Bvh.build_triangles(tris)
+    rays = scenes.make_primary("soup", 2000, 2000)
+    hits = bvh.intersect_rays(rays)
+    hit = hits["prim_id"] != INVALID
+    assert 0.3 < hit.mean() <= 1.0 and (hits["prim_id"][hit] < n).all()
+    assert (hits["t"][~hit] == rays[~hit, 7]).all() and (hits["t"][hit] > 0).all()
+    bounds, index_values, prim_ids = bvh.arrays()
+    assert np.array_equal(np.sort(prim_ids), np.arange(n, dtype=prim_ids.dtype))
+    tree = oracle.from_arrays(bounds, index_values, prim_ids)
+    assert oracle.check_invariants(tree, 8) == 0
+    oracle.set_triangles(tree, tris)
+    sample = np.sort(np.random.RandomState(4).choice(rays.shape[0], 5000, replace=False))
+    want = oracle.trace(tree, rays[sample], flags=O_LOWEST)
+    assert_hits_equal(hits_tuple(hits[sample]), want, "soup-10M sample vs oracle")
+
+
 def test_build_from_boxes_and_centres(gpu_lib, oracle):
     """bvh3f_build(pool, bboxes, centers, n, config) — the reference's own entry point — builds the same
     tree as the fused triangle path; bvh3f_set_triangles makes it traceable."""

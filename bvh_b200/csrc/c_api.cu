@@ -73,7 +73,8 @@ template <typename T> struct Handle {
     uint64_t synced_ids_hash = 0;             // hash of prim_ids the device triangles were permuted with
 
     // staging and side streams for host-pointer batches
-    static constexpr size_t kMaxChunks = 8;       // measured: 8 chunks of a 10M-ray batch overlap best
+    static constexpr size_t kMaxChunks = 16;
+    static constexpr size_t kDefaultChunks = 8;   // measured: 8 chunks of a 10M-ray batch overlap best
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t events[1 + 2 * kMaxChunks] = {};
     void* d_rays = nullptr; size_t d_rays_bytes = 0;
@@ -408,37 +409,18 @@ int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bv
     auto d_stats = static_cast<uint32_t*>(h->d_stats);
     constexpr size_t kMinChunk = 1u << 20;                   // 1M rays = 32 MB of float rays per chunk
     size_t chunks = n / kMinChunk;
+    if (chunks > Handle<T>::kDefaultChunks) chunks = Handle<T>::kDefaultChunks;
     if (const char* e = getenv("BVH_B200_E2E_CHUNKS")) chunks = (size_t)atol(e);      // experiments only
     if (chunks < 1) chunks = 1;
     if (chunks > Handle<T>::kMaxChunks) chunks = Handle<T>::kMaxChunks;
     // the staging buffers may still be in use by earlier work on the handle's stream
     BVH_CUDA_TRY(cudaEventRecord(h->events[0], h->stream));
     BVH_CUDA_TRY(cudaStreamWaitEvent(h->copy_in, h->events[0], 0));
-    // Chunk sizes taper towards the end (the last three are 1/2, 1/4 and 1/8 of a full one): the upload is the
-    // bottleneck and runs back to back, so what the call adds to it is the traversal and download of the LAST
-    // chunk, which should therefore be small.
-    bool taper = chunks >= 4;
-    if (const char* e = getenv("BVH_B200_E2E_TAPER")) taper = taper && atoi(e) != 0;
-    size_t bounds[Handle<T>::kMaxChunks + 1];
-    {
-        double weight[Handle<T>::kMaxChunks], total = 0;
-        for (size_t c = 0; c < chunks; ++c) {
-            const size_t from_end = chunks - 1 - c;
-            weight[c] = taper && from_end < 3 ? 1.0 / (double)(8 >> from_end) : 1.0;
-            total += weight[c];
-        }
-        double acc = 0;
-        bounds[0] = 0;
-        for (size_t c = 0; c < chunks; ++c) {
-            acc += weight[c];
-            size_t b = (size_t)((double)n * (acc / total));
-            b = (b + 31) & ~(size_t)31;                          // whole 32-ray groups (the kernel's chunk size)
-            bounds[c + 1] = b > n || c + 1 == chunks ? n : b;
-        }
-    }
+    // Equal chunks.  Measured (profiles/r01_e2e_chunking.txt): 8 equal chunks 6.86 ms; chunk sizes tapering
+    // towards the end 7.12 ms; 6 / 12 / 16 chunks 7.43 / 6.96 / 7.37 ms.  Upload (320 MB) and download (160 MB)
+    // share the link: the call runs at ~70 GB/s of combined PCIe traffic whatever the schedule.
     for (size_t c = 0; c < chunks; ++c) {
-        const size_t b = bounds[c], e = bounds[c + 1];
-        if (e <= b) continue;
+        const size_t b = n * c / chunks, e = n * (c + 1) / chunks;
         cudaEvent_t in_done = h->events[1 + 2 * c], tr_done = h->events[2 + 2 * c];
         BVH_CUDA_TRY(cudaMemcpyAsync(d_rays + b, rays + b, (e - b) * sizeof(RayPod), cudaMemcpyHostToDevice, h->copy_in));
         BVH_CUDA_TRY(cudaEventRecord(in_done, h->copy_in));

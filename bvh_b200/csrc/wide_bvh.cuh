@@ -145,6 +145,17 @@ BVH_HD float wide_fmin(float a, float b) {
 #endif
 }
 
+// Byte c of a packed word as a float.  On the device the int-to-float conversion (I2F runs on the quarter-rate
+// XU pipe, which capped this kernel: 24 conversions per node, XU at 80 % of peak in profiles/) is replaced by
+// one PRMT that drops the byte into the mantissa of 2^23 and one exact subtraction: same value, bit for bit.
+BVH_HD float wide_byte_to_float(uint32_t word, int c) {
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u | (uint32_t)c)), 8388608.0f);
+#else
+    return (float)((word >> (8 * c)) & 0xFFu);
+#endif
+}
+
 // One inner step through the wide node whose 16 words are in w (layout of WideNode).  Dequantises the four
 // child boxes straight into ray-parameter space, t = q * (cell * inv_dir) + (origin - org) * inv_dir,
 // visits the nearest hit child next and pushes the others far-to-near (any-hit: no ordering).  Returns
@@ -170,8 +181,8 @@ BVH_HD bool wide_step(const uint32_t (&w)[16], const RayCtx<float>& r, uint32_t&
     for (int c = 0; c < 4; ++c) {
         float tn = r.tmin, tf = r.tmax;
         for (int k = 0; k < 3; ++k) {
-            tn = wide_fmax(R::fma((float)((qn[k] >> (8 * c)) & 0xFFu), s[k], b[k]), tn);
-            tf = wide_fmin(R::fma((float)((qf[k] >> (8 * c)) & 0xFFu), sp[k], bp[k]), tf);
+            tn = wide_fmax(R::fma(wide_byte_to_float(qn[k], c), s[k], b[k]), tn);
+            tf = wide_fmin(R::fma(wide_byte_to_float(qf[k], c), sp[k], bp[k]), tf);
         }
         ref[c] = w[10 + c];
         t0[c] = (tn <= tf) ? tn : inf;                                   // +inf marks a miss

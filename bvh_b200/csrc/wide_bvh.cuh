@@ -145,16 +145,11 @@ BVH_HD float wide_fmin(float a, float b) {
 #endif
 }
 
-// Byte c of a packed word as a float.  On the device the int-to-float conversion (I2F runs on the quarter-rate
-// XU pipe, which capped this kernel: 24 conversions per node, XU at 80 % of peak in profiles/) is replaced by
-// one PRMT that drops the byte into the mantissa of 2^23 and one exact subtraction: same value, bit for bit.
-BVH_HD float wide_byte_to_float(uint32_t word, int c) {
-#if defined(__CUDA_ARCH__)
-    return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u | (uint32_t)c)), 8388608.0f);
-#else
-    return (float)((word >> (8 * c)) & 0xFFu);
-#endif
-}
+// Byte c of a packed word as a float: a plain int-to-float conversion (I2F, on the XU pipe).  Measured
+// alternative (run 20): one PRMT dropping the byte into the mantissa of 2^23 plus an exact subtraction takes
+// XU from 80 % to 6 % of peak but adds an issue slot per value to a kernel that is issue-bound afterwards —
+// 2.68-2.72 instead of 3.00 Grays/s on soup-1M.  The conversions stay on the otherwise idle XU pipe.
+BVH_HD float wide_byte_to_float(uint32_t word, int c) { return (float)((word >> (8 * c)) & 0xFFu); }
 
 // One inner step through the wide node whose 16 words are in w (layout of WideNode).  Dequantises the four
 // child boxes straight into ray-parameter space, t = q * (cell * inv_dir) + (origin - org) * inv_dir,

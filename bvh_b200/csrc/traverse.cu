@@ -121,7 +121,6 @@ template <typename T> struct TraceArgs {
     uint32_t* status;                 // device word set to 1 when a watchdog fired
     uint32_t watchdog;                // persistent kernels: trap after this many rounds of one warp (a hang becomes an error)
     int lowest_id;
-    bool forward_chunks;              // gather mode: forward completed 32-ray chunks instead of single records
 };
 
 template <typename T, bool kAny, bool kRobust, bool kStats>
@@ -189,64 +188,13 @@ template <typename T> __host__ __device__ constexpr size_t tma_smem_bytes() {
     return (size_t)(kTraceBlock / 32) * 2 * kTmaChunkRays * sizeof(DevRay<T>) + (size_t)(kTraceBlock / 32) * 2 * 8;
 }
 
-// Gather mode: per-warp table of the ray chunks in flight (chunk-complete forwarding, see the kernel).
-constexpr int kForwardSlots = 4;
-struct ForwardSlot { unsigned long long base; int remaining; uint32_t count; };     // remaining = -1: free
-constexpr size_t forward_smem_bytes() { return (size_t)(kTraceBlock / 32) * kForwardSlots * sizeof(ForwardSlot); }
-
-// Copies the finished hit record of ray i from the local array to every gather target (one lane per ray, 32
-// consecutive rays per warp instruction: 512 contiguous bytes per target instead of 32 scattered 16-byte stores).
-template <typename T>
-__device__ __forceinline__ void forward_hit(const HitSinks<T>& sinks, unsigned long long i) {
-    constexpr int kWords = (int)(sizeof(DevHit<T>) / 16);
-    uint4 o[kWords];
-    const uint4* src = reinterpret_cast<const uint4*>(sinks.local + i);
-    #pragma unroll
-    for (int k = 0; k < kWords; ++k) o[k] = __ldcg(src + k);
-    if (sizeof(T) == 4 && sinks.multicast) multimem_store_v4(sinks.multicast + i, o[0]);
-    else for (int p = 0; p < sinks.peer_count; ++p) {
-        uint4* dst = reinterpret_cast<uint4*>(sinks.peer[p] + i);
-        #pragma unroll
-        for (int k = 0; k < kWords; ++k) dst[k] = o[k];
-    }
-}
-// The local part of store_hit only (cached store: the record is read back by forward_hit).
-__device__ __forceinline__ void store_hit_local(const HitSinks<float>& sinks, size_t i, const HitState<float>& h,
-                                                float tmax, const uint32_t* __restrict__ prim_ids) {
-    uint4 o;
-    const bool was_hit = h.slot != kInvalidId;
-    o.x = was_hit ? prim_ids[h.slot] : kInvalidId;
-    o.y = __float_as_uint(was_hit ? h.t : tmax);
-    o.z = __float_as_uint(was_hit ? h.u : 0.f);
-    o.w = __float_as_uint(was_hit ? h.v : 0.f);
-    *reinterpret_cast<uint4*>(sinks.local + i) = o;
-}
-__device__ __forceinline__ void store_hit_local(const HitSinks<double>& sinks, size_t i, const HitState<double>& h,
-                                                double tmax, const uint32_t* __restrict__ prim_ids) {
-    const bool was_hit = h.slot != kInvalidId;
-    ulonglong2 a, b;
-    a.x = was_hit ? (unsigned long long)prim_ids[h.slot] : ~0ull;
-    a.y = (unsigned long long)__double_as_longlong(was_hit ? h.t : tmax);
-    b.x = (unsigned long long)__double_as_longlong(was_hit ? h.u : 0.0);
-    b.y = (unsigned long long)__double_as_longlong(was_hit ? h.v : 0.0);
-    ulonglong2* d = reinterpret_cast<ulonglong2*>(sinks.local + i);
-    d[0] = a; d[1] = b;
-}
-
 // Persistent kernel.  kTma = true stages the warp's next ray chunk into shared memory with a bulk
 // asynchronous copy (cp.async.bulk, SASS UBLKCP) signalled through an mbarrier, double-buffered, so
 // that the ray fetch of the refill path never waits on DRAM; kTma = false reads rays with streaming
 // 128-bit loads.
-//
-// kForward (gather mode with a local hit array, kTma only): instead of storing each finished ray's record to
-// every gather target on its own — 16-byte remote stores, half of NVLink's payload efficiency — a lane stores
-// the record locally and counts its 32-ray chunk down in a small per-warp table; when a chunk is complete the
-// warp forwards its records together, one lane per ray, as 512 contiguous bytes per target.  A chunk that finds
-// the table full is not tracked and its rays fall back to the direct remote stores.
-template <typename T, bool kAny, bool kRobust, bool kTma, bool kForward = false>
+template <typename T, bool kAny, bool kRobust, bool kTma>
 __global__ void __launch_bounds__(kTraceBlock, sizeof(T) == 4 ? 8 : 4)
 trace_persistent_kernel(TraceArgs<T> a) {
-    static_assert(!kForward || kTma, "chunk forwarding rides on the staged 32-ray chunks");
     using U = typename Real<T>::UInt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -266,9 +214,6 @@ trace_persistent_kernel(TraceArgs<T> a) {
     uint32_t bar0 = 0, bar1 = 0, phase0 = 0, phase1 = 0, count0 = 0, count1 = 0;
     unsigned long long base0 = 0, base1 = 0;
     uint32_t cur = 0, buf_pos = 0;
-    ForwardSlot* fslots = nullptr;                             // kForward: this warp's table (shared memory)
-    int fslot0 = -1, fslot1 = -1;                              // table slot of the chunk in buffer 0 / 1 (-1: untracked)
-    int my_fslot = -1;                                         // table slot of this lane's ray
 
     auto prefetch = [&] (uint32_t b) {      // claim the next chunk and start its bulk copy into buffer b
         unsigned long long base = 0;
@@ -277,18 +222,6 @@ trace_persistent_kernel(TraceArgs<T> a) {
         uint32_t cnt = 0;
         if (base < a.n) cnt = (uint32_t)(base + kTmaChunkRays < a.n ? kTmaChunkRays : a.n - base);
         if (b == 0) { count0 = cnt; base0 = base; } else { count1 = cnt; base1 = base; }
-        if (kForward) {                     // register the chunk (the warp is converged here)
-            __syncwarp();
-            int slot = -1;
-            if (cnt != 0) {
-                #pragma unroll
-                for (int k = kForwardSlots - 1; k >= 0; --k) if (fslots[k].remaining < 0) slot = k;
-            }
-            __syncwarp();
-            if (slot >= 0 && lane == 0) { fslots[slot].base = base; fslots[slot].count = cnt; fslots[slot].remaining = (int)cnt; }
-            __syncwarp();
-            if (b == 0) fslot0 = slot; else fslot1 = slot;
-        }
         if (cnt != 0 && lane == 0) {
             const uint32_t bar = b == 0 ? bar0 : bar1;
             fence_proxy_async_smem();       // earlier generic reads of this buffer happen-before the async write
@@ -306,10 +239,6 @@ trace_persistent_kernel(TraceArgs<T> a) {
         bar0 = smem_u32(bars + warp * 2 + 0);
         bar1 = smem_u32(bars + warp * 2 + 1);
         if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar1, 1); fence_mbar_init(); fence_proxy_async_smem(); }
-        if (kForward) {
-            fslots = reinterpret_cast<ForwardSlot*>(tma_base + tma_smem_bytes<T>()) + warp * kForwardSlots;
-            if (lane < (unsigned)kForwardSlots) fslots[lane].remaining = -1;
-        }
         __syncwarp();
         prefetch(0);
         prefetch(1);
@@ -321,17 +250,6 @@ trace_persistent_kernel(TraceArgs<T> a) {
     HitState<T> hit;
     T tmax_in = (T)0;
     U top = 0;
-
-    // Retires this lane's ray: its record is final.
-    auto retire = [&] () {
-        if (kForward && my_fslot >= 0) {
-            store_hit_local(a.hits, ray_index, hit, tmax_in, a.prim_ids);
-            __threadfence_block();                              // record before count
-            atomicSub(&fslots[my_fslot].remaining, 1);
-        } else {
-            store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
-        }
-    };
 
     uint32_t rounds = 0;
     for (;;) {
@@ -354,7 +272,6 @@ trace_persistent_kernel(TraceArgs<T> a) {
                 if (!has_ray && rank < take) {
                     ray_index = (cur == 0 ? base0 : base1) + buf_pos + rank;
                     read_ray_smem((cur == 0 ? ray_buf0 : ray_buf1) + buf_pos + rank, r);
-                    if (kForward) my_fslot = cur == 0 ? fslot0 : fslot1;
                     got = true;
                 }
                 buf_pos += take;
@@ -386,7 +303,7 @@ trace_persistent_kernel(TraceArgs<T> a) {
                 tmax_in = r.tmax;
                 hit.slot = kInvalidId; hit.t = r.tmax; hit.u = (T)0; hit.v = (T)0;
                 if (ray_interval_is_nan(r)) {
-                    retire();                                                    // can never hit: retire as a miss
+                    store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);     // can never hit: retire as a miss
                 } else {
                     ray_prologue<T, kRobust>(r);
                     top = root_index;
@@ -395,18 +312,6 @@ trace_persistent_kernel(TraceArgs<T> a) {
                 }
             }
             idle = __ballot_sync(kFull, !has_ray);
-        }
-        if (kForward) {                                      // forward the chunks whose last ray has retired
-            __syncwarp();
-            #pragma unroll
-            for (int k = 0; k < kForwardSlots; ++k) {
-                if (fslots[k].remaining == 0) {              // warp-uniform
-                    if (lane < fslots[k].count) forward_hit(a.hits, fslots[k].base + lane);
-                    __syncwarp();
-                    if (lane == 0) fslots[k].remaining = -1;
-                }
-            }
-            __syncwarp();
         }
         if (__ballot_sync(kFull, has_ray) == 0u) {
             if (exhausted) break;                            // nothing in flight and nothing left
@@ -421,7 +326,7 @@ trace_persistent_kernel(TraceArgs<T> a) {
                 --budget;
                 if (!inner_step<T, kAny, kRobust>(a.nodes, r, top, stack)) { has_ray = false; break; }
             }
-            if (!has_ray) retire();
+            if (!has_ray) store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
         }
         __syncwarp();
 
@@ -429,7 +334,7 @@ trace_persistent_kernel(TraceArgs<T> a) {
         if (has_ray && index_count(top) != 0) {
             leaf_step<T>(a.tris, a.prim_ids, lowest_id, top, r, hit, nullptr);
             if ((kAny && hit.slot != kInvalidId) || stack.empty()) {
-                retire();
+                store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
                 has_ray = false;
             } else {
                 top = stack.pop();
@@ -760,10 +665,8 @@ int launch(const TraceArgs<T>& args, bool simple, bool stats, int device, cudaSt
         kernel<<<(unsigned)grid, kTraceBlock, pair_smem, stream>>>(args);
     } else {
         const bool tma = args.use_tma;
-        const bool forward = tma && args.forward_chunks && args.hits.local && (args.hits.peer_count > 0 || args.hits.multicast);
-        auto kernel = forward ? trace_persistent_kernel<T, kAny, kRobust, true, true>
-                    : tma ? trace_persistent_kernel<T, kAny, kRobust, true> : trace_persistent_kernel<T, kAny, kRobust, false>;
-        const size_t total_smem = smem + (tma ? tma_smem_bytes<T>() : 0) + (forward ? forward_smem_bytes() : 0);
+        auto kernel = tma ? trace_persistent_kernel<T, kAny, kRobust, true> : trace_persistent_kernel<T, kAny, kRobust, false>;
+        const size_t total_smem = smem + (tma ? tma_smem_bytes<T>() : 0);
         if (configure_smem(kernel, total_smem)) return -1;
         int sm_count = 148, per_sm = 1;
         BVH_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -802,8 +705,6 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     } else if (!d_hits) { set_error("trace: no hit array"); return -1; }
     args.ray_stats = d_ray_stats;
     args.lowest_id = (flags & kTraceLastVisited) ? 0 : 1;
-    args.forward_chunks = true;
-    if (const char* e = getenv("BVH_B200_GATHER_FORWARD")) args.forward_chunks = atoi(e) != 0;      // A/B experiments
     uint32_t entries = bvh.depth + 1;
     entries = (entries + 7u) & ~7u;
     if (entries < 16) entries = 16;

@@ -87,10 +87,9 @@ class FusedGatherTracer:
     The gathered hit array lives in symmetric memory (``torch.distributed._symmetric_memory``): every rank
     holds the same (world * local_count, words) buffer and knows the address of each peer's copy.  One
     launch of the traversal kernel (``bvhNN_intersect_rays_gather``) traces this rank's shard and stores
-    the finished hit records into the shard's slot of EVERY rank's buffer — multimem stores through the
-    NVSwitch multicast address when the fabric offers it, otherwise peer stores per rank, a completed 32-ray
-    chunk (512 bytes) at a time — so the transfer rides along with the traversal instead of following it as
-    an NCCL call.  A
+    each finished ray's 16-byte record straight into the shard's slot of EVERY rank's buffer — one multimem
+    store through the NVSwitch multicast address when the fabric offers it, otherwise one peer store per
+    rank — so the transfer rides along with the traversal instead of following it as an NCCL call.  A
     symmetric-memory barrier at the end of the step orders the remote stores before anyone reads.
     """
 
@@ -114,11 +113,8 @@ class FusedGatherTracer:
         self.local = self.gathered[self.rank * self.local_count:(self.rank + 1) * self.local_count]
 
     def step(self) -> None:
-        # hits_ptr = this rank's own slice of the gathered array: the kernel stores finished records there first and
-        # forwards whole 32-ray chunks to the other ranks (512-byte coalesced remote stores instead of 16-byte ones)
         self.bvh.intersect_rays_gather(self.rays.data_ptr(), self.local_count, self.peers,
-                                       self.rank * self.local_count, hits_ptr=self.local.data_ptr(),
-                                       multicast_ptr=self.multicast, flags=self.flags)
+                                       self.rank * self.local_count, multicast_ptr=self.multicast, flags=self.flags)
         self.handle.barrier(channel=0)
 
     def global_hits(self) -> torch.Tensor:

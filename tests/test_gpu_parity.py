@@ -521,15 +521,13 @@ def test_gpu_refit_after_vertices_move(gpu_lib, oracle, dtype):
     assert_hits_equal(hits_tuple(bvh.intersect_rays(rays, flags=api.ROBUST)), oracle.brute_force(moved, rays), "refit trace")
 
 
-@pytest.mark.parametrize("forward", ["1", "0"])
 @pytest.mark.parametrize("dtype,flags_name", [(np.float32, None), (np.float32, "ANY_HIT"), (np.float64, None)])
-def test_gather_entry_point_on_one_gpu(gpu_lib, monkeypatch, forward, dtype, flags_name):
+def test_gather_entry_point_on_one_gpu(gpu_lib, dtype, flags_name):
     """bvhNN_intersect_rays_gather with both "ranks" on one device: the shard's records must land, identical to
-    the plain batched call, in the shard's slot of every gathered array (and nowhere else) — with the kernel
-    forwarding completed 32-ray chunks from the local array (default) and with direct per-ray stores."""
+    the plain batched call, in the shard's slot of every gathered array (and nowhere else), and in the local
+    array when one is given."""
     import torch
     api = gpu_lib
-    monkeypatch.setenv("BVH_B200_GATHER_FORWARD", forward)
     tris = scenes.soup(20000, seed=2).astype(dtype)
     bvh = api.Bvh.build_triangles(tris)
     rays = scenes.make_primary("soup", 301, 211, dtype=dtype)          # 63 511 rays: a ragged last chunk
@@ -542,16 +540,17 @@ def test_gather_entry_point_on_one_gpu(gpu_lib, monkeypatch, forward, dtype, fla
     offset = 1000                                                      # the shard's position in the gathered arrays
     total = m + 2 * offset
     gathered = [torch.full((total, words), 0x5A5A5A5A, dtype=torch.int32, device="cuda") for _ in range(2)]
-    for local_is_slice in (True, False):
+    expect = np.frombuffer(want.tobytes(), np.int32).reshape(m, words)
+    for with_local in (True, False):
         for g in gathered: g.fill_(0x5A5A5A5A)
-        local = gathered[0][offset:offset + m] if local_is_slice else torch.zeros((m, words), dtype=torch.int32, device="cuda")
+        local = torch.zeros((m, words), dtype=torch.int32, device="cuda") if with_local else None
         bvh.intersect_rays_gather(d_rays.data_ptr(), m, [g.data_ptr() for g in gathered], offset,
-                                  hits_ptr=local.data_ptr(), flags=flags)
+                                  hits_ptr=local.data_ptr() if with_local else 0, flags=flags)
         bvh.sync()
         torch.cuda.synchronize()
-        expect = np.frombuffer(want.tobytes(), np.int32).reshape(m, words)
         for g in gathered:
             got = g.cpu().numpy()
             assert (got[offset:offset + m] == expect).all()
             assert (got[:offset] == 0x5A5A5A5A).all() and (got[offset + m:] == 0x5A5A5A5A).all()
-        assert (local.cpu().numpy() == expect).all()
+        if with_local:
+            assert (local.cpu().numpy() == expect).all()

@@ -6,11 +6,12 @@
 //   K2 morton_kernel          final bounds reduce, grid quantisation (mini_tree_builder.h:170-183),
 //                             Morton interleave (utils.h:103-120), clears the arrival flags
 //   K3 radix sort             radix_sort.cuh, 3 kernels x 4 (30-bit keys) or x 8 (63-bit keys) passes
-//   K4 hierarchy_kernel       one thread per sorted primitive: leaf box (tri.h:24), BVH-order
+//   K4 hierarchy_thread_kernel  one thread per sorted primitive: leaf box (tri.h:24), BVH-order
 //                             PrecomputedTri (tri.h:35-37), then the bottom-up pass of build_core.cuh
 //                             that links parents, unions boxes (bvh.h:213-217), collapses subtrees into
 //                             leaves by SAH (split_heuristic.h:30-38) and stores each node once, in its
-//                             final reference-layout slot.
+//                             final reference-layout slot; merges inside a block's 128 leaves meet in
+//                             shared memory, the rest through global arrival flags.
 #include <cstdlib>
 #include <string>
 

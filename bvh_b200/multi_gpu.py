@@ -103,7 +103,9 @@ class FusedGatherTracer:
         self.handle = symm_mem.rendezvous(self.gathered, self.group)
         self.peers = [int(p) for p in self.handle.buffer_ptrs]
         multicast = int(getattr(self.handle, "multicast_ptr", 0) or 0)
-        if mode == "peer":
+        # Measured on B200 / NVSwitch (profiles/r01_gather_modes.txt): with two ranks the multicast store is the
+        # faster form (5227 vs 5155 Mrays/s), with four it is the slower one (8846 vs 10049) — "auto" follows that.
+        if mode == "peer" or (mode == "auto" and self.world > 2):
             multicast = 0
         if mode == "multicast" and not multicast:
             raise RuntimeError("no multicast address for the symmetric buffer on this fabric")

@@ -20,6 +20,7 @@
 #include "build_core.cuh"
 #include "engine.h"
 #include "radix_sort.cuh"
+#include "treelet_sah.cuh"
 #include "wide_bvh.cuh"
 
 namespace bvhb200 {
@@ -258,6 +259,36 @@ void launch_hierarchy(const BuildParams<T>& p, const K* keys, const uint32_t* va
 #undef BVH_LAUNCH_H
 }
 
+// ---- EXPERIMENTAL second pass: SAH rebuild of the bottom subtrees (treelet_sah.cuh) -------------------------
+// Not yet validated on hardware (the host emulation runs the same source, tests/test_host_emulation.py);
+// only reached with BuildOptions::sah_treelets / BVH_B200_SAH_TREELETS=1.
+// K5a: one thread per inner node: is it the root of a maximal subtree of <= kMaxPrims primitives?
+template <typename T, typename K>
+__global__ void __launch_bounds__(kBlock)
+find_treelets_kernel(const DevNode<T>* __restrict__ nodes, const K* __restrict__ keys, uint32_t n,
+                     Treelet* __restrict__ list, uint32_t* __restrict__ list_count) {
+    const uint32_t p = blockIdx.x * kBlock + threadIdx.x;
+    if (p + 1 >= n) return;
+    Treelet t;
+    if (treelet_probe<T, K>(nodes, keys, n, p, (uint32_t)TreeletCfg<T>::kMaxPrims, t)) list[atomicAdd(list_count, 1u)] = t;
+}
+
+// K5b: one block per treelet (grid-stride over the list).
+template <typename T>
+__global__ void __launch_bounds__(TreeletCfg<T>::kMaxPrims)
+treelet_kernel(const Treelet* __restrict__ list, const uint32_t* __restrict__ list_count, DevNode<T>* __restrict__ nodes,
+               uint32_t* __restrict__ prim_ids, DevTri<T>* __restrict__ tris, const T* __restrict__ leaf_src,
+               const T* __restrict__ centre_src, int leaf_mode, uint32_t min_leaf, uint32_t max_leaf, uint32_t* __restrict__ info) {
+    constexpr int S = TreeletCfg<T>::kMaxPrims;
+    __shared__ TreeletScratch<T, S> scratch;
+    const uint32_t count = *list_count, lbvh_depth = info[0];
+    for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
+        const Treelet t = list[i];
+        treelet_rebuild<T, S, BlockExec>(scratch, t, nodes, prim_ids, tris, leaf_src, centre_src, leaf_mode, min_leaf, max_leaf, info, lbvh_depth);
+        __syncthreads();
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock)
 permute_tris_kernel(const T* __restrict__ verts, const uint32_t* __restrict__ prim_ids, uint32_t n,
@@ -484,10 +515,23 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     launch_hierarchy<T, K>(p, keys_a, out.prim_ids, leaf_src, mode, out.tris, stream);
     BVH_CUDA_TRY(cudaGetLastError());
 
+    const bool treelets = options.sah_treelets && n > 2;
+    if (treelets) {                                          // EXPERIMENTAL, see treelet_sah.cuh
+        Treelet* list; uint32_t* list_count;
+        if (scratch.alloc(&list, (size_t)n / 3 + 1) || scratch.alloc(&list_count, 1)) return -1;
+        BVH_CUDA_TRY(cudaMemsetAsync(list_count, 0, sizeof(uint32_t), stream));
+        BVH_CUDA_TRY(cudaMemsetAsync(info + 2, 0, 2 * sizeof(uint32_t), stream));
+        find_treelets_kernel<T, K><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(out.nodes, keys_a, n, list, list_count);
+        const uint32_t max_blocks = (uint32_t)sm_count * 5u, want = n / 3 + 1;
+        treelet_kernel<T><<<want < max_blocks ? want : max_blocks, TreeletCfg<T>::kMaxPrims, 0, stream>>>(
+            list, list_count, out.nodes, out.prim_ids, out.tris, leaf_src, centre_src, mode, p.min_leaf, p.max_leaf, info);
+        BVH_CUDA_TRY(cudaGetLastError());
+    }
+
     uint32_t host_info[4] = { 0, 0, 0, 0 };
     BVH_CUDA_TRY(cudaMemcpyAsync(host_info, info, sizeof(host_info), cudaMemcpyDeviceToHost, stream));
     BVH_CUDA_TRY(cudaStreamSynchronize(stream));
-    out.depth = host_info[0];
+    out.depth = host_info[0] + (treelets ? host_info[2] : 0u);
     if (make_wide_tree(out, stream)) return -1;
     out.compact = false;
     return 0;
@@ -502,12 +546,14 @@ int build_lbvh(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const T* 
     if (!d_verts && (!d_bboxes || !d_centers)) { set_error("build: need vertices or boxes+centres"); return -1; }
     // first_id must fit Index<32,4>: 2n-1 <= 2^28-1 for float (index.h:39)
     if (sizeof(T) == 4 && 2 * (uint64_t)n > ((uint64_t)1 << 28)) { set_error("build: too many primitives for a 32-bit index"); return -1; }
+    BuildOptions opts = options;
+    if (const char* e = std::getenv("BVH_B200_SAH_TREELETS")) opts.sah_treelets = std::atoi(e) != 0;   // experiments only
     int bits = options.morton_bits;
     if (const char* e = std::getenv("BVH_B200_MORTON_BITS")) bits = std::atoi(e);      // test hook: 30 or 63
     if (bits == 0) bits = n >= (1u << 22) ? 63 : 30;
     int rc;
-    if (bits <= 30) rc = build_with_key<T, uint32_t>(out, d_verts, d_bboxes, d_centers, n, options, 30, stream);
-    else            rc = build_with_key<T, uint64_t>(out, d_verts, d_bboxes, d_centers, n, options, 63, stream);
+    if (bits <= 30) rc = build_with_key<T, uint32_t>(out, d_verts, d_bboxes, d_centers, n, opts, 30, stream);
+    else            rc = build_with_key<T, uint64_t>(out, d_verts, d_bboxes, d_centers, n, opts, 63, stream);
     if (rc) release(out, stream);
     return rc;
 }

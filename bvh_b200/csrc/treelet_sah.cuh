@@ -1,0 +1,364 @@
+// bvh_b200/csrc/treelet_sah.cuh — SAH rebuild of the bottom of the LBVH ("treelets").  EXPERIMENTAL: validated
+// on the CPU emulation only (tests/test_host_emulation.py); off unless BuildOptions::sah_treelets is set.
+//
+// Why: measured on the emulation, the 11-23 % more traversal steps the LBVH needs compared with
+// the reference's SAH trees come from the bottom levels: keeping the LBVH above and rebuilding every maximal
+// subtree of at most 256 primitives with the reference's sweep-SAH rule recovers the reference's step counts
+// on the soup and about half of the gap on the height-field, while a SAH top level over LBVH subtrees
+// recovers nothing.
+//
+// What: for every maximal LBVH subtree with at most kMaxPrims primitives (found from the sorted keys alone,
+// treelet_probe), one thread block rebuilds the subtree top-down with the greedy rule of the reference's
+// SweepSahBuilder / TopDownSahBuilder (sweep_sah_builder.h:57-139, top_down_sah_builder.h:74-131): primitives
+// sorted once along each axis, per node the split minimising area(L)*|L| + area(R)*|R| over the three axes
+// and all positions, leaf when no split beats area*(count - 1) and count <= max_leaf_size, median split on
+// the largest axis otherwise, stable partition of the other two orders, larger-area child first (SATO).
+// All nodes of one LEVEL of the treelet are processed together: the three orders keep each node's primitives in
+// one contiguous segment, and prefix / suffix boxes, split costs, minima and partitions are segmented scans
+// over the whole array.  The subtree is written into the node slots the LBVH subtree owned (pairs l .. r-1 of the
+// sorted range [l, r]), primitives are re-ordered inside [l, r] only, and the subtree's box is unchanged, so
+// nothing above the treelet moves.
+//
+// The algorithm is written as PHASES over array positions, parametrised by an execution policy: on the device a
+// phase is a block-strided loop followed by __syncthreads(), in the host emulation a plain loop — the same
+// source, the same arithmetic (Real<T> ops, no contraction), hence the same tree.
+#pragma once
+
+#include "build_core.cuh"
+
+namespace bvhb200 {
+
+template <typename T> struct TreeletCfg { static constexpr int kMaxPrims = sizeof(T) == 4 ? 256 : 128; };
+
+struct Treelet { uint32_t slot, l, r; };     // device slot of the subtree's root record, sorted range [l, r]
+
+// ---- finding the treelet roots ----------------------------------------------------------------------
+// The LBVH is the Cartesian tree of the boundary "distances" (build_core.cuh: Delta): inner node p (the split
+// between sorted primitives p and p+1) covers the maximal range around the boundary in which every other
+// boundary is more similar.  Returns the number of primitives of node p and its range, or 0 as soon as the
+// range exceeds `limit` primitives.
+template <typename K>
+BVH_HD uint32_t treelet_range(const K* __restrict__ keys, uint32_t n, uint32_t p, uint32_t limit, uint32_t& l, uint32_t& r) {
+    const Delta<K> dp = delta_at(keys, p);
+    l = p; r = p + 1;
+    while (l > 0 && delta_less(delta_at(keys, l - 1), dp)) { --l; if (r - l + 1 > limit) return 0; }
+    while (r + 1 < n && delta_less(delta_at(keys, r), dp)) { ++r; if (r - l + 1 > limit) return 0; }
+    return r - l + 1;
+}
+
+// Is inner node p the root of a treelet (at most `limit` primitives, parent larger or absent)?  On success
+// fills `out` (the slot is found by looking at the parent's two child records, which the SATO swap may have
+// exchanged).  Nodes of fewer than three primitives are left alone (the LBVH pass already decided them by the
+// same rule).
+template <typename T, typename K>
+BVH_HD bool treelet_probe(const DevNode<T>* __restrict__ nodes, const K* __restrict__ keys, uint32_t n, uint32_t p,
+                          uint32_t limit, Treelet& out) {
+    using U = typename Real<T>::UInt;
+    uint32_t l, r;
+    const uint32_t count = treelet_range(keys, n, p, limit, l, r);
+    if (count < 3) return false;
+    out.l = l; out.r = r;
+    if (l == 0 && r == n - 1) { out.slot = 1; return true; }            // the whole tree is one treelet
+    uint32_t parent, side;
+    choose_parent(keys, n, l, r, parent, side);
+    uint32_t pl, pr;
+    if (treelet_range(keys, n, parent, limit, pl, pr) != 0) return false;     // the parent is small enough itself
+    const U as_inner = make_index<U>((U)(2 * (size_t)p + 1), 0), as_leaf = make_index<U>((U)l, count);
+    for (uint32_t s = 0; s < 2; ++s) {
+        const U index = nodes[child_slot(parent, s)].index;
+        if (index == as_inner || (count <= kMaxLeafPrims && index == as_leaf)) { out.slot = (uint32_t)child_slot(parent, s); return true; }
+    }
+    return false;                                                        // unreachable for a consistent tree
+}
+
+// ---- execution policies --------------------------------------------------------------------------------
+struct HostExec {
+    template <typename F> static void phase(uint32_t n, F f) { for (uint32_t i = 0; i < n; ++i) f(i); }
+    static uint32_t atomic_add(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
+    static void atomic_max(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
+};
+#if defined(__CUDACC__)
+struct BlockExec {
+    template <typename F> static __device__ __forceinline__ void phase(uint32_t n, F f) {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) f(i);
+        __syncthreads();
+    }
+    static __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+    static __device__ __forceinline__ void atomic_max(uint32_t* p, uint32_t v) { atomicMax(p, v); }
+};
+#endif
+
+// ---- scratch of one treelet (shared memory on the device) ------------------------------------------
+template <typename T, int S> struct TreeletScratch {
+    T box[6][S];                         // per PRIMITIVE (local index): minx,maxx,miny,maxy,minz,maxz
+    T centre[3][S];
+    uint32_t old_ids[S];                 // prim_ids[l + i] before the rebuild
+    uint16_t order[3][S];                // local primitive indices sorted along each axis, segment by segment
+    uint16_t tmp16[S];
+    uint16_t seg_begin[S], seg_end[S];   // per POSITION: its segment; seg_end == 0: the segment became a leaf
+    T scan[2][6][S];                     // ping-pong buffers of the segmented box scans
+    T right_cost[S], right_area[S];      // cost / half-area of [pos, end) on the current axis
+    T cand_cost[2][S];                   // ping-pong buffers of the segmented min-scan ...
+    uint16_t cand_pos[2][S];             // ... and of the segmented flag sums
+    // per SEGMENT, stored at the position of its head (= seg_begin)
+    T nbox[6][S];
+    T leaf_cost[S], best_cost[S], best_larea[S], best_rarea[S];
+    uint16_t best_pos[S];
+    uint8_t best_axis[S], split[S], seg_depth[S];
+    uint32_t dst_slot[S], left_slot[S], right_slot[S];
+    uint8_t side[S];                     // per PRIMITIVE: 1 = goes to the left part
+    uint32_t counters[4];                // [0] next pair, [1] live segments, [2] treelet depth, [3] longest live segment
+};
+
+template <typename T> BVH_HD T treelet_inf() { return Real<T>::from_bits(sizeof(T) == 4 ? (typename Real<T>::UInt)0x7F800000u : (typename Real<T>::UInt)0x7FF0000000000000ull); }
+
+template <typename T, int S> BVH_HD T treelet_half_area(const T (&b)[2][6][S], int buf, uint32_t pos) {
+    const T mn[3] = { b[buf][0][pos], b[buf][2][pos], b[buf][4][pos] }, mx[3] = { b[buf][1][pos], b[buf][3][pos], b[buf][5][pos] };
+    return half_area(mn, mx);
+}
+
+// Rebuilds one treelet.  `leaf_src`: vertices (n x 9, leaf_mode 0) or boxes (n x 6, leaf_mode 1); `centre_src`:
+// vertices or centres (n x 3), indexed by ORIGINAL primitive id.  `tris` (leaf_mode 0 only) receives the
+// BVH-order triangle records of the range.  info[2] collects by how much a treelet got deeper than the subtree
+// it replaces (the traversal stack is sized from info[0] + info[2]).
+template <typename T, int S, typename Exec>
+BVH_HD void treelet_rebuild(TreeletScratch<T, S>& w, const Treelet& t, DevNode<T>* __restrict__ nodes,
+                            uint32_t* __restrict__ prim_ids, DevTri<T>* __restrict__ tris,
+                            const T* __restrict__ leaf_src, const T* __restrict__ centre_src, int leaf_mode,
+                            uint32_t min_leaf, uint32_t max_leaf, uint32_t* __restrict__ info, uint32_t lbvh_depth) {
+    using R = Real<T>;
+    using U = typename R::UInt;
+    const uint32_t n = t.r - t.l + 1, l = t.l;
+    const T inf = treelet_inf<T>();
+    // depth of the subtree being replaced (its root record still carries it; the tree's root record does not)
+    const uint32_t old_depth = t.slot == 1 ? lbvh_depth : AuxPack<T>::depth(nodes[t.slot].pad);
+
+    // ---- load the primitives ----
+    Exec::phase(n, [&] (uint32_t i) {
+        const uint32_t id = prim_ids[l + i];
+        w.old_ids[i] = id;
+        T bmin[3], bmax[3], c[3];
+        if (leaf_mode == 0) {
+            T v[9];
+            for (int k = 0; k < 9; ++k) v[k] = leaf_src[9 * (size_t)id + k];
+            tri_bounds_center(v, bmin, bmax, c);
+        } else {
+            for (int k = 0; k < 3; ++k) {
+                bmin[k] = leaf_src[6 * (size_t)id + k]; bmax[k] = leaf_src[6 * (size_t)id + 3 + k];
+                c[k] = centre_src[3 * (size_t)id + k];
+            }
+        }
+        for (int k = 0; k < 3; ++k) { w.box[2 * k][i] = bmin[k]; w.box[2 * k + 1][i] = bmax[k]; w.centre[k][i] = c[k]; }
+        w.seg_begin[i] = 0; w.seg_end[i] = (uint16_t)n;
+        if (i == 0) {
+            w.dst_slot[0] = t.slot; w.seg_depth[0] = 0;
+            w.counters[0] = 0; w.counters[1] = 1; w.counters[2] = 0; w.counters[3] = n;
+        }
+    });
+    // ---- sort once along each axis: rank of a primitive = number of primitives before it in (centre, index) order
+    Exec::phase(3 * n, [&] (uint32_t x) {
+        const uint32_t a = x / n, i = x - a * n;
+        const T ci = w.centre[a][i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; ++j) {
+            const T cj = w.centre[a][j];
+            rank += (cj < ci || (cj == ci && j < i)) ? 1u : 0u;
+        }
+        w.order[a][rank] = (uint16_t)i;        // a NaN centre gives colliding ranks: such input is undefined in the reference too
+    });
+
+    // ---- level by level ----
+    while (w.counters[1] != 0) {
+        const uint32_t longest = w.counters[3];
+        for (int a = 0; a < 3; ++a) {
+            // suffix boxes: scan[cur][.][pos] = union of the boxes at positions [pos, segment end)
+            int cur = 0;
+            Exec::phase(n, [&] (uint32_t pos) {
+                const uint32_t prim = w.order[a][pos];
+                for (int c = 0; c < 6; ++c) w.scan[0][c][pos] = w.box[c][prim];
+            });
+            for (uint32_t d = 1; d < longest; d <<= 1) {
+                Exec::phase(n, [&] (uint32_t pos) {
+                    const uint32_t se = w.seg_end[pos];
+                    const bool take = se != 0 && pos + d < se;
+                    for (int c = 0; c < 6; c += 2) {
+                        const T mn = w.scan[cur][c][pos], mx = w.scan[cur][c + 1][pos];
+                        w.scan[cur ^ 1][c][pos]     = take ? robust_min(mn, w.scan[cur][c][pos + d]) : mn;
+                        w.scan[cur ^ 1][c + 1][pos] = take ? robust_max(mx, w.scan[cur][c + 1][pos + d]) : mx;
+                    }
+                });
+                cur ^= 1;
+            }
+            Exec::phase(n, [&] (uint32_t pos) {
+                const uint32_t se = w.seg_end[pos];
+                if (se == 0) return;
+                const T area = treelet_half_area(w.scan, cur, pos);
+                w.right_area[pos] = area;
+                w.right_cost[pos] = R::mul(area, (T)(se - pos));                       // get_leaf_cost, split_heuristic.h:30-33
+                if (a == 0 && w.seg_begin[pos] == pos) {                                // the head: this is the node's box
+                    for (int c = 0; c < 6; ++c) w.nbox[c][pos] = w.scan[cur][c][pos];
+                    const T lc = R::mul(area, (T)(se - pos - 1));                       // get_non_split_cost, :35-38 (cost_ratio 1)
+                    w.leaf_cost[pos] = lc; w.best_cost[pos] = lc;
+                    w.best_pos[pos] = (uint16_t)((pos + se + 1) / 2); w.best_axis[pos] = 0;     // sweep_sah_builder.h:111
+                    w.best_larea[pos] = (T)0; w.best_rarea[pos] = (T)0;
+                }
+            });
+            // prefix boxes: scan[cur][.][pos] = union of the boxes at positions [segment begin, pos]
+            cur = 0;
+            Exec::phase(n, [&] (uint32_t pos) {
+                const uint32_t prim = w.order[a][pos];
+                for (int c = 0; c < 6; ++c) w.scan[0][c][pos] = w.box[c][prim];
+            });
+            for (uint32_t d = 1; d < longest; d <<= 1) {
+                Exec::phase(n, [&] (uint32_t pos) {
+                    const bool take = w.seg_end[pos] != 0 && pos >= w.seg_begin[pos] + d;
+                    for (int c = 0; c < 6; c += 2) {
+                        const T mn = w.scan[cur][c][pos], mx = w.scan[cur][c + 1][pos];
+                        w.scan[cur ^ 1][c][pos]     = take ? robust_min(mn, w.scan[cur][c][pos - d]) : mn;
+                        w.scan[cur ^ 1][c + 1][pos] = take ? robust_max(mx, w.scan[cur][c + 1][pos - d]) : mx;
+                    }
+                });
+                cur ^= 1;
+            }
+            // cost of splitting after position pos (left = [begin, pos], right = [pos + 1, end)); first minimum per segment
+            int cc = 0;
+            Exec::phase(n, [&] (uint32_t pos) {
+                const uint32_t se = w.seg_end[pos], sb = w.seg_begin[pos];
+                T cost = inf;
+                if (se != 0 && pos + 1 < se)
+                    cost = R::add(R::mul(treelet_half_area(w.scan, cur, pos), (T)(pos + 1 - sb)), w.right_cost[pos + 1]);
+                w.cand_cost[0][pos] = cost; w.cand_pos[0][pos] = (uint16_t)(pos + 1);
+            });
+            for (uint32_t d = 1; d < longest; d <<= 1) {
+                Exec::phase(n, [&] (uint32_t pos) {
+                    T c = w.cand_cost[cc][pos]; uint16_t k = w.cand_pos[cc][pos];
+                    if (w.seg_end[pos] != 0 && pos >= w.seg_begin[pos] + d) {
+                        const T cl = w.cand_cost[cc][pos - d];
+                        if (cl <= c) { c = cl; k = w.cand_pos[cc][pos - d]; }            // ties: the earlier position (strict < in the reference's sweep)
+                    }
+                    w.cand_cost[cc ^ 1][pos] = c; w.cand_pos[cc ^ 1][pos] = k;
+                });
+                cc ^= 1;
+            }
+            Exec::phase(n, [&] (uint32_t pos) {                                         // heads: keep the best axis (first one on ties)
+                const uint32_t se = w.seg_end[pos];
+                if (se == 0 || w.seg_begin[pos] != pos || se - pos < 2) return;
+                const T c = w.cand_cost[cc][se - 1];
+                if (c < w.best_cost[pos]) {
+                    const uint32_t k = w.cand_pos[cc][se - 1];
+                    w.best_cost[pos] = c; w.best_pos[pos] = (uint16_t)k; w.best_axis[pos] = (uint8_t)a;
+                    w.best_larea[pos] = treelet_half_area(w.scan, cur, k - 1);
+                    w.best_rarea[pos] = w.right_area[k];
+                }
+            });
+        }
+
+        // ---- decide every live segment: leaf, SAH split or median fallback; write the node record ----
+        Exec::phase(n, [&] (uint32_t pos) {
+            const uint32_t se = w.seg_end[pos];
+            if (se == 0 || w.seg_begin[pos] != pos) return;
+            const uint32_t count = se - pos;
+            bool do_split = false;
+            if (count > min_leaf) {                                                      // top_down_sah_builder.h:89
+                if (w.best_cost[pos] < w.leaf_cost[pos]) do_split = true;                // sweep_sah_builder.h:116
+                else if (count > max_leaf) {                                             // :117-123: median on the largest axis
+                    const T d0 = R::sub(w.nbox[1][pos], w.nbox[0][pos]), d1 = R::sub(w.nbox[3][pos], w.nbox[2][pos]),
+                            d2 = R::sub(w.nbox[5][pos], w.nbox[4][pos]);
+                    uint8_t axis = 0;                                                    // Vec::get_largest_axis
+                    if (d0 < d1) axis = 1;
+                    if ((axis == 0 ? d0 : d1) < d2) axis = 2;
+                    w.best_pos[pos] = (uint16_t)((pos + se + 1) / 2); w.best_axis[pos] = axis;
+                    w.best_larea[pos] = (T)0; w.best_rarea[pos] = (T)0;                  // (no SATO swap for the fallback)
+                    do_split = true;
+                }
+            }
+            const T bmin[3] = { w.nbox[0][pos], w.nbox[2][pos], w.nbox[4][pos] }, bmax[3] = { w.nbox[1][pos], w.nbox[3][pos], w.nbox[5][pos] };
+            if (do_split) {
+                const uint32_t pair = l + Exec::atomic_add(&w.counters[0], 1u);          // one of the pairs l .. r-1 the LBVH subtree owned
+                const bool swap = w.best_larea[pos] < w.best_rarea[pos];                 // SATO, top_down_sah_builder.h:101-108
+                w.left_slot[pos]  = (uint32_t)child_slot(pair, swap ? 1 : 0);
+                w.right_slot[pos] = (uint32_t)child_slot(pair, swap ? 0 : 1);
+                write_node(nodes + w.dst_slot[pos], bmin, bmax, make_index<U>((U)(2 * (size_t)pair + 1), 0));
+                w.split[pos] = 1;
+            } else {
+                write_node(nodes + w.dst_slot[pos], bmin, bmax, make_index<U>((U)(l + pos), count));
+                Exec::atomic_max(&w.counters[2], (uint32_t)w.seg_depth[pos]);
+                w.split[pos] = 0;
+            }
+        });
+
+        // ---- partition: mark sides on the split axis, stable-partition the two other orders ----
+        Exec::phase(n, [&] (uint32_t pos) {
+            const uint32_t se = w.seg_end[pos];
+            if (se == 0) return;
+            const uint32_t h = w.seg_begin[pos];
+            if (w.split[h]) w.side[w.order[w.best_axis[h]][pos]] = pos < w.best_pos[h] ? 1 : 0;
+        });
+        for (int b = 0; b < 3; ++b) {
+            int cc = 0;
+            Exec::phase(n, [&] (uint32_t pos) {
+                const uint32_t se = w.seg_end[pos];
+                uint16_t f = 0;
+                if (se != 0) { const uint32_t h = w.seg_begin[pos]; if (w.split[h] && w.best_axis[h] != b) f = w.side[w.order[b][pos]]; }
+                w.cand_pos[0][pos] = f;
+            });
+            for (uint32_t d = 1; d < longest; d <<= 1) {
+                Exec::phase(n, [&] (uint32_t pos) {
+                    uint16_t v = w.cand_pos[cc][pos];
+                    if (w.seg_end[pos] != 0 && pos >= w.seg_begin[pos] + d) v = (uint16_t)(v + w.cand_pos[cc][pos - d]);
+                    w.cand_pos[cc ^ 1][pos] = v;
+                });
+                cc ^= 1;
+            }
+            Exec::phase(n, [&] (uint32_t pos) {
+                const uint32_t se = w.seg_end[pos];
+                uint32_t dst = pos;
+                if (se != 0) {
+                    const uint32_t h = w.seg_begin[pos];
+                    if (w.split[h] && w.best_axis[h] != b) {
+                        const uint32_t f = w.side[w.order[b][pos]], before = w.cand_pos[cc][pos] - f, k = w.best_pos[h];
+                        dst = f ? h + before : k + (pos - h - before);
+                    }
+                }
+                w.tmp16[dst] = w.order[b][pos];
+            });
+            Exec::phase(n, [&] (uint32_t pos) { w.order[b][pos] = w.tmp16[pos]; });
+        }
+        // ---- the children become the segments of the next level ----
+        Exec::phase(n, [&] (uint32_t pos) {                                              // heads hand slots and depth to both children
+            const uint32_t se = w.seg_end[pos];
+            if (se == 0 || w.seg_begin[pos] != pos || !w.split[pos]) return;
+            const uint32_t k = w.best_pos[pos];
+            const uint8_t depth = (uint8_t)(w.seg_depth[pos] + 1);
+            w.dst_slot[k] = w.right_slot[pos]; w.seg_depth[k] = depth;
+            w.dst_slot[pos] = w.left_slot[pos]; w.seg_depth[pos] = depth;
+        });
+        Exec::phase(n, [&] (uint32_t pos) {                                              // positions move to their child segment
+            if (pos == 0) { w.counters[1] = 0; w.counters[3] = 0; }
+            const uint32_t se = w.seg_end[pos];
+            if (se == 0) return;
+            const uint32_t h = w.seg_begin[pos];                                         // (reads the OLD head's decision only)
+            if (!w.split[h]) { w.seg_end[pos] = 0; return; }                             // its node became a leaf: finished
+            const uint32_t k = w.best_pos[h];
+            if (pos < k) w.seg_end[pos] = (uint16_t)k; else w.seg_begin[pos] = (uint16_t)k;
+        });
+        Exec::phase(n, [&] (uint32_t pos) {
+            const uint32_t se = w.seg_end[pos];
+            if (se != 0 && w.seg_begin[pos] == pos) { Exec::atomic_add(&w.counters[1], 1u); Exec::atomic_max(&w.counters[3], se - pos); }
+        });
+    }
+
+    // ---- final primitive order = order along axis 0 (every leaf's primitives are contiguous in all three) ----
+    Exec::phase(n, [&] (uint32_t pos) {
+        const uint32_t id = w.old_ids[w.order[0][pos]];
+        prim_ids[l + pos] = id;
+        if (leaf_mode == 0 && tris) {
+            T v[9];
+            for (int k = 0; k < 9; ++k) v[k] = leaf_src[9 * (size_t)id + k];
+            tris[l + pos] = precompute_tri(v);
+        }
+        if (pos == 0 && w.counters[2] > old_depth) Exec::atomic_max(info + 2, w.counters[2] - old_depth);
+    });
+}
+
+} // namespace bvhb200

@@ -29,7 +29,7 @@ def build_host_emul() -> str:
     out_dir = os.path.join(ROOT, "tests", "_build")
     out = os.path.join(out_dir, "libhost_emul.so")
     csrc = os.path.join(ROOT, "bvh_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("core.cuh", "build_core.cuh", "traverse_core.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("core.cuh", "build_core.cuh", "traverse_core.cuh", "treelet_sah.cuh", "wide_bvh.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(out_dir, exist_ok=True)
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC",
@@ -54,6 +54,8 @@ class HostEmul:
         L.emul_wide_build.argtypes = [P, P, C.c_size_t, P]
         L.emul_wide_trace.argtypes = [P, P, P, P, C.c_size_t, C.c_uint, P, P, P, P, P]
         L.emul_set_block.argtypes = [C.c_int, C.c_int]
+        L.emul_set_treelets.argtypes = [C.c_int]
+        L.emul_last_treelet_count.restype = C.c_int
         L.emul_morton30.restype = C.c_uint32
         L.emul_morton30.argtypes = [C.c_uint32] * 3
         L.emul_morton63.restype = C.c_uint64
@@ -75,6 +77,10 @@ class HostEmul:
         getattr(self.lib, f"emul_build{s}")(_ptr(tris), _ptr(bboxes), _ptr(centers), n, min_leaf, max_leaf, morton_bits,
                                             _ptr(nodes), _ptr(ids), _ptr(dtris), C.byref(depth))
         return dict(nodes=nodes, prim_ids=ids, tris=dtris, depth=depth.value, dtype=dtype, n=n)
+
+    def set_treelets(self, on: bool):
+        """Experimental second build pass: SAH rebuild of the LBVH's bottom subtrees (treelet_sah.cuh)."""
+        self.lib.emul_set_treelets(1 if on else 0)
 
     def set_block(self, leaves=0, order=0):
         """0 leaves: every merge through the global flags; else the device kernel's block-local first phase."""

@@ -9,9 +9,11 @@
 #include <cstdint>
 #include <cstring>
 #include <numeric>
+#include <memory>
 #include <vector>
 
 #include "build_core.cuh"
+#include "treelet_sah.cuh"
 #include "traverse_core.cuh"
 #include "wide_bvh.cuh"
 
@@ -27,7 +29,7 @@ template <typename U> struct HostStack {
     bool empty() const { return sp == 0; }
 };
 
-static int g_block_leaves = 0, g_block_order = 0;
+static int g_block_leaves = 0, g_block_order = 0, g_treelets = 0, g_last_treelets = 0;
 
 template <typename T, typename K>
 uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t n, uint32_t min_leaf, uint32_t max_leaf,
@@ -107,7 +109,22 @@ uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t 
             }
         }
     }
-    *depth_out = info[0];
+    if (g_treelets && n > 1) {
+        // the experimental second pass (treelet_sah.cuh): rebuild every maximal subtree of <= kMaxPrims primitives
+        constexpr int S = TreeletCfg<T>::kMaxPrims;
+        std::vector<Treelet> list;
+        for (uint32_t q = 0; q + 1 < n; ++q) {
+            Treelet t;
+            if (treelet_probe<T, K>(nodes, sorted.data(), n, q, (uint32_t)S, t)) list.push_back(t);
+        }
+        auto scratch = std::make_unique<TreeletScratch<T, S>>();
+        const T* leaf_src = verts ? verts : bboxes;
+        for (const Treelet& t : list)
+            treelet_rebuild<T, S, HostExec>(*scratch, t, nodes, prim_ids, verts ? tris : nullptr, leaf_src, centers, verts ? 0 : 1,
+                                            min_leaf, max_leaf, info, info[0]);
+        g_last_treelets = (int)list.size();
+    }
+    *depth_out = info[0] + info[2];
     return info[1];
 }
 
@@ -269,6 +286,8 @@ void emul_wide_trace(const void* wide, const void* tris, const uint32_t* prim_id
 }
 EMUL_API(float, 3f)
 EMUL_API(double, 3d)
+void emul_set_treelets(int on) { g_treelets = on; }
+int emul_last_treelet_count() { return g_last_treelets; }
 void emul_set_block(int leaves, int order) { g_block_leaves = leaves; g_block_order = order; }
 uint32_t emul_morton30(uint32_t x, uint32_t y, uint32_t z) { return MortonTraits<uint32_t>::encode(x, y, z); }
 uint64_t emul_morton63(uint64_t x, uint64_t y, uint64_t z) { return MortonTraits<uint64_t>::encode(x, y, z); }

@@ -554,3 +554,29 @@ def test_gather_entry_point_on_one_gpu(gpu_lib, dtype, flags_name):
             assert (got[:offset] == 0x5A5A5A5A).all() and (got[offset + m:] == 0x5A5A5A5A).all()
         if with_local:
             assert (local.cpu().numpy() == expect).all()
+
+
+@pytest.mark.skipif(os.environ.get("BVH_B200_EXPERIMENTAL") != "1",
+                    reason="the SAH treelet pass has not been validated on hardware yet (set BVH_B200_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("kind,n,dtype", [("soup", 20000, np.float32), ("grid", 20000, np.float32), ("soup", 6000, np.float64),
+                                           ("soup", 200, np.float32), ("soup", 3, np.float32)])
+def test_experimental_sah_treelets_match_the_emulation(gpu_lib, emul, monkeypatch, kind, n, dtype):
+    """BVH_B200_SAH_TREELETS=1: the device runs the same phase code as the host emulation, so the compacted
+    trees must be identical and the traversal results equal to the plain LBVH's."""
+    api = gpu_lib
+    tris = (scenes.soup(n, seed=7) if kind == "soup" else scenes.make_mesh(kind, n)).astype(dtype)
+    rays = scenes.make_primary(kind, 128, 128, dtype=dtype)
+    plain = api.Bvh.build_triangles(tris)
+    monkeypatch.setenv("BVH_B200_SAH_TREELETS", "1")
+    bvh = api.Bvh.build_triangles(tris)
+    monkeypatch.delenv("BVH_B200_SAH_TREELETS")
+    bounds, index_values, prim_ids = bvh.arrays()
+    try:
+        emul.set_treelets(True)
+        etree = emul.build(tris=tris)
+    finally:
+        emul.set_treelets(False)
+    eb, ei = emul.compact(etree)
+    assert eb.shape == bounds.shape and (eb == bounds).all() and (ei == index_values).all()
+    assert (etree["prim_ids"] == prim_ids).all() and bvh.depth == etree["depth"]
+    assert_hits_equal(hits_tuple(bvh.intersect_rays(rays)), hits_tuple(plain.intersect_rays(rays)), "treelets vs plain LBVH")

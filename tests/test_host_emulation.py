@@ -231,3 +231,60 @@ def test_block_local_phase_builds_the_same_tree(emul, kind, n, dtype):
                 assert np.array_equal(got["prim_ids"], ref["prim_ids"])
     finally:
         emul.set_block(0, 0)
+
+
+@pytest.mark.parametrize("kind,n,dtype", [("soup", 20000, np.float32), ("grid", 20000, np.float32), ("soup", 6000, np.float64),
+                                           ("soup", 200, np.float32), ("soup", 3, np.float32), ("soup", 2, np.float32), ("soup", 1, np.float32)])
+def test_sah_treelet_pass_keeps_results_and_saves_steps(emul, oracle, kind, n, dtype):
+    """The experimental second build pass (treelet_sah.cuh: SAH rebuild of every maximal LBVH subtree of at most
+    256 / 128 primitives) must leave a valid reference-layout BVH that answers every ray like the plain LBVH
+    (canonical tie-break), with the recorded depth still bounding the traversal stack, and with fewer steps."""
+    tris = (scenes.soup(n, seed=7) if kind == "soup" else scenes.make_mesh(kind, n)).astype(dtype)
+    rays = scenes.make_primary(kind, 96, 96, dtype=dtype)
+    plain = emul.build(tris=tris)
+    try:
+        emul.set_treelets(True)
+        tree = emul.build(tris=tris)
+    finally:
+        emul.set_treelets(False)
+    assert np.array_equal(np.sort(tree["prim_ids"]), np.arange(tris.shape[0]))
+    bounds, index_values = emul.compact(tree)
+    otree = oracle.from_arrays(bounds, index_values, tree["prim_ids"])
+    assert oracle.check_invariants(otree, 8) == 0
+    before = otree.arrays()[0]
+    oracle.refit(otree)                                   # every inner box is exactly the union of its children
+    assert (otree.arrays()[0] == before).all()
+    # depth bound: walk the compact tree
+    first, count = (index_values >> 4).astype(np.int64), (index_values & 15)
+    depth, stack = 0, [(0, 0)]
+    while stack:
+        i, d = stack.pop()
+        if count[i] == 0:
+            depth = max(depth, d + 1)
+            stack.append((first[i], d + 1)); stack.append((first[i] + 1, d + 1))
+    assert depth <= tree["depth"]
+    for flags in (TIE_LOWEST_ID, TIE_LOWEST_ID | ANY_HIT):
+        a, b = emul.trace(plain, rays, flags), emul.trace(tree, rays, flags)
+        if flags & ANY_HIT:
+            assert np.array_equal(a[0] != INVALID, b[0] != INVALID)
+        else:
+            assert_hits_equal(b[:4], a[:4], f"treelets {kind}-{n}")
+    if tris.shape[0] >= 6000:
+        steps_plain, steps_tree = emul.trace(plain, rays, TIE_LOWEST_ID)[4][:, 0].mean(), emul.trace(tree, rays, TIE_LOWEST_ID)[4][:, 0].mean()
+        assert steps_tree < 0.95 * steps_plain, (steps_plain, steps_tree)
+
+
+def test_sah_treelet_pass_on_boxes_and_duplicates(emul, oracle):
+    """Boxes + centres input (the reference's own build entry point) and heavily duplicated primitives."""
+    tris = scenes.soup(3000, seed=1)
+    tris = np.concatenate([tris, tris[:500], tris[:500]])                 # 1000 exact duplicates
+    bb, cc = oracle.tri_bboxes_centers(tris)
+    try:
+        emul.set_treelets(True)
+        tree = emul.build(bboxes=bb, centers=cc)
+    finally:
+        emul.set_treelets(False)
+    assert np.array_equal(np.sort(tree["prim_ids"]), np.arange(tris.shape[0]))
+    bounds, index_values = emul.compact(tree)
+    otree = oracle.from_arrays(bounds, index_values, tree["prim_ids"])
+    assert oracle.check_invariants(otree, 8) == 0

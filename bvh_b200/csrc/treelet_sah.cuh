@@ -77,6 +77,13 @@ struct HostExec {
     static uint32_t atomic_add(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p = o + v; return o; }
     static void atomic_max(uint32_t* p, uint32_t v) { if (v > *p) *p = v; }
 };
+// Same phases, iterations in descending order: a phase whose iterations depended on each other (a hazard between
+// the threads of the block on the device) would give a different tree (tests/test_host_emulation.py).
+struct HostExecReversed {
+    template <typename F> static void phase(uint32_t n, F f) { for (uint32_t i = n; i-- > 0;) f(i); }
+    static uint32_t atomic_add(uint32_t* p, uint32_t v) { return HostExec::atomic_add(p, v); }
+    static void atomic_max(uint32_t* p, uint32_t v) { HostExec::atomic_max(p, v); }
+};
 #if defined(__CUDACC__)
 struct BlockExec {
     template <typename F> static __device__ __forceinline__ void phase(uint32_t n, F f) {

@@ -78,9 +78,10 @@ class HostEmul:
                                             _ptr(nodes), _ptr(ids), _ptr(dtris), C.byref(depth))
         return dict(nodes=nodes, prim_ids=ids, tris=dtris, depth=depth.value, dtype=dtype, n=n)
 
-    def set_treelets(self, on: bool):
-        """Experimental second build pass: SAH rebuild of the LBVH's bottom subtrees (treelet_sah.cuh)."""
-        self.lib.emul_set_treelets(1 if on else 0)
+    def set_treelets(self, on, reversed_phases: bool = False):
+        """Experimental second build pass: SAH rebuild of the LBVH's bottom subtrees (treelet_sah.cuh);
+        ``reversed_phases`` runs the iterations of every phase in descending order (hazard check)."""
+        self.lib.emul_set_treelets((2 if reversed_phases else 1) if on else 0)
 
     def set_block(self, leaves=0, order=0):
         """0 leaves: every merge through the global flags; else the device kernel's block-local first phase."""

@@ -119,9 +119,14 @@ uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t 
         }
         auto scratch = std::make_unique<TreeletScratch<T, S>>();
         const T* leaf_src = verts ? verts : bboxes;
-        for (const Treelet& t : list)
-            treelet_rebuild<T, S, HostExec>(*scratch, t, nodes, prim_ids, verts ? tris : nullptr, leaf_src, centers, verts ? 0 : 1,
-                                            min_leaf, max_leaf, info, info[0]);
+        for (const Treelet& t : list) {
+            if (g_treelets == 2)          // iterations of every phase in descending order (hazard check)
+                treelet_rebuild<T, S, HostExecReversed>(*scratch, t, nodes, prim_ids, verts ? tris : nullptr, leaf_src, centers, verts ? 0 : 1,
+                                                        min_leaf, max_leaf, info, info[0]);
+            else
+                treelet_rebuild<T, S, HostExec>(*scratch, t, nodes, prim_ids, verts ? tris : nullptr, leaf_src, centers, verts ? 0 : 1,
+                                                min_leaf, max_leaf, info, info[0]);
+        }
         g_last_treelets = (int)list.size();
     }
     *depth_out = info[0] + info[2];

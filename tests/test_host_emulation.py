@@ -288,3 +288,21 @@ def test_sah_treelet_pass_on_boxes_and_duplicates(emul, oracle):
     bounds, index_values = emul.compact(tree)
     otree = oracle.from_arrays(bounds, index_values, tree["prim_ids"])
     assert oracle.check_invariants(otree, 8) == 0
+
+
+@pytest.mark.parametrize("kind,n,dtype", [("soup", 30000, np.float32), ("grid", 30000, np.float32), ("soup", 5000, np.float64)])
+def test_sah_treelet_phases_have_no_order_dependence(emul, kind, n, dtype):
+    """On the device the iterations of a phase are the threads of a block; running them in descending instead of
+    ascending order on the host must give the same tree (compacted: the order in which splits draw their node
+    pairs is free), or a phase reads something another iteration of the same phase writes."""
+    tris = (scenes.soup(n, seed=11) if kind == "soup" else scenes.make_mesh(kind, n)).astype(dtype)
+    try:
+        emul.set_treelets(True)
+        a = emul.build(tris=tris)
+        emul.set_treelets(True, reversed_phases=True)
+        b = emul.build(tris=tris)
+    finally:
+        emul.set_treelets(False)
+    (ab, ai), (bb, bi) = emul.compact(a), emul.compact(b)
+    assert ab.shape == bb.shape and (ab == bb).all() and (ai == bi).all()
+    assert (a["prim_ids"] == b["prim_ids"]).all() and a["depth"] == b["depth"]

@@ -306,3 +306,47 @@ def test_sah_treelet_phases_have_no_order_dependence(emul, kind, n, dtype):
     (ab, ai), (bb, bi) = emul.compact(a), emul.compact(b)
     assert ab.shape == bb.shape and (ab == bb).all() and (ai == bi).all()
     assert (a["prim_ids"] == b["prim_ids"]).all() and a["depth"] == b["depth"]
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_emulation_against_the_oracle(emul, oracle, seed):
+    """Random small scenes (clustered, duplicated, flat and degenerate triangles; random, axis-parallel and
+    zero-direction rays; both scalar types; both Morton widths; with and without the treelet pass): the device
+    code run on the host must agree with the reference algorithm on the same tree, bit for bit, counters included."""
+    rng = np.random.RandomState(1000 + seed)
+    dtype = np.float64 if seed % 4 == 3 else np.float32
+    n = int(rng.choice([1, 2, 3, 7, 33, 200, 900, 2500]))
+    centres = rng.rand(max(1, n // 20), 3) * rng.choice([1.0, 100.0, 1e-3])
+    base = centres[rng.randint(0, centres.shape[0], n)]
+    tris = (base[:, None, :] + (rng.rand(n, 3, 3) - 0.5) * rng.choice([0.02, 0.5])).reshape(n, 9)
+    if n >= 7:
+        tris[rng.randint(0, n, n // 7)] = tris[rng.randint(0, n, n // 7)]         # exact duplicates
+        flat = rng.randint(0, n, n // 7)
+        tris[flat, 2::3] = tris[flat, 2:3]                                        # axis-aligned (flat in z)
+        deg = rng.randint(0, n, max(1, n // 20))
+        tris[deg, 3:6] = tris[deg, 0:3]                                           # zero-area
+    tris = tris.astype(dtype)
+    m = 300
+    org = (rng.rand(m, 3) * 1.6 - 0.3) * float(np.abs(tris).max() + 1e-3)
+    target = tris.reshape(n, 3, 3).mean(axis=1)[rng.randint(0, n, m)]
+    d = target - org + (rng.rand(m, 3) - 0.5) * 0.05
+    d[:20, 0] = 0; d[20:30, :2] = 0; d[30:33] = 0                                 # axis-parallel and zero directions
+    rays = np.concatenate([org, d, np.zeros((m, 1)), np.full((m, 1), rng.choice([1.0, 2.0, np.finfo(np.float32).max]))], axis=1).astype(dtype)
+    try:
+        emul.set_treelets(seed % 2 == 1)
+        tree = emul.build(tris=tris, morton_bits=63 if seed % 3 == 2 else 30,
+                          min_leaf=int(rng.choice([1, 2])), max_leaf=int(rng.choice([1, 4, 8, 15])))
+    finally:
+        emul.set_treelets(False)
+    bounds, index_values = emul.compact(tree)
+    otree = oracle.from_arrays(bounds, index_values, tree["prim_ids"])
+    assert oracle.check_invariants(otree, 15) == 0
+    oracle.set_triangles(otree, tris)
+    for _, flags in MODES:
+        got = emul.trace(tree, rays, flags)
+        want = oracle.trace(otree, rays, flags=flags, stats=True)
+        assert_hits_equal(got[:4], want[:4], f"seed {seed} flags {flags}")
+        assert (got[4] == want[4]).all()
+    robust = [f for _, f in MODES if f & ROBUST and not f & ANY_HIT and f & TIE_LOWEST_ID]
+    if robust:
+        assert_hits_equal(emul.trace(tree, rays, robust[0])[:4], oracle.brute_force(tris, rays, flags=robust[0] & ~ROBUST), f"seed {seed} brute force")

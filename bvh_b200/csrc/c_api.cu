@@ -80,6 +80,9 @@ template <typename T> struct Handle {
     void* d_rays = nullptr; size_t d_rays_bytes = 0;
     void* d_hits = nullptr; size_t d_hits_bytes = 0;
     void* d_stats = nullptr; size_t d_stats_bytes = 0;
+    // Batched calls on one handle share its stream, staging buffers and the kernels' cursor/status words:
+    // concurrent callers are serialised (the reference's per-ray calls are const and run on the host mirror).
+    std::mutex batch_mutex;
 };
 
 template <typename T> int init_handle(Handle<T>& h) {
@@ -386,6 +389,7 @@ int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bv
     static_assert(sizeof(RayPod) == sizeof(DevRay<T>) && sizeof(HitPod) == sizeof(DevHit<T>), "POD layouts");
     if (!h) { set_error("null handle"); return -1; }
     if (n == 0) return 0;
+    std::lock_guard<std::mutex> lock(h->batch_mutex);
     BVH_CUDA_TRY(cudaSetDevice(h->device));
     if (ensure_device(*h)) return -1;
     const unsigned tf = translate_flags(flags);
@@ -416,9 +420,9 @@ int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bv
     // the staging buffers may still be in use by earlier work on the handle's stream
     BVH_CUDA_TRY(cudaEventRecord(h->events[0], h->stream));
     BVH_CUDA_TRY(cudaStreamWaitEvent(h->copy_in, h->events[0], 0));
-    // Equal chunks.  Measured (profiles/r01_e2e_chunking.txt): 8 equal chunks 6.86 ms; chunk sizes tapering
-    // towards the end 7.12 ms; 6 / 12 / 16 chunks 7.43 / 6.96 / 7.37 ms.  Upload (320 MB) and download (160 MB)
-    // share the link: the call runs at ~70 GB/s of combined PCIe traffic whatever the schedule.
+    // Equal chunks.  Measured (profiles/r01_e2e_chunking.txt): 8 equal chunks 6.86 ms; with chunk sizes tapering
+    // towards the end 7.12 ms (and 7.43 / 6.96 / 7.37 ms for 6 / 12 / 16 tapered chunks).  Upload (320 MB) and
+    // download (160 MB) share the link: the call runs at ~70 GB/s of combined PCIe traffic whatever the schedule.
     for (size_t c = 0; c < chunks; ++c) {
         const size_t b = n * c / chunks, e = n * (c + 1) / chunks;
         cudaEvent_t in_done = h->events[1 + 2 * c], tr_done = h->events[2 + 2 * c];
@@ -680,6 +684,7 @@ BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete p
         auto h = H(T, bvh);                                                                                        \
         if (!h) { set_error("null handle"); return -1; }                                                           \
         if (!gathered_hits || world_size < 1 || world_size > 8) { set_error("gather: need 1..8 gathered arrays"); return -1; } \
+        std::lock_guard<std::mutex> lock(h->batch_mutex);                                                          \
         BVH_CUDA_TRY(cudaSetDevice(h->device));                                                                    \
         if (ensure_device(*h)) return -1;                                                                          \
         GatherTargets g;                                                                                           \

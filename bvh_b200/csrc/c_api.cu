@@ -83,6 +83,7 @@ template <typename T> struct Handle {
     // Batched calls on one handle share its stream, staging buffers and the kernels' cursor/status words:
     // concurrent callers are serialised (the reference's per-ray calls are const and run on the host mirror).
     std::mutex batch_mutex;
+    std::mutex mirror_mutex;                      // the lazy download of the mirror (first legacy call) happens once
 };
 
 template <typename T> int init_handle(Handle<T>& h) {
@@ -133,6 +134,7 @@ template <typename T> uint64_t mirror_hash(const Handle<T>& h) {
 // depth-first order: root at 0, children of a node adjacent, left child at an odd index (bvh.h:34-54).
 template <typename T> int download_mirror(Handle<T>& h) {
     using U = typename Real<T>::UInt;
+    std::lock_guard<std::mutex> lock(h.mirror_mutex);       // concurrent bvhNN_intersect_ray* callers (bvh_impl.h:244)
     if (h.host_valid) return 0;
     if (!h.device_valid) { set_error("handle holds no BVH"); return -1; }
     BVH_CUDA_TRY(cudaSetDevice(h.device));

@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--mesh", default="soup", choices=["soup", "grid"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sah-treelets", action="store_true",
+                    help="EXPERIMENTAL: build with the SAH treelet pass (treelet_sah.cuh; not the default, not yet validated on hardware)")
     ap.add_argument("--kernel", default="persistent", choices=["persistent", "simple"])
     ap.add_argument("--chunks", type=int, default=4, help="NCCL gather chunks per step when N > 1")
     ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "peer", "nccl"],
@@ -189,6 +191,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     kind = args.mesh
+    if args.sah_treelets:
+        os.environ["BVH_B200_SAH_TREELETS"] = "1"
     workload = f"{kind}-1M triangles, {IMG}x{IMG} = {IMG * IMG} coherent primary rays per GPU, closest-hit"
 
     if args.impl == "reference":
@@ -380,7 +384,8 @@ def main():
             "metric": "primary closest-hit rays per second", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "bvh": "LBVH (30-bit Morton, SAH leaf collapse, max_leaf_size 8) built on the GPU, replicated per rank",
+            "config": {"workload": workload, "bvh": "LBVH (30-bit Morton, SAH leaf collapse, max_leaf_size 8)" + (" + experimental SAH treelet pass" if args.sah_treelets else "")
+                              + " built on the GPU, replicated per rank",
                        "kernel": args.kernel, "tie_break": "lowest original id (canonical)",
                        "l2": "inputs larger than L2: 320 MB of rays + 160 MB of hits streamed per step, no flush needed",
                        "hit_fraction": hit_frac, "inner_steps_per_ray": s_inner, "leaves_per_ray": s_leaves, "tri_tests_per_ray": s_tri,

@@ -96,17 +96,27 @@ struct BlockExec {
 #endif
 
 // ---- scratch of one treelet (shared memory on the device) ------------------------------------------
+// Segmented scans are BLOCKED: a chunk of kTreeletChunk consecutive positions is scanned sequentially by one
+// iteration, the chunk aggregates by a short data-parallel scan, and the carry is applied per position —
+// O(n) work per scan instead of the O(n log n) of a flat data-parallel scan.
+constexpr int kTreeletChunk = 8;
+
 template <typename T, int S> struct TreeletScratch {
+    static constexpr int NC = S / kTreeletChunk;
     T box[6][S];                         // per PRIMITIVE (local index): minx,maxx,miny,maxy,minz,maxz
     T centre[3][S];
     uint32_t old_ids[S];                 // prim_ids[l + i] before the rebuild
     uint16_t order[3][S];                // local primitive indices sorted along each axis, segment by segment
     uint16_t tmp16[S];
     uint16_t seg_begin[S], seg_end[S];   // per POSITION: its segment; seg_end == 0: the segment became a leaf
-    T scan[2][6][S];                     // ping-pong buffers of the segmented box scans
-    T right_cost[S], right_area[S];      // cost / half-area of [pos, end) on the current axis
-    T cand_cost[2][S];                   // ping-pong buffers of the segmented min-scan ...
-    uint16_t cand_pos[2][S];             // ... and of the segmented flag sums
+    T pre[6][S], suf[6][S];              // boxes of [segment begin, pos] and of [pos, segment end) on the current axis
+    T right_cost[S];                     // cost of [pos, segment end) as a leaf
+    T cand_cost[S];                      // cost of splitting after pos, then its running first minimum
+    uint16_t cand_pos[S];                // ... the position that goes with it; later the running sums of the side flags
+    // chunk aggregates (ping-pong) of the blocked scans
+    T cpre[2][6][NC], csuf[2][6][NC], ccost[2][NC];
+    uint16_t cpos[2][NC];
+    uint8_t cfl[2][NC], cbl[2][NC];      // the chunk contains a forward / backward reset
     // per SEGMENT, stored at the position of its head (= seg_begin)
     T nbox[6][S];
     T leaf_cost[S], best_cost[S], best_larea[S], best_rarea[S];
@@ -116,11 +126,13 @@ template <typename T, int S> struct TreeletScratch {
     uint8_t side[S];                     // per PRIMITIVE: 1 = goes to the left part
     uint32_t counters[4];                // [0] next pair, [1] live segments, [2] treelet depth, [3] longest live segment
 };
+static_assert(sizeof(TreeletScratch<float, TreeletCfg<float>::kMaxPrims>) <= 48 * 1024, "static shared memory");
+static_assert(sizeof(TreeletScratch<double, TreeletCfg<double>::kMaxPrims>) <= 48 * 1024, "static shared memory");
 
 template <typename T> BVH_HD T treelet_inf() { return Real<T>::from_bits(sizeof(T) == 4 ? (typename Real<T>::UInt)0x7F800000u : (typename Real<T>::UInt)0x7FF0000000000000ull); }
 
-template <typename T, int S> BVH_HD T treelet_half_area(const T (&b)[2][6][S], int buf, uint32_t pos) {
-    const T mn[3] = { b[buf][0][pos], b[buf][2][pos], b[buf][4][pos] }, mx[3] = { b[buf][1][pos], b[buf][3][pos], b[buf][5][pos] };
+template <typename T, int S> BVH_HD T treelet_half_area(const T (&b)[6][S], uint32_t pos) {
+    const T mn[3] = { b[0][pos], b[2][pos], b[4][pos] }, mx[3] = { b[1][pos], b[3][pos], b[5][pos] };
     return half_area(mn, mx);
 }
 
@@ -135,10 +147,17 @@ BVH_HD void treelet_rebuild(TreeletScratch<T, S>& w, const Treelet& t, DevNode<T
                             uint32_t min_leaf, uint32_t max_leaf, uint32_t* __restrict__ info, uint32_t lbvh_depth) {
     using R = Real<T>;
     using U = typename R::UInt;
+    constexpr uint32_t C = kTreeletChunk;
     const uint32_t n = t.r - t.l + 1, l = t.l;
+    const uint32_t nc = (n + C - 1) / C;                     // chunks in use
     const T inf = treelet_inf<T>();
     // depth of the subtree being replaced (its root record still carries it; the tree's root record does not)
     const uint32_t old_depth = t.slot == 1 ? lbvh_depth : AuxPack<T>::depth(nodes[t.slot].pad);
+
+    // a scan running forward restarts at a segment head, one running backward at a segment's last position;
+    // positions of finished segments always restart
+    auto fwd_reset = [&] (uint32_t p) { return w.seg_end[p] == 0 || w.seg_begin[p] == p; };
+    auto bwd_reset = [&] (uint32_t p) { return w.seg_end[p] == 0 || p + 1 == w.seg_end[p]; };
 
     // ---- load the primitives ----
     Exec::phase(n, [&] (uint32_t i) {
@@ -176,86 +195,133 @@ BVH_HD void treelet_rebuild(TreeletScratch<T, S>& w, const Treelet& t, DevNode<T
 
     // ---- level by level ----
     while (w.counters[1] != 0) {
-        const uint32_t longest = w.counters[3];
+        const uint32_t reach = (w.counters[3] + C - 1) / C;   // a segment's head chunk is at most this many chunks before its last chunk
         for (int a = 0; a < 3; ++a) {
-            // suffix boxes: scan[cur][.][pos] = union of the boxes at positions [pos, segment end)
-            int cur = 0;
+            // ---- prefix boxes (pre) and suffix boxes (suf) of every live segment along axis a ----
             Exec::phase(n, [&] (uint32_t pos) {
                 const uint32_t prim = w.order[a][pos];
-                for (int c = 0; c < 6; ++c) w.scan[0][c][pos] = w.box[c][prim];
+                for (int c = 0; c < 6; ++c) { const T v = w.box[c][prim]; w.pre[c][pos] = v; w.suf[c][pos] = v; }
             });
-            for (uint32_t d = 1; d < longest; d <<= 1) {
-                Exec::phase(n, [&] (uint32_t pos) {
-                    const uint32_t se = w.seg_end[pos];
-                    const bool take = se != 0 && pos + d < se;
-                    for (int c = 0; c < 6; c += 2) {
-                        const T mn = w.scan[cur][c][pos], mx = w.scan[cur][c + 1][pos];
-                        w.scan[cur ^ 1][c][pos]     = take ? robust_min(mn, w.scan[cur][c][pos + d]) : mn;
-                        w.scan[cur ^ 1][c + 1][pos] = take ? robust_max(mx, w.scan[cur][c + 1][pos + d]) : mx;
+            Exec::phase(2 * nc, [&] (uint32_t x) {                                       // inside each chunk, sequentially
+                const uint32_t c = x < nc ? x : x - nc, first = c * C, last = (first + C < n ? first + C : n) - 1;
+                bool flag = false;
+                if (x < nc) {
+                    for (uint32_t p = first; p <= last; ++p) {
+                        const bool reset = fwd_reset(p);
+                        flag = flag || reset;
+                        if (p > first && !reset)
+                            for (int k = 0; k < 6; k += 2) {
+                                w.pre[k][p] = robust_min(w.pre[k][p], w.pre[k][p - 1]);
+                                w.pre[k + 1][p] = robust_max(w.pre[k + 1][p], w.pre[k + 1][p - 1]);
+                            }
+                    }
+                    for (int k = 0; k < 6; ++k) w.cpre[0][k][c] = w.pre[k][last];
+                    w.cfl[0][c] = flag;
+                } else {
+                    for (uint32_t p = last + 1; p-- > first;) {
+                        const bool reset = bwd_reset(p);
+                        flag = flag || reset;
+                        if (p < last && !reset)
+                            for (int k = 0; k < 6; k += 2) {
+                                w.suf[k][p] = robust_min(w.suf[k][p], w.suf[k][p + 1]);
+                                w.suf[k + 1][p] = robust_max(w.suf[k + 1][p], w.suf[k + 1][p + 1]);
+                            }
+                    }
+                    for (int k = 0; k < 6; ++k) w.csuf[0][k][c] = w.suf[k][first];
+                    w.cbl[0][c] = flag;
+                }
+            });
+            int cur = 0;
+            for (uint32_t d = 1; d <= reach && d < nc; d <<= 1) {                        // across the chunks, data-parallel
+                Exec::phase(2 * nc, [&] (uint32_t x) {
+                    if (x < nc) {
+                        const uint32_t c = x;
+                        const bool take = c >= d && !w.cfl[cur][c];
+                        for (int k = 0; k < 6; k += 2) {
+                            const T mn = w.cpre[cur][k][c], mx = w.cpre[cur][k + 1][c];
+                            w.cpre[cur ^ 1][k][c]     = take ? robust_min(mn, w.cpre[cur][k][c - d]) : mn;
+                            w.cpre[cur ^ 1][k + 1][c] = take ? robust_max(mx, w.cpre[cur][k + 1][c - d]) : mx;
+                        }
+                        w.cfl[cur ^ 1][c] = take ? w.cfl[cur][c - d] : w.cfl[cur][c];
+                    } else {
+                        const uint32_t c = x - nc;
+                        const bool take = c + d < nc && !w.cbl[cur][c];
+                        for (int k = 0; k < 6; k += 2) {
+                            const T mn = w.csuf[cur][k][c], mx = w.csuf[cur][k + 1][c];
+                            w.csuf[cur ^ 1][k][c]     = take ? robust_min(mn, w.csuf[cur][k][c + d]) : mn;
+                            w.csuf[cur ^ 1][k + 1][c] = take ? robust_max(mx, w.csuf[cur][k + 1][c + d]) : mx;
+                        }
+                        w.cbl[cur ^ 1][c] = take ? w.cbl[cur][c + d] : w.cbl[cur][c];
                     }
                 });
                 cur ^= 1;
             }
-            Exec::phase(n, [&] (uint32_t pos) {
+            Exec::phase(n, [&] (uint32_t pos) {                                          // carries in; leaf costs; the node's box at the head
                 const uint32_t se = w.seg_end[pos];
                 if (se == 0) return;
-                const T area = treelet_half_area(w.scan, cur, pos);
-                w.right_area[pos] = area;
-                w.right_cost[pos] = R::mul(area, (T)(se - pos));                       // get_leaf_cost, split_heuristic.h:30-33
-                if (a == 0 && w.seg_begin[pos] == pos) {                                // the head: this is the node's box
-                    for (int c = 0; c < 6; ++c) w.nbox[c][pos] = w.scan[cur][c][pos];
-                    const T lc = R::mul(area, (T)(se - pos - 1));                       // get_non_split_cost, :35-38 (cost_ratio 1)
+                const uint32_t c = pos / C, sb = w.seg_begin[pos];
+                if (c > 0 && sb < c * C)
+                    for (int k = 0; k < 6; k += 2) {
+                        w.pre[k][pos] = robust_min(w.pre[k][pos], w.cpre[cur][k][c - 1]);
+                        w.pre[k + 1][pos] = robust_max(w.pre[k + 1][pos], w.cpre[cur][k + 1][c - 1]);
+                    }
+                if (c + 1 < nc && se > (c + 1) * C)
+                    for (int k = 0; k < 6; k += 2) {
+                        w.suf[k][pos] = robust_min(w.suf[k][pos], w.csuf[cur][k][c + 1]);
+                        w.suf[k + 1][pos] = robust_max(w.suf[k + 1][pos], w.csuf[cur][k + 1][c + 1]);
+                    }
+                const T area = treelet_half_area(w.suf, pos);
+                w.right_cost[pos] = R::mul(area, (T)(se - pos));                         // get_leaf_cost, split_heuristic.h:30-33
+                if (a == 0 && sb == pos) {                                               // the head: suf is the node's box
+                    for (int k = 0; k < 6; ++k) w.nbox[k][pos] = w.suf[k][pos];
+                    const T lc = R::mul(area, (T)(se - pos - 1));                        // get_non_split_cost, :35-38 (cost_ratio 1)
                     w.leaf_cost[pos] = lc; w.best_cost[pos] = lc;
-                    w.best_pos[pos] = (uint16_t)((pos + se + 1) / 2); w.best_axis[pos] = 0;     // sweep_sah_builder.h:111
+                    w.best_pos[pos] = (uint16_t)((pos + se + 1) / 2); w.best_axis[pos] = 0;      // sweep_sah_builder.h:111
                     w.best_larea[pos] = (T)0; w.best_rarea[pos] = (T)0;
                 }
             });
-            // prefix boxes: scan[cur][.][pos] = union of the boxes at positions [segment begin, pos]
-            cur = 0;
+            // ---- cost of splitting after pos (left = [begin, pos], right = [pos + 1, end)); first minimum per segment ----
             Exec::phase(n, [&] (uint32_t pos) {
-                const uint32_t prim = w.order[a][pos];
-                for (int c = 0; c < 6; ++c) w.scan[0][c][pos] = w.box[c][prim];
+                const uint32_t se = w.seg_end[pos];
+                T cost = inf;
+                if (se != 0 && pos + 1 < se)
+                    cost = R::add(R::mul(treelet_half_area(w.pre, pos), (T)(pos + 1 - w.seg_begin[pos])), w.right_cost[pos + 1]);
+                w.cand_cost[pos] = cost; w.cand_pos[pos] = (uint16_t)(pos + 1);
             });
-            for (uint32_t d = 1; d < longest; d <<= 1) {
-                Exec::phase(n, [&] (uint32_t pos) {
-                    const bool take = w.seg_end[pos] != 0 && pos >= w.seg_begin[pos] + d;
-                    for (int c = 0; c < 6; c += 2) {
-                        const T mn = w.scan[cur][c][pos], mx = w.scan[cur][c + 1][pos];
-                        w.scan[cur ^ 1][c][pos]     = take ? robust_min(mn, w.scan[cur][c][pos - d]) : mn;
-                        w.scan[cur ^ 1][c + 1][pos] = take ? robust_max(mx, w.scan[cur][c + 1][pos - d]) : mx;
+            Exec::phase(nc, [&] (uint32_t c) {
+                const uint32_t first = c * C, last = (first + C < n ? first + C : n) - 1;
+                bool flag = false;
+                for (uint32_t p = first; p <= last; ++p) {
+                    const bool reset = fwd_reset(p);
+                    flag = flag || reset;
+                    if (p > first && !reset && w.cand_cost[p - 1] <= w.cand_cost[p]) {    // ties: the earlier position (strict < in the reference's sweep)
+                        w.cand_cost[p] = w.cand_cost[p - 1]; w.cand_pos[p] = w.cand_pos[p - 1];
                     }
+                }
+                w.ccost[0][c] = w.cand_cost[last]; w.cpos[0][c] = w.cand_pos[last]; w.cfl[0][c] = flag;
+            });
+            cur = 0;
+            for (uint32_t d = 1; d <= reach && d < nc; d <<= 1) {
+                Exec::phase(nc, [&] (uint32_t c) {
+                    T cost = w.ccost[cur][c]; uint16_t k = w.cpos[cur][c]; uint8_t flag = w.cfl[cur][c];
+                    if (c >= d && !flag) {
+                        if (w.ccost[cur][c - d] <= cost) { cost = w.ccost[cur][c - d]; k = w.cpos[cur][c - d]; }
+                        flag = w.cfl[cur][c - d];
+                    }
+                    w.ccost[cur ^ 1][c] = cost; w.cpos[cur ^ 1][c] = k; w.cfl[cur ^ 1][c] = flag;
                 });
                 cur ^= 1;
             }
-            // cost of splitting after position pos (left = [begin, pos], right = [pos + 1, end)); first minimum per segment
-            int cc = 0;
-            Exec::phase(n, [&] (uint32_t pos) {
-                const uint32_t se = w.seg_end[pos], sb = w.seg_begin[pos];
-                T cost = inf;
-                if (se != 0 && pos + 1 < se)
-                    cost = R::add(R::mul(treelet_half_area(w.scan, cur, pos), (T)(pos + 1 - sb)), w.right_cost[pos + 1]);
-                w.cand_cost[0][pos] = cost; w.cand_pos[0][pos] = (uint16_t)(pos + 1);
-            });
-            for (uint32_t d = 1; d < longest; d <<= 1) {
-                Exec::phase(n, [&] (uint32_t pos) {
-                    T c = w.cand_cost[cc][pos]; uint16_t k = w.cand_pos[cc][pos];
-                    if (w.seg_end[pos] != 0 && pos >= w.seg_begin[pos] + d) {
-                        const T cl = w.cand_cost[cc][pos - d];
-                        if (cl <= c) { c = cl; k = w.cand_pos[cc][pos - d]; }            // ties: the earlier position (strict < in the reference's sweep)
-                    }
-                    w.cand_cost[cc ^ 1][pos] = c; w.cand_pos[cc ^ 1][pos] = k;
-                });
-                cc ^= 1;
-            }
-            Exec::phase(n, [&] (uint32_t pos) {                                         // heads: keep the best axis (first one on ties)
+            Exec::phase(n, [&] (uint32_t pos) {                                          // heads: keep the best axis (first one on ties)
                 const uint32_t se = w.seg_end[pos];
                 if (se == 0 || w.seg_begin[pos] != pos || se - pos < 2) return;
-                const T c = w.cand_cost[cc][se - 1];
-                if (c < w.best_cost[pos]) {
-                    const uint32_t k = w.cand_pos[cc][se - 1];
-                    w.best_cost[pos] = c; w.best_pos[pos] = (uint16_t)k; w.best_axis[pos] = (uint8_t)a;
-                    w.best_larea[pos] = treelet_half_area(w.scan, cur, k - 1);
-                    w.best_rarea[pos] = w.right_area[k];
+                const uint32_t last = se - 1, c = last / C;
+                T cost = w.cand_cost[last]; uint32_t k = w.cand_pos[last];
+                if (c > 0 && pos < c * C && w.ccost[cur][c - 1] <= cost) { cost = w.ccost[cur][c - 1]; k = w.cpos[cur][c - 1]; }
+                if (cost < w.best_cost[pos]) {
+                    w.best_cost[pos] = cost; w.best_pos[pos] = (uint16_t)k; w.best_axis[pos] = (uint8_t)a;
+                    w.best_larea[pos] = treelet_half_area(w.pre, k - 1);
+                    w.best_rarea[pos] = treelet_half_area(w.suf, k);
                 }
             });
         }
@@ -302,30 +368,40 @@ BVH_HD void treelet_rebuild(TreeletScratch<T, S>& w, const Treelet& t, DevNode<T
             if (w.split[h]) w.side[w.order[w.best_axis[h]][pos]] = pos < w.best_pos[h] ? 1 : 0;
         });
         for (int b = 0; b < 3; ++b) {
-            int cc = 0;
-            Exec::phase(n, [&] (uint32_t pos) {
-                const uint32_t se = w.seg_end[pos];
-                uint16_t f = 0;
-                if (se != 0) { const uint32_t h = w.seg_begin[pos]; if (w.split[h] && w.best_axis[h] != b) f = w.side[w.order[b][pos]]; }
-                w.cand_pos[0][pos] = f;
+            auto moves = [&] (uint32_t pos) {                                            // does position pos of order b get partitioned?
+                if (w.seg_end[pos] == 0) return false;
+                const uint32_t h = w.seg_begin[pos];
+                return w.split[h] != 0 && w.best_axis[h] != b;
+            };
+            Exec::phase(nc, [&] (uint32_t c) {                                           // running count of left-goers inside each chunk
+                const uint32_t first = c * C, last = (first + C < n ? first + C : n) - 1;
+                bool flag = false;
+                for (uint32_t p = first; p <= last; ++p) {
+                    const bool reset = fwd_reset(p);
+                    flag = flag || reset;
+                    uint16_t v = moves(p) ? w.side[w.order[b][p]] : (uint16_t)0;
+                    if (p > first && !reset) v = (uint16_t)(v + w.cand_pos[p - 1]);
+                    w.cand_pos[p] = v;
+                }
+                w.cpos[0][c] = w.cand_pos[last]; w.cfl[0][c] = flag;
             });
-            for (uint32_t d = 1; d < longest; d <<= 1) {
-                Exec::phase(n, [&] (uint32_t pos) {
-                    uint16_t v = w.cand_pos[cc][pos];
-                    if (w.seg_end[pos] != 0 && pos >= w.seg_begin[pos] + d) v = (uint16_t)(v + w.cand_pos[cc][pos - d]);
-                    w.cand_pos[cc ^ 1][pos] = v;
+            int cur = 0;
+            for (uint32_t d = 1; d <= reach && d < nc; d <<= 1) {
+                Exec::phase(nc, [&] (uint32_t c) {
+                    uint16_t v = w.cpos[cur][c]; uint8_t flag = w.cfl[cur][c];
+                    if (c >= d && !flag) { v = (uint16_t)(v + w.cpos[cur][c - d]); flag = w.cfl[cur][c - d]; }
+                    w.cpos[cur ^ 1][c] = v; w.cfl[cur ^ 1][c] = flag;
                 });
-                cc ^= 1;
+                cur ^= 1;
             }
             Exec::phase(n, [&] (uint32_t pos) {
-                const uint32_t se = w.seg_end[pos];
                 uint32_t dst = pos;
-                if (se != 0) {
-                    const uint32_t h = w.seg_begin[pos];
-                    if (w.split[h] && w.best_axis[h] != b) {
-                        const uint32_t f = w.side[w.order[b][pos]], before = w.cand_pos[cc][pos] - f, k = w.best_pos[h];
-                        dst = f ? h + before : k + (pos - h - before);
-                    }
+                if (moves(pos)) {
+                    const uint32_t h = w.seg_begin[pos], c = pos / C, k = w.best_pos[h];
+                    const uint32_t f = w.side[w.order[b][pos]];
+                    const uint32_t incl = w.cand_pos[pos] + (c > 0 && h < c * C ? w.cpos[cur][c - 1] : 0u);
+                    const uint32_t before = incl - f;
+                    dst = f ? h + before : k + (pos - h - before);
                 }
                 w.tmp16[dst] = w.order[b][pos];
             });

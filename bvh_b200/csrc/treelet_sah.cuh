@@ -129,6 +129,14 @@ template <typename T, int S> struct TreeletScratch {
 static_assert(sizeof(TreeletScratch<float, TreeletCfg<float>::kMaxPrims>) <= 48 * 1024, "static shared memory");
 static_assert(sizeof(TreeletScratch<double, TreeletCfg<double>::kMaxPrims>) <= 48 * 1024, "static shared memory");
 
+// Monotone map of a scalar to an unsigned integer (negative values reversed below the positive ones): a total
+// order even when a centre is a NaN, so the rank sort below always yields a permutation.
+template <typename T> BVH_HD typename Real<T>::UInt treelet_sort_key(T x) {
+    using U = typename Real<T>::UInt;
+    const U bits = Real<T>::bits(x), sign = (U)1 << (8 * sizeof(U) - 1);
+    return (bits & sign) ? (U)~bits : (U)(bits | sign);
+}
+
 template <typename T> BVH_HD T treelet_inf() { return Real<T>::from_bits(sizeof(T) == 4 ? (typename Real<T>::UInt)0x7F800000u : (typename Real<T>::UInt)0x7FF0000000000000ull); }
 
 template <typename T, int S> BVH_HD T treelet_half_area(const T (&b)[6][S], uint32_t pos) {
@@ -184,13 +192,13 @@ BVH_HD void treelet_rebuild(TreeletScratch<T, S>& w, const Treelet& t, DevNode<T
     // ---- sort once along each axis: rank of a primitive = number of primitives before it in (centre, index) order
     Exec::phase(3 * n, [&] (uint32_t x) {
         const uint32_t a = x / n, i = x - a * n;
-        const T ci = w.centre[a][i];
+        const U ki = treelet_sort_key(w.centre[a][i]);
         uint32_t rank = 0;
         for (uint32_t j = 0; j < n; ++j) {
-            const T cj = w.centre[a][j];
-            rank += (cj < ci || (cj == ci && j < i)) ? 1u : 0u;
+            const U kj = treelet_sort_key(w.centre[a][j]);
+            rank += (kj < ki || (kj == ki && j < i)) ? 1u : 0u;
         }
-        w.order[a][rank] = (uint16_t)i;        // a NaN centre gives colliding ranks: such input is undefined in the reference too
+        w.order[a][rank] = (uint16_t)i;
     });
 
     // ---- level by level ----

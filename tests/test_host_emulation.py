@@ -350,3 +350,20 @@ def test_fuzz_emulation_against_the_oracle(emul, oracle, seed):
     robust = [f for _, f in MODES if f & ROBUST and not f & ANY_HIT and f & TIE_LOWEST_ID]
     if robust:
         assert_hits_equal(emul.trace(tree, rays, robust[0])[:4], oracle.brute_force(tris, rays, flags=robust[0] & ~ROBUST), f"seed {seed} brute force")
+
+
+def test_sah_treelet_pass_survives_nan_and_inf_vertices(emul):
+    """NaN / infinite vertices (undefined in the reference) must not break the pass: the result is still a
+    permutation of the primitives, and rays get the same answers as from the plain LBVH."""
+    tris = scenes.soup(1500, seed=21)
+    tris[7, 4] = np.nan; tris[400, 0] = np.inf; tris[401, 8] = -np.inf; tris[900, :] = np.nan
+    rays = scenes.make_primary("soup", 64, 64)
+    plain = emul.build(tris=tris)
+    try:
+        emul.set_treelets(True)
+        tree = emul.build(tris=tris)
+    finally:
+        emul.set_treelets(False)
+    assert np.array_equal(np.sort(tree["prim_ids"]), np.arange(tris.shape[0]))
+    a, b = emul.trace(plain, rays, TIE_LOWEST_ID), emul.trace(tree, rays, TIE_LOWEST_ID)
+    assert_hits_equal(b[:4], a[:4], "treelets with NaN / inf vertices")

@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """bench.py — the hot path of BASELINE.json measured on B200(s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mesh soup|grid]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c2|c3|c4|c5] [--mesh soup|grid]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step is one pass of the batched closest-hit traversal over 10M coherent primary rays (3163 x 3163
-pinhole camera, reference test/benchmark.cpp:340-358) against a 1M-triangle synthetic mesh
-(BASELINE.json configs[1]); with N GPUs every rank traces its own 10M-ray shard of an N x 10M batch
-(BVH replicated, weak scaling) and the 16-byte hit records are all-gathered over NCCL chunk by chunk,
-overlapped with the traversal.  `value` is whole-job Mrays/s with rays resident in HBM; `build` reports
-the LBVH build rate of the same mesh (Mtris/s) timed in the same run; `e2e` is the same metric through
-the C ABI with pinned HOST buffers (H2D of the rays and D2H of the hits inside the timed region).
+Default (`--config c2`, BASELINE.json configs[1]): a step is one pass of the batched closest-hit traversal
+over 10M coherent primary rays (3163 x 3163 pinhole camera, reference test/benchmark.cpp:340-358) against a
+1M-triangle synthetic mesh; with N GPUs every rank traces its own 10M-ray shard of an N x 10M batch (BVH
+replicated, weak scaling) and the 16-byte hit records are gathered on every rank inside the traversal kernel
+(peer stores over NVLink) or by NCCL.  `value` is whole-job Mrays/s with rays resident in HBM; `build` reports
+the LBVH build rate of the same mesh (Mtris/s) timed in the same run; `e2e` is the same metric through the
+C ABI with pinned HOST buffers (H2D of the rays and D2H of the hits inside the timed region).
 
-`--impl reference` times the reference's own CPU implementation (oracle/_ref = the unmodified
-reference compiled in place; the plain-C oracle port when that is absent) on a bounded sample of the
-same workload with every host thread, and prints the same JSON line with "impl": "reference".
+Other BASELINE configs (same JSON shape): c3 = 10M incoherent AO-style rays, any-hit; c4 = 10M triangles,
+100M primary rays sharded over the ranks (strong scaling, 63-bit Morton keys); c5 = double precision,
+100K triangles, 1M rays.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref = the unmodified reference
+compiled in place; the plain-C oracle port when that is absent) on the SAME rays with every usable host
+thread, and prints the same JSON line with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -33,10 +37,20 @@ sys.path.insert(0, ROOT)
 
 from bvh_b200 import scenes  # noqa: E402
 
-TRIS = 1_000_000
-IMG = 3163                       # 3163^2 = 10 004 569 rays
-CPU_SAMPLE_ROWS = 320            # ~1M rays for the CPU arm (a band of image rows through the centre)
 FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
+
+# BASELINE.json configs[1..4].  img: the camera is img x img primary rays; count: incoherent rays.
+CONFIGS = {
+    "c2": dict(tris=1_000_000, img=3163, dtype="f32", any_hit=False, scaling="weak",
+               metric="primary closest-hit rays per second"),
+    "c3": dict(tris=1_000_000, count=10_000_000, dtype="f32", any_hit=True, scaling="weak",
+               metric="incoherent any-hit (AO) rays per second"),
+    "c4": dict(tris=10_000_000, img=10_000, dtype="f32", any_hit=False, scaling="strong",
+               metric="primary closest-hit rays per second"),
+    "c5": dict(tris=100_000, img=1000, dtype="f64", any_hit=False, scaling="weak",
+               metric="primary closest-hit rays per second"),
+}
+C4_CPU_ROW_STRIDE = 10           # the CPU arm of c4 traces every 10th image row (10M of the 100M rays)
 
 
 def parse_args():
@@ -45,15 +59,18 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--mesh", default="soup", choices=["soup", "grid"])
+    ap.add_argument("--quality", default=None, choices=["low", "medium", "high"],
+                    help="DefaultBuilder::Quality passed to the build (default: the library default, High)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--sah-treelets", action="store_true",
-                    help="EXPERIMENTAL: build with the SAH treelet pass (treelet_sah.cuh; not the default, not yet validated on hardware)")
-    ap.add_argument("--kernel", default="persistent", choices=["persistent", "simple"])
-    ap.add_argument("--chunks", type=int, default=4, help="NCCL gather chunks per step when N > 1")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "persistent", "wide", "simple"],
+                    help="auto: the library's default choice for the flags of the config")
+    ap.add_argument("--chunks", type=int, default=4, help="NCCL gather chunks per step when N > 1 and --gather nccl")
     ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "peer", "nccl"],
                     help="N > 1: fused peer-memory gather (multicast / peer stores) or NCCL all-gather")
+    ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind the rank to its GPU's NUMA node")
     return ap.parse_args()
 
 
@@ -63,6 +80,59 @@ def hbm_peak():
         return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def usable_cpus():
+    """CPUs this process may actually use: the affinity mask, capped by the cgroup CPU quota (a pool of
+    hardware_concurrency threads on a host whose cgroup grants fewer CPUs oversubscribes and thrashes)."""
+    try:
+        affinity = len(os.sched_getaffinity(0))
+    except Exception:
+        affinity = os.cpu_count() or 1
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    usable = affinity if quota is None else max(1, min(affinity, int(quota)))
+    return {"usable": usable, "affinity": affinity, "cgroup_quota": quota, "hardware": os.cpu_count()}
+
+
+def bind_to_gpu_numa_node(local_rank: int):
+    """Multi-rank runs: pin this rank (and therefore the first-touch placement of its pinned host buffers)
+    to the NUMA node its GPU hangs off.  Eight ranks streaming 70 GB/s each through whatever socket the
+    scheduler put them on is what collapsed the 8-GPU e2e number in round 1."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        sysfs = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+        node = int(open(sysfs).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {exc}"}
 
 
 class ClockSampler(threading.Thread):
@@ -124,43 +194,86 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
-def camera_rays(kind, rank=0, world=1, rows=None):
-    """This rank's shard: the same 3163^2 camera with a sub-pixel offset of rank/world, so that the
-    global batch is world x 10M distinct primary rays of one distribution."""
-    kw = dict(pixel_offset=rank / world)
-    if rows is not None:
-        kw.update(y_begin=rows[0], y_end=rows[1])
-    return scenes.make_primary(kind, IMG, IMG, **kw)
+# ------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------
+def np_dtype(cfg):
+    return np.float32 if cfg["dtype"] == "f32" else np.float64
+
+
+def make_tris(cfg, kind):
+    return scenes.make_mesh(kind, cfg["tris"], dtype=np_dtype(cfg))
+
+
+def make_rays(cfg, kind, tris, rank=0, world=1, row_stride=1):
+    """This rank's rays.  weak scaling: the full batch of the config, made distinct per rank (sub-pixel camera
+    offset rank/world; another seed for the incoherent rays) so that the global batch is world x the config's
+    rays of one distribution.  strong scaling (c4): this rank's band of image rows."""
+    dt = np_dtype(cfg)
+    if "count" in cfg:
+        return scenes.incoherent_rays(tris, cfg["count"], seed=12345 + rank)
+    img = cfg["img"]
+    if cfg["scaling"] == "strong":
+        assert img % world == 0, "the c4 camera has 10000 rows: use 1, 2, 4, 5, 8 or 10 ranks"
+        y0, y1 = rank * img // world, (rank + 1) * img // world
+        rays = scenes.make_primary(kind, img, img, dtype=dt, y_begin=y0, y_end=y1)
+    else:
+        rays = scenes.make_primary(kind, img, img, dtype=dt, pixel_offset=rank / world)
+    if row_stride > 1:
+        rays = np.ascontiguousarray(rays.reshape(-1, img, 8)[::row_stride].reshape(-1, 8))
+    return rays
+
+
+def workload_text(cfg, kind, name):
+    rays = (f"{cfg['count']} incoherent AO-style rays (tmax 0.25), any-hit" if "count" in cfg else
+            f"{cfg['img']}x{cfg['img']} = {cfg['img'] ** 2} coherent primary rays, closest-hit")
+    per = "sharded over the ranks" if cfg["scaling"] == "strong" else "per GPU"
+    return f"{name}: {kind}-{cfg['tris']} triangles, {rays} {per}, {cfg['dtype']}"
+
+
+def bytes_per_ray(cfg, s_inner, s_tri):
+    """ray in + hit out + 2 packed nodes per inner step + one PrecomputedTri per test."""
+    if cfg["dtype"] == "f64":
+        return 64 + 32 + 128 * s_inner + 96 * s_tri
+    return 32 + (4 if cfg["any_hit"] else 16) + 64 * s_inner + 48 * s_tri
 
 
 # ------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU path on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_arm(kind, steps, warmup, quick=False):
-    """Times DefaultBuilder (Quality::High, the library default) and Bvh::intersect over a bounded sample
-    with all host threads.  Only this function (and tests/, smoke()) touches oracle/."""
-    from oracle.pyoracle import TIE_LOWEST_ID, Oracle, Ref, ref_available
-    tris = scenes.make_mesh(kind, TRIS)
-    r0 = (IMG - CPU_SAMPLE_ROWS) // 2
-    rays = camera_rays(kind, rows=(r0, r0 + CPU_SAMPLE_ROWS))
-    sample = f"{rays.shape[0]} rays = image rows {r0}..{r0 + CPU_SAMPLE_ROWS} of the {IMG}x{IMG} camera, {tris.shape[0]} triangles"
+def cpu_arm(cfg, kind, name, steps, warmup):
+    """Times DefaultBuilder (Quality::High, the library default) and Bvh::intersect with every usable host
+    thread on the rays of rank 0 (c4: every 10th image row).  Per-step times -> MEDIAN.  Only this function
+    (and tests/, smoke()) touches oracle/."""
+    from oracle.pyoracle import ANY_HIT, TIE_LOWEST_ID, Oracle, Ref, ref_available
+    DYNAMIC = 1 << 8             # ref_driver.cpp kDynamic: workers claim 4096-ray blocks (no static n/threads split)
+    tris = make_tris(cfg, kind)
+    stride = C4_CPU_ROW_STRIDE if name == "c4" else 1
+    rays = make_rays(cfg, kind, tris, row_stride=stride)
+    flags = TIE_LOWEST_ID | (ANY_HIT if cfg["any_hit"] else 0)
+    cpus = usable_cpus()
+    what = "all rays of one rank's batch" if stride == 1 else f"every {stride}th row of the {cfg['img']}x{cfg['img']} camera"
+    sample = f"{rays.shape[0]} rays ({what}), {tris.shape[0]} triangles, median of {steps} steps"
     if ref_available():
         ref = Ref()
-        cores = ref.thread_count(0)
+        threads = cpus["usable"]
+        cores = ref.thread_count(threads)
         bb, cc = ref.tri_bboxes_centers(tris)
         t0 = time.perf_counter()
-        tree = ref.build(bb, cc, quality="high", threads=0)
+        tree = ref.build(bb, cc, quality="high", threads=threads)
         build_s = time.perf_counter() - t0
-        build_low_s = ref.time_build(bb, cc, quality="low", threads=0)
+        build_low_s = ref.time_build(bb, cc, quality="low", threads=threads)
         ref.set_triangles(tree, tris)
         times = []
         for i in range(warmup + steps):
-            ref.trace(tree, rays, flags=TIE_LOWEST_ID, threads=0, outputs=False)
+            ref.trace(tree, rays, flags=flags | DYNAMIC, threads=threads, outputs=False)
             if i >= warmup:
                 times.append(ref.last_trace_seconds)
         kind_ = "reference"
-        ref.trace(tree, rays[:100000], flags=TIE_LOWEST_ID, threads=-1, outputs=False)
-        single = 100000 / ref.last_trace_seconds / 1e6
+        ref.trace(tree, rays, flags=flags, threads=threads, outputs=False)       # the executor's static split, for the record
+        static_mrays = rays.shape[0] / ref.last_trace_seconds / 1e6
+        ref.trace(tree, rays[:200000], flags=flags, threads=-1, outputs=False)
+        single = 200000 / ref.last_trace_seconds / 1e6
     else:
         orc = Oracle()
         cores = 1
@@ -169,19 +282,21 @@ def cpu_arm(kind, steps, warmup, quick=False):
         tree = orc.build(bb, cc, quality="low")
         build_s = build_low_s = time.perf_counter() - t0
         orc.set_triangles(tree, tris)
-        rays = rays[: rays.shape[0] // 8]
-        sample = f"{rays.shape[0]} rays (scalar port), {tris.shape[0]} triangles"
+        rays = rays[:: 16]
+        sample = f"{rays.shape[0]} rays (every 16th ray; scalar port), {tris.shape[0]} triangles, median of {steps} steps"
         times = []
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            orc.trace(tree, rays, flags=TIE_LOWEST_ID)
+            orc.trace(tree, rays, flags=flags)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
         kind_ = "port"
-        single = rays.shape[0] / np.median(times) / 1e6
-    mean_s = float(np.mean(times))
-    return {"value": rays.shape[0] / mean_s / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind_, "sample": sample,
-            "ms_per_step": mean_s * 1e3, "single_thread_mrays": single,
+        single = static_mrays = rays.shape[0] / np.median(times) / 1e6
+    med = float(np.median(times))
+    return {"value": rays.shape[0] / med / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind_, "sample": sample,
+            "ms_per_step": med * 1e3, "spread": {"min_ms": float(np.min(times)) * 1e3, "max_ms": float(np.max(times)) * 1e3},
+            "schedule": "reference ThreadPool + ParallelExecutor, workers claim 4096-ray blocks",
+            "static_split_mrays": static_mrays, "single_thread_mrays": single, "cpus": cpus,
             "build_high_mtris": tris.shape[0] / build_s / 1e6, "build_low_mtris": tris.shape[0] / build_low_s / 1e6}
 
 
@@ -190,24 +305,30 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    kind = args.mesh
-    if args.sah_treelets:
-        os.environ["BVH_B200_SAH_TREELETS"] = "1"
-    workload = f"{kind}-1M triangles, {IMG}x{IMG} = {IMG * IMG} coherent primary rays per GPU, closest-hit"
+    kind, name = args.mesh, args.config
+    cfg = CONFIGS[name]
+    workload = workload_text(cfg, kind, name)
+    metric = cfg["metric"]
 
     if args.impl == "reference":
         if rank != 0:
             return
-        res = cpu_arm(kind, args.steps, args.warmup)
-        line = {"impl": "reference", "metric": "primary closest-hit rays per second", "value": res["value"], "unit": "Mrays/s",
+        res = cpu_arm(cfg, kind, name, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": metric, "value": res["value"], "unit": "Mrays/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "bvh": "reference DefaultBuilder Quality::High", "sample": res["sample"]},
+                "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+                "config": {"workload": workload, "bvh": "reference DefaultBuilder Quality::High", "sample": res["sample"],
+                           "schedule": res["schedule"], "cpus": res["cpus"], "spread": res["spread"],
+                           "static_split_mrays": res["static_split_mrays"], "single_thread_mrays": res["single_thread_mrays"]},
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "build": {"high_mtris_per_s": res["build_high_mtris"], "low_mtris_per_s": res["build_low_mtris"]},
                 "e2e": {"value": res["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
+
+    numa = None
+    if world > 1 and not args.no_numa:
+        numa = bind_to_gpu_numa_node(local_rank)          # before torch allocates pinned memory
 
     import torch
     import torch.distributed as dist
@@ -230,76 +351,97 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    def max_over_ranks(values):
+        t = torch.tensor(values, dtype=torch.float64, device=device).reshape(-1)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.cpu().tolist()
 
     # ---- inputs -----------------------------------------------------------------------------------
-    tris_np = scenes.make_mesh(kind, TRIS)
+    dt = np_dtype(cfg)
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    sfx = "3f" if dt == np.float32 else "3d"
+    ray_bytes, hit_bytes = (32, 16) if dt == np.float32 else (64, 32)
+    hit_words = hit_bytes // 4
+    hit_dtype = api.HIT3F if dt == np.float32 else api.HIT3D
+    L = api.lib()
+    tris_np = make_tris(cfg, kind)
     n_tris = tris_np.shape[0]
     verts = torch.from_numpy(tris_np).to(device)
-    rays_np = camera_rays(kind, rank, world)
+    rays_np = make_rays(cfg, kind, tris_np, rank, world)
     n_rays = rays_np.shape[0]
     rays_pinned = torch.from_numpy(rays_np).pin_memory()
     rays = rays_pinned.to(device, non_blocking=True)
     torch.cuda.synchronize()
+    total_rays = world * n_rays
     peak_gbs, peak_src = hbm_peak()
-    kflag = api.KERNEL_SIMPLE if args.kernel == "simple" else 0
+    base_flags = api.ANY_HIT if cfg["any_hit"] else 0
+    kflag = {"auto": 0, "persistent": api.KERNEL_TMA, "wide": api.KERNEL_WIDE, "simple": api.KERNEL_SIMPLE}[args.kernel]
 
     # ---- build: K timed LBVH builds from device-resident vertices ----------------------------------
     def build():
-        return api.Bvh.build_triangles(verts.data_ptr(), count=n_tris, dtype=np.float32, flags=api.DEVICE_POINTERS)
+        return api.Bvh.build_triangles(verts.data_ptr(), count=n_tris, dtype=dt, flags=api.DEVICE_POINTERS, quality=args.quality)
 
+    build_steps = args.steps if n_tris <= 2_000_000 else max(3, args.steps // 5)
     for _ in range(args.warmup):
         build().destroy()
     barrier()
-    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    b0.record()
-    for _ in range(args.steps):
+    bev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(build_steps)]
+    for s, e in bev:
+        s.record()
         build().destroy()
-    b1.record()
+        e.record()
     barrier()
-    build_ms = max_over_ranks(b0.elapsed_time(b1) / args.steps)
+    build_ms = float(np.median(max_over_ranks([s.elapsed_time(e) for s, e in bev])))
     bvh = build()
+    props = bvh.properties()
     t0 = time.perf_counter()
     for _ in range(3):
-        api.Bvh.build_triangles(tris_np).destroy()
+        api.Bvh.build_triangles(tris_np, quality=args.quality).destroy()
     build_e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
-    build_bytes = 300.0                            # 32-bit Morton pipeline, bytes per triangle
-    build_info = {"value": n_tris / build_ms / 1e3, "unit": "Mtris/s", "ms": build_ms, "scope": "per GPU (BVH replicated)",
-                  "e2e_ms_host_vertices": build_e2e_ms, "depth": bvh.depth,
+    morton_bits = int(props.get("morton_bits", 30))
+    build_bytes = 300.0 if morton_bits <= 32 else 440.0        # bytes per triangle of the LBVH pipeline
+    traffic_db = {}
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    build_info = {"value": n_tris / build_ms / 1e3, "unit": "Mtris/s", "ms": build_ms, "steps": build_steps, "scope": "per GPU (BVH replicated)",
+                  "e2e_ms_host_vertices": build_e2e_ms, "depth": bvh.depth, "morton_bits": morton_bits,
+                  "quality": args.quality or "high (library default)", "pipeline": props.get("pipeline"),
                   "roofline": {"bound": "hbm", "achieved": build_bytes * n_tris / (build_ms * 1e-3) / 1e9, "peak": peak_gbs,
                                "unit": "GB/s", "frac": build_bytes * n_tris / (build_ms * 1e-3) / 1e9 / peak_gbs,
-                               "traffic": None, "bytes_per_tri": build_bytes}}
+                               "traffic": traffic_db.get(f"build_{kind}_{n_tris}"), "bytes_per_tri": build_bytes}}
 
-    # ---- algorithmic bytes of the traversal, measured on the tree actually traversed ---------------
-    stats_sample = rays[: min(n_rays, 2_000_000)].contiguous()
-    st = torch.empty((stats_sample.shape[0], 3), dtype=torch.int32, device=device)
-    scratch_hits = torch.empty((stats_sample.shape[0], 4), dtype=torch.int32, device=device)
-    if api.lib().bvh3f_intersect_rays_stats(bvh.handle, stats_sample.data_ptr(), stats_sample.shape[0], scratch_hits.data_ptr(),
-                                            st.data_ptr(), api.DEVICE_POINTERS):
+    # ---- algorithmic bytes of the traversal, measured on the tree actually traversed, over the WHOLE timed batch
+    st = torch.empty((n_rays, 3), dtype=torch.int32, device=device)
+    scratch_hits = torch.empty((n_rays, hit_words), dtype=torch.int32, device=device)
+    if getattr(L, f"bvh{sfx}_intersect_rays_stats")(bvh.handle, rays.data_ptr(), n_rays, scratch_hits.data_ptr(),
+                                                    st.data_ptr(), api.DEVICE_POINTERS | base_flags):
         raise SystemExit(api.last_error())
     torch.cuda.synchronize()
-    s_inner, s_leaves, s_tri = (float(x) for x in st.double().mean(dim=0).tolist())
-    hit_frac = float((scratch_hits[:, 0] != -1).double().mean().item())
-    bytes_per_ray = 32 + 16 + 64 * s_inner + 48 * s_tri
-    del st, scratch_hits, stats_sample
+    s_inner, s_leaves, s_tri = (float(x) for x in st.sum(dim=0, dtype=torch.float64).div(n_rays).tolist())
+    if dt == np.float32:
+        hit_frac = float((scratch_hits[:, 0] != -1).double().mean().item())
+    else:
+        hit_frac = float((scratch_hits.view(torch.int64)[:, 0] != -1).double().mean().item())
+    bpr = bytes_per_ray(cfg, s_inner, s_tri)
+    del st, scratch_hits
 
     # ---- traversal: W warm-up + K timed steps -------------------------------------------------------
+    trace_fn = getattr(L, f"bvh{sfx}_intersect_rays")
+
     def trace(b, e, out):
-        if api.lib().bvh3f_intersect_rays(bvh.handle, rays.data_ptr() + 32 * b, e - b, out.data_ptr(), api.DEVICE_POINTERS | kflag):
+        if trace_fn(bvh.handle, rays.data_ptr() + ray_bytes * b, e - b, out.data_ptr(), api.DEVICE_POINTERS | base_flags | kflag):
             raise SystemExit(api.last_error())
 
     tracer, gather_desc = None, None
     if world > 1 and args.gather != "nccl":
         try:
             from bvh_b200.multi_gpu import FusedGatherTracer
-            tracer = FusedGatherTracer(bvh, rays, 4, flags=api.DEVICE_POINTERS | kflag, mode=args.gather)
-            gather_desc = (f"fused in the traversal kernel: every hit record stored into all {world} ranks' symmetric-memory "
-                           f"buffers ({'one multimem store via the NVSwitch multicast address' if tracer.mode == 'multicast' else 'one NVLink peer store per rank'}), "
+            tracer = FusedGatherTracer(bvh, rays, hit_words, flags=api.DEVICE_POINTERS | base_flags | kflag, mode=args.gather)
+            gather_desc = (f"fused in the traversal kernel: hit records staged per warp and stored into all {world} ranks' symmetric-memory "
+                           f"buffers ({'multimem stores via the NVSwitch multicast address' if tracer.mode == 'multicast' else 'NVLink peer stores'}), "
                            "symmetric-memory barrier per step")
         except Exception as exc:                 # no symmetric memory on this box: NCCL all-gather instead
             if args.gather != "auto":
@@ -308,7 +450,7 @@ def main():
                 print(f"[bench] fused gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
             tracer = None
     if tracer is None:
-        tracer = ShardedTracer(n_rays, 4, torch.int32, device, trace, chunks=args.chunks if world > 1 else 1)
+        tracer = ShardedTracer(n_rays, hit_words, torch.int32, device, trace, chunks=args.chunks if world > 1 else 1)
         if world > 1:
             gather_desc = f"NCCL all_gather_into_tensor of hit records, {args.chunks} chunks overlapped with traversal"
     for _ in range(max(3, args.warmup)):
@@ -327,19 +469,21 @@ def main():
     e1.record()
     barrier()
     clocks = sampler.summary()
-    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    total_ms = max_over_ranks([e0.elapsed_time(e1)])[0]
     ms_per_step = total_ms / args.steps
-    kernel_ms = float(np.mean([s.elapsed_time(e) for s, e in zip(starts, ends)])) if world == 1 else None
-    value = world * n_rays / ms_per_step / 1e3                     # Mrays/s, whole job
+    step_ms = max_over_ranks([s.elapsed_time(e) for s, e in zip(starts, ends)])     # per step, max over ranks
+    kernel_ms = float(np.median(step_ms))
+    value = total_rays / ms_per_step / 1e3                     # Mrays/s, whole job
+    kernel_name = bvh.properties().get("last_kernel", "trace_persistent_kernel")
 
-    hits_np = tracer.local.cpu().numpy().view(api.HIT3F).reshape(-1)
-    checksum = int(hits_np["prim_id"].astype(np.uint64).sum())
+    hits_np = tracer.local.cpu().numpy().view(hit_dtype).reshape(-1)
+    checksum = int(hits_np["prim_id"].astype(np.uint64).sum() & np.uint64(0xFFFFFFFFFFFFFFFF))
     if world > 1:
         g = tracer.global_hits()
-        assert g.shape[0] == world * n_rays
+        assert g.shape[0] == total_rays
         assert torch.equal(g[rank * n_rays:(rank + 1) * n_rays], tracer.local), "gathered hits do not match the local shard"
         # every rank must hold every other rank's shard: compare per-shard checksums across ranks
-        sums = g.view(world, n_rays, 4)[:, :, 0].to(torch.int64).sum(dim=1)
+        sums = g.view(world, n_rays, hit_words)[:, :, 0].to(torch.int64).sum(dim=1)
         ref_sums = sums.clone()
         dist.broadcast(ref_sums, src=0)
         assert torch.equal(sums, ref_sums), "ranks disagree on the gathered hit records"
@@ -347,53 +491,50 @@ def main():
     # ---- e2e through the C ABI with pinned host buffers ----------------------------------------------
     e2e = None
     if not args.no_e2e:
-        hits_pinned = torch.empty((n_rays, 4), dtype=torch.int32).pin_memory()
+        hits_pinned = torch.empty((n_rays, hit_words), dtype=torch.int32).pin_memory()
+
         def call():
-            if api.lib().bvh3f_intersect_rays(bvh.handle, rays_pinned.data_ptr(), n_rays, hits_pinned.data_ptr(), kflag):
+            if trace_fn(bvh.handle, rays_pinned.data_ptr(), n_rays, hits_pinned.data_ptr(), base_flags | kflag):
                 raise SystemExit(api.last_error())
         for _ in range(2):
             call()
         barrier()
+        e2e_steps = args.steps if n_rays <= 20_000_000 else max(3, args.steps // 5)
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(e2e_steps):
             call()
         torch.cuda.synchronize()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) / args.steps * 1e3)
-        assert np.array_equal(hits_pinned.numpy().view(api.HIT3F).reshape(-1), hits_np), "e2e hits differ from device-resident hits"
-        e2e = {"value": world * n_rays / e2e_ms / 1e3, "unit": "Mrays/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": int(n_rays * 32), "d2h_bytes_per_step": int(n_rays * 16),
-               "api": "bvh3f_intersect_rays(host rays, host hits) with pinned buffers"}
+        e2e_ms = max_over_ranks([(time.perf_counter() - t0) / e2e_steps * 1e3])[0]
+        assert np.array_equal(hits_pinned.numpy().view(hit_dtype).reshape(-1), hits_np), "e2e hits differ from device-resident hits"
+        e2e = {"value": total_rays / e2e_ms / 1e3, "unit": "Mrays/s", "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "h2d_bytes_per_step": int(n_rays * ray_bytes), "d2h_bytes_per_step": int(n_rays * hit_bytes),
+               "api": f"bvh{sfx}_intersect_rays(host rays, host hits) with pinned buffers", "numa": numa}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        res = cpu_arm(kind, 3, 1)
+        res = cpu_arm(cfg, kind, name, 5, 2)
         cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        cpu.update(single_thread_mrays=res["single_thread_mrays"], build_high_mtris=res["build_high_mtris"],
-                   build_low_mtris=res["build_low_mtris"])
+        cpu.update(single_thread_mrays=res["single_thread_mrays"], static_split_mrays=res["static_split_mrays"],
+                   build_high_mtris=res["build_high_mtris"], build_low_mtris=res["build_low_mtris"], spread=res["spread"])
 
     if rank == 0:
-        dur_ms = kernel_ms if kernel_ms is not None else ms_per_step
-        achieved = bytes_per_ray * n_rays / (dur_ms * 1e-3) / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"trace_{args.kernel}_{kind}")
-        except Exception:
-            pass
+        achieved = bpr * n_rays / (kernel_ms * 1e-3) / 1e9       # one launch = one rank's shard
         line = {
-            "metric": "primary closest-hit rays per second", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "metric": metric, "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "bvh": "LBVH (30-bit Morton, SAH leaf collapse, max_leaf_size 8)" + (" + experimental SAH treelet pass" if args.sah_treelets else "")
-                              + " built on the GPU, replicated per rank",
-                       "kernel": args.kernel, "tie_break": "lowest original id (canonical)",
-                       "l2": "inputs larger than L2: 320 MB of rays + 160 MB of hits streamed per step, no flush needed",
+            "scaling": cfg["scaling"], "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+            "config": {"workload": workload, "bvh": f"{props.get('pipeline', 'LBVH')} built on the GPU, replicated per rank",
+                       "kernel": kernel_name, "tie_break": "lowest original id (canonical)",
+                       "l2": f"inputs larger than L2: {n_rays * ray_bytes / 1e6:.0f} MB of rays + {n_rays * hit_bytes / 1e6:.0f} MB of hits streamed per step, no flush needed",
                        "hit_fraction": hit_frac, "inner_steps_per_ray": s_inner, "leaves_per_ray": s_leaves, "tri_tests_per_ray": s_tri,
-                       "gather": gather_desc,
-                       "hits_checksum": checksum},
-            "roofline": {"bound": "hbm", "kernel": f"trace_{args.kernel}_kernel<float>", "achieved": achieved, "peak": peak_gbs,
-                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
-                         "bytes_per_ray": bytes_per_ray, "launch_ms": dur_ms},
+                       "stats_rays": n_rays, "gather": gather_desc, "hits_checksum": checksum,
+                       "step_ms": {"median": kernel_ms, "max": float(np.max(step_ms)), "min": float(np.min(step_ms))}},
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak_gbs,
+                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs,
+                         "traffic": traffic_db.get(f"trace_{name}_{kind}"),
+                         "bytes_per_ray": bpr, "launch_ms": kernel_ms,
+                         "note": "algorithmic bytes over time; the tree is L2-resident, so frac can exceed 1 (traffic = DRAM bytes per launch, ncu)"},
             "build": build_info,
             "cpu_baseline": cpu,
             "e2e": e2e,

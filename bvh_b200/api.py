@@ -66,6 +66,10 @@ def lib() -> C.CDLL:
     L.bvh_host_alloc.restype = P
     L.bvh_host_alloc.argtypes = [SZ]
     L.bvh_host_free.argtypes = [P]
+    L.bvh_cuda_trim.restype = C.c_int
+    L.bvh_cuda_trim.argtypes = [C.c_int]
+    L.bvh_set_option.restype = C.c_int
+    L.bvh_set_option.argtypes = [C.c_char_p, C.c_long]
     L.bvh_thread_pool_create.restype = P
     L.bvh_thread_pool_create.argtypes = [SZ]
     L.bvh_thread_pool_destroy.argtypes = [P]
@@ -102,6 +106,8 @@ def lib() -> C.CDLL:
         f("sync").argtypes = [P]
         f("get_depth").restype = SZ
         f("get_depth").argtypes = [P]
+        f("get_property").restype = SZ
+        f("get_property").argtypes = [P, C.c_int]
         for name in ("intersect_ray", "intersect_ray_any", "intersect_ray_robust", "intersect_ray_any_robust"):
             f(name).argtypes = [P, P, P]
         n = lambda name: getattr(L, f"bvh_node{s}_{name}")
@@ -137,6 +143,24 @@ def set_stream(cuda_stream: int | None) -> None:
         lib().bvh_cuda_reset_stream()
     else:
         lib().bvh_cuda_set_stream(C.c_void_p(int(cuda_stream)))
+
+
+def set_option(name: str, value: int) -> None:
+    """``bvh_set_option``: process-wide experiment / test switches (``include/bvh_b200.h``)."""
+    if lib().bvh_set_option(name.encode(), int(value)):
+        raise BvhError(last_error())
+
+
+def trim(device: int = 0) -> None:
+    """Hands the library's cached device memory back to the driver (``bvh_cuda_trim``)."""
+    if lib().bvh_cuda_trim(device):
+        raise BvhError(last_error())
+
+
+PROPERTIES = {"depth": 0, "node_slots": 1, "morton_bits": 2, "quality": 3, "treelets": 4, "wide_nodes": 5,
+              "last_kernel": 6, "stream": 7}
+KERNEL_NAMES = {0: None, 1: "trace_persistent_kernel<kTma=true>", 2: "trace_persistent_kernel<kTma=false>",
+                3: "trace_simple_kernel", 4: "trace_simple_kernel<kStats=true>", 5: "trace_pair_kernel", 6: "trace_wide_kernel"}
 
 
 def _sfx(dtype) -> str:
@@ -276,6 +300,26 @@ class Bvh:
     @property
     def depth(self) -> int:
         return self._f("get_depth")(self.handle)
+
+    def get_property(self, name: str) -> int:
+        v = self._f("get_property")(self.handle, PROPERTIES[name])
+        if v == C.c_size_t(-1).value:
+            raise BvhError(last_error() or f"unknown property {name}")
+        return v
+
+    def properties(self) -> dict:
+        """Provenance of the device tree and the kernel of the last batched call (``bvhNN_get_property``)."""
+        p = {k: self.get_property(k) for k in PROPERTIES}
+        q = p["quality"] if p["quality"] < 3 else None
+        p["last_kernel"] = KERNEL_NAMES.get(p["last_kernel"])
+        bits = p["morton_bits"]
+        if bits:
+            p["pipeline"] = (f"LBVH ({bits}-bit Morton, SAH leaf collapse, max_leaf_size 8)"
+                             + (f" + SAH treelet pass ({p['treelets']} subtrees of <= 64 primitives)" if p["treelets"] else "")
+                             + f", quality {('low', 'medium', 'high')[q] if q is not None else '?'}")
+        else:
+            p["pipeline"] = "tree uploaded from the host mirror"
+        return p
 
     def arrays(self):
         """(bounds[n,6] as minx,maxx,miny,maxy,minz,maxz; index_values[n] u64; prim_ids[p] u64) read

@@ -132,13 +132,31 @@ template <> struct AuxPack<double> {
     static BVH_HD uint32_t depth(uint64_t w) { return (uint32_t)w; }
 };
 
+// A bottom subtree handed to the SAH treelet pass (treelet_sah.cuh): device slot of its root record and the
+// range [l, r] of sorted primitives it covers.
+struct Treelet { uint32_t slot, l, r; };
+
 template <typename T> struct BuildParams {
     DevNode<T>* nodes;            // 2n device slots (slot = reference index + 1)
     int* flags;                   // n-1, initialised to -1
     uint32_t* info;               // [0] tree depth (max stack entries needed), [1] root split position
     uint32_t n;
     uint32_t min_leaf, max_leaf;  // TopDownSahBuilder::Config, top_down_sah_builder.h:27-40
+    // Treelet discovery (quality Medium / High): every MAXIMAL subtree of 3..treelet_max primitives is appended
+    // to treelets[] by the thread that merges it into a larger parent.  treelet_max == 0 switches it off.
+    Treelet* treelets = nullptr;
+    uint32_t* treelet_count = nullptr;
+    uint32_t treelet_max = 0;
 };
+
+template <typename T> BVH_HD void append_treelet(const BuildParams<T>& p, uint32_t slot, uint32_t l, uint32_t r) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t at = atomicAdd(p.treelet_count, 1u);
+#else
+    const uint32_t at = (*p.treelet_count)++;
+#endif
+    p.treelets[at] = Treelet { slot, l, r };
+}
 
 template <typename T> BVH_HD void write_node(DevNode<T>* dst, const T bmin[3], const T bmax[3],
                                              typename Real<T>::UInt index, typename Real<T>::UInt pad = 0) {
@@ -230,7 +248,18 @@ template <typename T> BVH_HD bool merge_into_parent(const BuildParams<T>& p, Cli
         write_node(p.nodes + child_slot(parent, 1 - side), s.bmin, s.bmax, own.index, own.pad);
         write_node(p.nodes + child_slot(parent, side), smin, smax, sn.index, sn.pad);
     }
+    const uint32_t own_l = s.l, own_r = s.r;
     if (side == 0) s.r = other; else s.l = other;
+    if (p.treelet_max != 0 && s.r - s.l + 1 > p.treelet_max) {
+        // the parent is too large for a treelet: each child of 3..treelet_max primitives is a maximal one
+        const uint32_t own_count = own_r - own_l + 1, sib_count = (s.r - s.l + 1) - own_count;
+        const uint32_t own_side = swap ? 1 - side : side;
+        if (own_count >= 3 && own_count <= p.treelet_max) append_treelet(p, (uint32_t)child_slot(parent, own_side), own_l, own_r);
+        if (sib_count >= 3 && sib_count <= p.treelet_max) {
+            const uint32_t sib_l = side == 0 ? parent + 1 : other, sib_r = side == 0 ? other : parent;
+            append_treelet(p, (uint32_t)child_slot(parent, 1 - own_side), sib_l, sib_r);
+        }
+    }
     // parent box = left.get_bbox().extend(right.get_bbox()) (bvh.h:213-217), left/right as they now sit in memory
     const bool own_first = swap ? !own_is_left : own_is_left;
     for (int k = 0; k < 3; ++k) {
@@ -254,6 +283,7 @@ template <typename T> BVH_HD bool merge_into_parent(const BuildParams<T>& p, Cli
     if (s.l == 0 && s.r == p.n - 1) {                       // this is the root: reference index 0
         write_node(p.nodes + 1, s.bmin, s.bmax, s.index);
         p.info[0] = s.depth; p.info[1] = parent;
+        if (p.treelet_max != 0 && p.n >= 3 && p.n <= p.treelet_max) append_treelet(p, 1u, 0u, p.n - 1);   // the whole tree is one treelet
         return true;
     }
     return false;

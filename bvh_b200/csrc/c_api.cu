@@ -27,31 +27,83 @@ static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 const char* last_error() { return g_error.c_str(); }
 
+Tunables& tunables() {
+    static Tunables t;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto env = [] (const char* name, long fallback) { const char* e = getenv(name); return e ? atol(e) : fallback; };
+        t.morton_bits = (int)env("BVH_B200_MORTON_BITS", 0);
+        t.sah_treelets = (int)env("BVH_B200_SAH_TREELETS", -1);
+        if (const char* e = getenv("BVH_B200_HIERARCHY")) {
+            const std::string v = e;
+            t.hierarchy = v == "global" ? 0 : v == "thread64" ? 64 : v == "thread256" ? 256 : 128;
+        }
+        t.e2e_chunks = (int)env("BVH_B200_E2E_CHUNKS", 0);
+        t.variant = (int)env("BVH_B200_VARIANT", 1);
+        t.use_wide = (int)env("BVH_B200_USE_WIDE", -1);
+        const long budget = env("BVH_B200_INNER_BUDGET", 12);
+        t.inner_budget = budget <= 0 ? 0xFFFFFFFFu : (uint32_t)budget;
+        const long wbudget = env("BVH_B200_WIDE_BUDGET", 4);
+        t.wide_budget = wbudget <= 0 ? 0xFFFFFFFFu : (uint32_t)wbudget;
+        t.watchdog = (uint32_t)env("BVH_B200_WATCHDOG", 1l << 26);
+    });
+    return t;
+}
+
 static thread_local int g_device = 0;
 static thread_local cudaStream_t g_user_stream = nullptr;
 static thread_local bool g_have_user_stream = false;
 
+// One PRIVATE memory pool per device (stream-ordered allocation): freed blocks stay cached in it so that
+// rebuilds never go back to the driver, without touching the process-wide default pool of the host
+// application (bvh_cuda_trim() hands the cached memory back).
+static std::mutex g_pool_mutex;
+static cudaMemPool_t g_pools[64] = {};
+
 int prepare_device(int device) {
-    static std::mutex mutex;
-    static bool prepared[64] = {};
-    BVH_CUDA_TRY(cudaSetDevice(device));
-    std::lock_guard<std::mutex> lock(mutex);
-    if (device >= 0 && device < 64 && !prepared[device]) {
+    if (device < 0 || device >= 64) { set_error("device index out of range"); return -1; }
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
         cudaMemPool_t pool;
-        BVH_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
-        unsigned long long threshold = ~0ull;      // keep freed blocks cached: rebuilds never hit the driver
+        BVH_CUDA_TRY(cudaMemPoolCreate(&pool, &props));
+        unsigned long long threshold = ~0ull;
         BVH_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
-        prepared[device] = true;
+        g_pools[device] = pool;
     }
     return 0;
 }
 
 int device_alloc(void** ptr, size_t bytes, cudaStream_t stream) {
     *ptr = nullptr;
-    BVH_CUDA_TRY(cudaMallocAsync(ptr, bytes ? bytes : 16, stream));
+    int device = 0;
+    BVH_CUDA_TRY(cudaGetDevice(&device));
+    cudaMemPool_t pool = nullptr;
+    if (device >= 0 && device < 64) { std::lock_guard<std::mutex> lock(g_pool_mutex); pool = g_pools[device]; }
+    if (!pool) { if (prepare_device(device)) return -1; std::lock_guard<std::mutex> lock(g_pool_mutex); pool = g_pools[device]; }
+    BVH_CUDA_TRY(cudaMallocFromPoolAsync(ptr, bytes ? bytes : 16, pool, stream));
     return 0;
 }
 void device_free(void* ptr, cudaStream_t stream) { if (ptr) cudaFreeAsync(ptr, stream); }
+
+// Every entry point runs on the handle's device and puts the caller's current device back afterwards.
+struct DeviceGuard {
+    int prev = -1, dev;
+    bool ok = true;
+    explicit DeviceGuard(int device) : dev(device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) {
+            set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(cudaGetLastError()));
+            ok = false;
+        }
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+#define BVH_ON_DEVICE(device) DeviceGuard device_guard__(device); if (!device_guard__.ok) return -1
 
 // ---- host mirror ------------------------------------------------------------------------------
 template <typename T> struct HostNode { T bounds[6]; typename Real<T>::UInt index; };
@@ -87,7 +139,7 @@ template <typename T> struct Handle {
 };
 
 template <typename T> int init_handle(Handle<T>& h) {
-    h.device = g_device;
+    h.device = g_device;                        // (the caller holds a DeviceGuard on g_device)
     if (prepare_device(h.device)) return -1;
     h.dev.device = h.device;
     if (g_have_user_stream) { h.stream = g_user_stream; h.own_stream = false; }
@@ -97,7 +149,7 @@ template <typename T> int init_handle(Handle<T>& h) {
 
 template <typename T> void destroy_handle(Handle<T>* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     release(h->dev, h->stream);
     device_free(h->d_rays, h->stream); device_free(h->d_hits, h->stream); device_free(h->d_stats, h->stream);
     cudaStreamSynchronize(h->stream);
@@ -137,7 +189,7 @@ template <typename T> int download_mirror(Handle<T>& h) {
     std::lock_guard<std::mutex> lock(h.mirror_mutex);       // concurrent bvhNN_intersect_ray* callers (bvh_impl.h:244)
     if (h.host_valid) return 0;
     if (!h.device_valid) { set_error("handle holds no BVH"); return -1; }
-    BVH_CUDA_TRY(cudaSetDevice(h.device));
+    BVH_ON_DEVICE(h.device);
     std::vector<DevNode<T>> dev_nodes(h.dev.node_slots);
     std::vector<uint32_t> dev_ids(h.dev.prim_count);
     BVH_CUDA_TRY(cudaMemcpyAsync(dev_nodes.data(), h.dev.nodes, dev_nodes.size() * sizeof(DevNode<T>), cudaMemcpyDeviceToHost, h.stream));
@@ -177,7 +229,7 @@ template <typename T> int download_mirror(Handle<T>& h) {
 
 // Mirror -> device: reference node i goes to device slot i + 1, padded to 32 / 64 bytes.
 template <typename T> int upload_mirror(Handle<T>& h) {
-    BVH_CUDA_TRY(cudaSetDevice(h.device));
+    BVH_ON_DEVICE(h.device);
     const size_t node_count = h.nodes.size();
     if (node_count == 0) { set_error("upload: empty BVH"); return -1; }
     std::vector<DevNode<T>> dev_nodes(node_count + 1);
@@ -188,7 +240,10 @@ template <typename T> int upload_mirror(Handle<T>& h) {
         dev_nodes[i + 1].pad = 0;
     }
     std::vector<uint32_t> ids(h.prim_ids.size());
-    for (size_t i = 0; i < ids.size(); ++i) ids[i] = (uint32_t)h.prim_ids[i];
+    for (size_t i = 0; i < ids.size(); ++i) {
+        if (h.prim_ids[i] >= ids.size()) { set_error("upload: primitive id out of range"); return -1; }
+        ids[i] = (uint32_t)h.prim_ids[i];
+    }
 
     // depth = longest chain of inner nodes (bounds the traversal stack); also validates child indices
     uint32_t depth = 0;
@@ -200,7 +255,11 @@ template <typename T> int upload_mirror(Handle<T>& h) {
             auto [i, d] = stack.back();
             stack.pop_back();
             if (++visited > node_count) { set_error("upload: the node graph is not a tree"); return -1; }
-            if (index_count(h.nodes[i].index) != 0) continue;
+            if (const uint32_t leaf_count = index_count(h.nodes[i].index)) {
+                // the kernels index tris[first .. first + count) and prim_ids[slot] without further checks
+                if ((size_t)index_first(h.nodes[i].index) + leaf_count > ids.size()) { set_error("upload: leaf range exceeds the primitive count"); return -1; }
+                continue;
+            }
             const size_t first = (size_t)index_first(h.nodes[i].index);
             if (first == 0 || first + 1 >= node_count) { set_error("upload: child index out of range"); return -1; }
             depth = std::max(depth, d + 1);
@@ -283,8 +342,20 @@ void intersect_nodes(const NodeVec& nodes, const T* ray, const Callback* cb) {
     for (int k = 0; k < kDim; ++k) { r.org[k] = ray[k]; r.dir[k] = ray[kDim + k]; }
     r.tmin = ray[2 * kDim]; r.tmax = ray[2 * kDim + 1];
     ray_prologue<T, kRobust, kDim>(r);
-    U stack[64];                                           // SmallStack<Index, 64>, bvh_impl.h:241
-    unsigned sp = 0;
+    // SmallStack<Index, 64> (bvh_impl.h:241) that spills to the heap instead of asserting (stack.h:21): an LBVH
+    // over 63-bit keys with duplicate runs can be up to 91 levels deep.
+    U fixed[64];
+    std::vector<U> spill;
+    U* stack = fixed;
+    size_t capacity = 64, sp = 0;
+    auto push = [&] (U v) {
+        if (sp == capacity) {
+            if (stack == fixed) spill.assign(fixed, fixed + sp);
+            spill.resize(2 * capacity);                     // (keeps the entries already spilled)
+            stack = spill.data(); capacity *= 2;
+        }
+        stack[sp++] = v;
+    };
     U top = nodes[0].index;
     for (;;) {
         bool alive = true;
@@ -300,7 +371,7 @@ void intersect_nodes(const NodeVec& nodes, const T* ray, const Callback* cb) {
                 if (hr) {
                     U far_i = right.index;
                     if (!kAny && l0 > r0) std::swap(near_i, far_i);
-                    if (sp < 64) stack[sp++] = far_i;
+                    push(far_i);
                 }
                 top = near_i;
             } else if (hr) top = right.index;
@@ -350,6 +421,8 @@ template <typename T>
 Handle<T>* build_handle(const T* verts, const T* bboxes, const T* centers, size_t n,
                         const bvh_build_config* config, bool device_ptrs) {
     if (n == 0 || n > 0xFFFFFFFFull) { set_error("build: prim_count out of range"); return nullptr; }
+    DeviceGuard guard(g_device);
+    if (!guard.ok) return nullptr;
     auto h = new Handle<T>();
     if (init_handle(*h)) { delete h; return nullptr; }
     int rc = 0;
@@ -392,7 +465,7 @@ int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bv
     if (!h) { set_error("null handle"); return -1; }
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lock(h->batch_mutex);
-    BVH_CUDA_TRY(cudaSetDevice(h->device));
+    BVH_ON_DEVICE(h->device);
     if (ensure_device(*h)) return -1;
     const unsigned tf = translate_flags(flags);
     if (flags & BVH_DEVICE_POINTERS) {
@@ -416,7 +489,7 @@ int intersect_batch(Handle<T>* h, const RayPod* rays, size_t n, HitPod* hits, bv
     constexpr size_t kMinChunk = 1u << 20;                   // 1M rays = 32 MB of float rays per chunk
     size_t chunks = n / kMinChunk;
     if (chunks > Handle<T>::kDefaultChunks) chunks = Handle<T>::kDefaultChunks;
-    if (const char* e = getenv("BVH_B200_E2E_CHUNKS")) chunks = (size_t)atol(e);      // experiments only
+    if (const int forced = tunables().e2e_chunks.load()) chunks = (size_t)(forced > 0 ? forced : 1);   // experiments only
     if (chunks < 1) chunks = 1;
     if (chunks > Handle<T>::kMaxChunks) chunks = Handle<T>::kMaxChunks;
     // the staging buffers may still be in use by earlier work on the handle's stream
@@ -453,13 +526,34 @@ template <typename T> void save_mirror(Handle<T>& h, FILE* file) {
 
 template <typename T> Handle<T>* load_mirror(FILE* file) {
     using U = typename Real<T>::UInt;
+    DeviceGuard guard(g_device);
+    if (!guard.ok) return nullptr;
     auto h = new Handle<T>();
     if (init_handle(*h)) { delete h; return nullptr; }
     U node_count = 0, prim_count = 0;                       // short reads give defaults (stream.h:13-18)
     if (fread(&node_count, sizeof(U), 1, file) != 1) node_count = 0;
     if (fread(&prim_count, sizeof(U), 1, file) != 1) prim_count = 0;
-    h->nodes.resize((size_t)node_count);
-    h->prim_ids.resize((size_t)prim_count);
+    // A corrupt header must not turn into a multi-gigabyte resize: the counts are bounded by what the file
+    // still holds (seekable streams) and allocation failures never cross the C boundary.
+    const long here = ftell(file);
+    if (here >= 0 && fseek(file, 0, SEEK_END) == 0) {
+        const long end = ftell(file);
+        fseek(file, here, SEEK_SET);
+        const double need = (double)node_count * (6 * sizeof(T) + sizeof(U)) + (double)prim_count * sizeof(U);
+        if (end >= here && need > (double)(end - here)) {
+            set_error("load: the header announces more nodes / primitives than the file holds");
+            destroy_handle(h);
+            return nullptr;
+        }
+    }
+    try {
+        h->nodes.resize((size_t)node_count);
+        h->prim_ids.resize((size_t)prim_count);
+    } catch (const std::exception&) {
+        set_error("load: out of memory for the announced node / primitive counts");
+        destroy_handle(h);
+        return nullptr;
+    }
     for (auto& n : h->nodes) {
         std::memset(&n, 0, sizeof n);
         if (fread(n.bounds, sizeof(T), 6, file) != 6) std::memset(n.bounds, 0, sizeof n.bounds);
@@ -562,6 +656,29 @@ BVH_EXPORT void* bvh_host_alloc(size_t bytes) {
     return p;
 }
 BVH_EXPORT void bvh_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+BVH_EXPORT int bvh_set_option(const char* name, long value) {
+    if (!name) { set_error("set_option: null name"); return -1; }
+    Tunables& t = tunables();
+    const std::string n = name;
+    if (n == "morton_bits") t.morton_bits = (int)value;
+    else if (n == "sah_treelets") t.sah_treelets = (int)value;
+    else if (n == "hierarchy") t.hierarchy = (int)value;
+    else if (n == "e2e_chunks") t.e2e_chunks = (int)value;
+    else if (n == "variant") t.variant = (int)value;
+    else if (n == "use_wide") t.use_wide = (int)value;
+    else if (n == "inner_budget") t.inner_budget = value <= 0 ? 0xFFFFFFFFu : (uint32_t)value;
+    else if (n == "wide_budget") t.wide_budget = value <= 0 ? 0xFFFFFFFFu : (uint32_t)value;
+    else if (n == "watchdog") t.watchdog = (uint32_t)value;
+    else { set_error("set_option: unknown option " + n); return -1; }
+    return 0;
+}
+BVH_EXPORT int bvh_cuda_trim(int device) {
+    if (device < 0 || device >= 64) { set_error("no such CUDA device"); return -1; }
+    cudaMemPool_t pool;
+    { std::lock_guard<std::mutex> lock(g_pool_mutex); pool = g_pools[device]; }
+    if (pool) BVH_CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+    return 0;
+}
 
 // The pool is an API token only: CUDA streams do the work that ThreadPool does in the reference.
 struct bvh_thread_pool { size_t thread_count; };
@@ -653,7 +770,7 @@ BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete p
     BVH_EXPORT int bvh##S##_set_triangles(struct bvh##S* bvh, const T* vertices, size_t prim_count, unsigned flags) { \
         auto h = H(T, bvh);                                                                                        \
         if (!h) { set_error("null handle"); return -1; }                                                           \
-        BVH_CUDA_TRY(cudaSetDevice(h->device));                                                                    \
+        BVH_ON_DEVICE(h->device);                                                                    \
         if (ensure_device(*h)) return -1;                                                                          \
         if (prim_count != h->dev.prim_count) { set_error("set_triangles: prim_count mismatch"); return -1; }       \
         DeviceInput<T> dv(h->stream);                                                                              \
@@ -665,7 +782,7 @@ BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete p
     BVH_EXPORT int bvh##S##_refit_triangles(struct bvh##S* bvh, const T* vertices, size_t prim_count, unsigned flags) { \
         auto h = H(T, bvh);                                                                                        \
         if (!h) { set_error("null handle"); return -1; }                                                           \
-        BVH_CUDA_TRY(cudaSetDevice(h->device));                                                                    \
+        BVH_ON_DEVICE(h->device);                                                                    \
         if (ensure_device(*h)) return -1;                                                                          \
         if (prim_count != h->dev.prim_count) { set_error("refit_triangles: prim_count mismatch"); return -1; }     \
         DeviceInput<T> dv(h->stream);                                                                              \
@@ -687,7 +804,7 @@ BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete p
         if (!h) { set_error("null handle"); return -1; }                                                           \
         if (!gathered_hits || world_size < 1 || world_size > 8) { set_error("gather: need 1..8 gathered arrays"); return -1; } \
         std::lock_guard<std::mutex> lock(h->batch_mutex);                                                          \
-        BVH_CUDA_TRY(cudaSetDevice(h->device));                                                                    \
+        BVH_ON_DEVICE(h->device);                                                                    \
         if (ensure_device(*h)) return -1;                                                                          \
         GatherTargets g;                                                                                           \
         for (int r = 0; r < 8; ++r) g.peer[r] = r < world_size ? gathered_hits[r] : nullptr;                      \
@@ -703,13 +820,28 @@ BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete p
     BVH_EXPORT int bvh##S##_sync(struct bvh##S* bvh) {                                                             \
         auto h = H(T, bvh);                                                                                        \
         if (!h) { set_error("null handle"); return -1; }                                                           \
-        BVH_CUDA_TRY(cudaSetDevice(h->device));                                                                    \
+        BVH_ON_DEVICE(h->device);                                                                    \
         return check_trace_status(h->dev, h->stream);                                                              \
     }                                                                                                              \
     BVH_EXPORT size_t bvh##S##_get_depth(struct bvh##S* bvh) {                                                     \
         auto h = H(T, bvh);                                                                                        \
         if (!h || ensure_device(*h)) return 0;                                                                     \
         return h->dev.depth;                                                                                       \
+    }                                                                                                              \
+    BVH_EXPORT size_t bvh##S##_get_property(struct bvh##S* bvh, int property) {                                    \
+        auto h = H(T, bvh);                                                                                        \
+        if (!h || ensure_device(*h)) return (size_t)-1;                                                            \
+        switch (property) {                                                                                        \
+            case BVH_PROP_DEPTH: return h->dev.depth;                                                              \
+            case BVH_PROP_NODE_SLOTS: return h->dev.node_slots;                                                    \
+            case BVH_PROP_MORTON_BITS: return (size_t)h->dev.morton_bits;                                          \
+            case BVH_PROP_QUALITY: return (size_t)h->dev.quality;                                                  \
+            case BVH_PROP_TREELETS: return h->dev.treelets;                                                        \
+            case BVH_PROP_WIDE_NODES: return h->dev.wide ? h->dev.wide_count : 0;                                  \
+            case BVH_PROP_LAST_KERNEL: return (size_t)h->dev.last_kernel;                                          \
+            case BVH_PROP_STREAM: return (size_t)reinterpret_cast<uintptr_t>(h->stream);                           \
+            default: return (size_t)-1;                                                                            \
+        }                                                                                                          \
     }
 
 BVH_IMPL_3D(float, 3f, bvh_intersect_callbackf)

@@ -2,6 +2,7 @@
 // pipelines (lbvh_build.cu, traverse.cu).  Nothing here is exported.
 #pragma once
 
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -33,6 +34,22 @@ int device_alloc(void** ptr, size_t bytes, cudaStream_t stream);
 void device_free(void* ptr, cudaStream_t stream);
 int prepare_device(int device);
 
+// Process-wide switches for experiments and tests; the defaults are the measured best.  Initialised once from
+// the BVH_B200_* environment variables, changed at run time with bvh_set_option — nothing on a
+// call path reads the environment.
+struct Tunables {
+    std::atomic<int> morton_bits { 0 };         // 0: auto (63 from 2^22 primitives), 30, 63
+    std::atomic<int> sah_treelets { -1 };       // -1: by quality (Medium / High), 0 / 1: forced off / on
+    std::atomic<int> hierarchy { 128 };         // leaves per block of the hierarchy kernel (64 / 128 / 256), 0: global flags only
+    std::atomic<int> e2e_chunks { 0 };          // chunks of the host-buffer pipeline, 0: auto
+    std::atomic<int> variant { 1 };             // persistent kernel: 1 TMA-staged ray chunks, 0 streaming loads
+    std::atomic<int> use_wide { -1 };           // -1: auto (wide tree where its semantics allow), 0 / 1
+    std::atomic<uint32_t> inner_budget { 12 };  // inner steps per lane per round
+    std::atomic<uint32_t> wide_budget { 4 };    // same for the wide kernel
+    std::atomic<uint32_t> watchdog { 1u << 26 };
+};
+Tunables& tunables();
+
 struct BuildOptions {
     uint32_t min_leaf = 1;          // TopDownSahBuilder::Config (top_down_sah_builder.h:27-40)
     uint32_t max_leaf = 8;
@@ -59,7 +76,14 @@ template <typename T> struct DeviceBvh {
     WideNode* wide = nullptr;
     uint32_t wide_depth = 0;            // number of wide levels (bounds the fast path's stack)
     uint32_t wide_count = 0;
+    // provenance, reported through bvhNN_get_property
+    int morton_bits = 0;                // 30 / 63; 0 when the tree was uploaded from a host mirror
+    int quality = -1;                   // DefaultBuilder::Quality the build ran with (-1: not built here)
+    uint32_t treelets = 0;              // subtrees rebuilt by the SAH treelet pass
+    mutable int last_kernel = 0;        // TraceKernel of the most recent trace_rays call
 };
+
+enum TraceKernel : int { kKernelNone = 0, kKernelPersistentTma, kKernelPersistent, kKernelSimple, kKernelStats, kKernelPair, kKernelWide };
 
 // (Re)derives the wide tree from the binary one, e.g. after an upload from the host mirror.
 // force = false: only if the tree already has one (refresh) or the environment asks for it at build time;

@@ -248,44 +248,39 @@ hierarchy_thread_kernel(BuildParams<T> p, const K* __restrict__ keys, const uint
 template <typename T, typename K>
 void launch_hierarchy(const BuildParams<T>& p, const K* keys, const uint32_t* vals, const T* leaf_src, int mode,
                       DevTri<T>* tris, cudaStream_t stream) {
-    const char* e = std::getenv("BVH_B200_HIERARCHY");
-    const std::string v = e ? e : "thread128";
+    const int v = tunables().hierarchy.load();
     const uint32_t n = p.n;
 #define BVH_LAUNCH_H(B) hierarchy_thread_kernel<T, K, B><<<(n + B - 1) / B, B, 0, stream>>>(p, keys, vals, leaf_src, mode, tris)
-    if (v == "global") hierarchy_global_kernel<T, K><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(p, keys, vals, leaf_src, mode, tris);
-    else if (v == "thread64") BVH_LAUNCH_H(64);
-    else if (v == "thread256" && sizeof(T) == 4) BVH_LAUNCH_H((sizeof(T) == 4 ? 256 : 128));
+    if (v == 0) hierarchy_global_kernel<T, K><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(p, keys, vals, leaf_src, mode, tris);
+    else if (v == 64) BVH_LAUNCH_H(64);
+    else if (v == 256 && sizeof(T) == 4) BVH_LAUNCH_H((sizeof(T) == 4 ? 256 : 128));
     else BVH_LAUNCH_H(128);
 #undef BVH_LAUNCH_H
 }
 
-// ---- EXPERIMENTAL second pass: SAH rebuild of the bottom subtrees (treelet_sah.cuh) -------------------------
-// Not yet validated on hardware (the host emulation runs the same source, tests/test_host_emulation.py);
-// only reached with BuildOptions::sah_treelets / BVH_B200_SAH_TREELETS=1.
-// K5a: one thread per inner node: is it the root of a maximal subtree of <= kMaxPrims primitives?
-template <typename T, typename K>
-__global__ void __launch_bounds__(kBlock)
-find_treelets_kernel(const DevNode<T>* __restrict__ nodes, const K* __restrict__ keys, uint32_t n,
-                     Treelet* __restrict__ list, uint32_t* __restrict__ list_count) {
-    const uint32_t p = blockIdx.x * kBlock + threadIdx.x;
-    if (p + 1 >= n) return;
-    Treelet t;
-    if (treelet_probe<T, K>(nodes, keys, n, p, (uint32_t)TreeletCfg<T>::kMaxPrims, t)) list[atomicAdd(list_count, 1u)] = t;
-}
+// ---- second pass of Quality Medium / High: SAH rebuild of the bottom subtrees (treelet_sah.cuh) -------------
+// The treelets were listed by the hierarchy kernel (build_core.cuh merge_into_parent).  One WARP per treelet:
+// warps claim list entries from a global cursor (treelets differ in size), the scratch of a treelet is the
+// warp's slice of the block's dynamic shared memory.
+constexpr int kTreeletWarps = 3;          // 3 x 14.4 KB of scratch per block: 5 blocks = 15 warps per SM
 
-// K5b: one block per treelet (grid-stride over the list).
 template <typename T>
-__global__ void __launch_bounds__(TreeletCfg<T>::kMaxPrims)
-treelet_kernel(const Treelet* __restrict__ list, const uint32_t* __restrict__ list_count, DevNode<T>* __restrict__ nodes,
-               uint32_t* __restrict__ prim_ids, DevTri<T>* __restrict__ tris, const T* __restrict__ leaf_src,
-               const T* __restrict__ centre_src, int leaf_mode, uint32_t min_leaf, uint32_t max_leaf, uint32_t* __restrict__ info) {
+__global__ void __launch_bounds__(kTreeletWarps * 32)
+treelet_kernel(const Treelet* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t* __restrict__ cursor,
+               DevNode<T>* __restrict__ nodes, uint32_t* __restrict__ prim_ids, DevTri<T>* __restrict__ tris,
+               const T* __restrict__ leaf_src, const T* __restrict__ centre_src, int leaf_mode, uint32_t min_leaf,
+               uint32_t max_leaf, uint32_t* __restrict__ info) {
     constexpr int S = TreeletCfg<T>::kMaxPrims;
-    __shared__ TreeletScratch<T, S> scratch;
+    extern __shared__ __align__(16) unsigned char treelet_smem[];
+    TreeletScratch<T, S>& scratch = reinterpret_cast<TreeletScratch<T, S>*>(treelet_smem)[threadIdx.x >> 5];
     const uint32_t count = *list_count, lbvh_depth = info[0];
-    for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
-        const Treelet t = list[i];
-        treelet_rebuild<T, S, BlockExec>(scratch, t, nodes, prim_ids, tris, leaf_src, centre_src, leaf_mode, min_leaf, max_leaf, info, lbvh_depth);
-        __syncthreads();
+    for (;;) {
+        uint32_t i = 0;
+        if ((threadIdx.x & 31u) == 0) i = atomicAdd(cursor, 1u);
+        i = __shfl_sync(0xFFFFFFFFu, i, 0);
+        if (i >= count) break;
+        treelet_rebuild<T, S, WarpExec>(scratch, list[i], nodes, prim_ids, tris, leaf_src, centre_src, leaf_mode, min_leaf, max_leaf, info, lbvh_depth);
+        __syncwarp();
     }
 }
 
@@ -439,8 +434,7 @@ inline int build_wide(DeviceBvh<double>&, uint32_t, uint32_t*, uint2*, uint2*, c
 // The wide tree is derived lazily, the first time a trace asks for it (trace_rays), unless the
 // environment asks for it at build time (experiments: BVH_B200_USE_WIDE=1 makes it the default path).
 bool wide_enabled() {
-    static const bool on = [] { const char* e = getenv("BVH_B200_USE_WIDE"); return e && atoi(e) != 0; }();
-    return on;
+    return tunables().use_wide.load() > 0;
 }
 
 struct Scratch {
@@ -512,26 +506,45 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     p.min_leaf = options.min_leaf < 1 ? 1 : options.min_leaf;
     p.max_leaf = options.max_leaf > kMaxLeafPrims ? kMaxLeafPrims : (options.max_leaf < 1 ? 1 : options.max_leaf);
     if (p.min_leaf > p.max_leaf) p.min_leaf = p.max_leaf;
+    // Quality Low: the plain LBVH (+ SAH leaf collapse); Medium / High: + SAH treelet pass
+    const bool treelets = options.sah_treelets && n > 2;
+    uint32_t* treelet_words = nullptr;                       // [0] list length, [1] the warps' cursor
+    if (treelets) {
+        Treelet* list;
+        if (scratch.alloc(&list, (size_t)n / 3 + 1) || scratch.alloc(&treelet_words, 2)) return -1;
+        BVH_CUDA_TRY(cudaMemsetAsync(treelet_words, 0, 2 * sizeof(uint32_t), stream));
+        BVH_CUDA_TRY(cudaMemsetAsync(info, 0, 4 * sizeof(uint32_t), stream));
+        p.treelets = list; p.treelet_count = treelet_words; p.treelet_max = (uint32_t)TreeletCfg<T>::kMaxPrims;
+    }
     launch_hierarchy<T, K>(p, keys_a, out.prim_ids, leaf_src, mode, out.tris, stream);
     BVH_CUDA_TRY(cudaGetLastError());
 
-    const bool treelets = options.sah_treelets && n > 2;
-    if (treelets) {                                          // EXPERIMENTAL, see treelet_sah.cuh
-        Treelet* list; uint32_t* list_count;
-        if (scratch.alloc(&list, (size_t)n / 3 + 1) || scratch.alloc(&list_count, 1)) return -1;
-        BVH_CUDA_TRY(cudaMemsetAsync(list_count, 0, sizeof(uint32_t), stream));
-        BVH_CUDA_TRY(cudaMemsetAsync(info + 2, 0, 2 * sizeof(uint32_t), stream));
-        find_treelets_kernel<T, K><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(out.nodes, keys_a, n, list, list_count);
-        const uint32_t max_blocks = (uint32_t)sm_count * 5u, want = n / 3 + 1;
-        treelet_kernel<T><<<want < max_blocks ? want : max_blocks, TreeletCfg<T>::kMaxPrims, 0, stream>>>(
-            list, list_count, out.nodes, out.prim_ids, out.tris, leaf_src, centre_src, mode, p.min_leaf, p.max_leaf, info);
+    if (treelets) {
+        constexpr size_t smem = kTreeletWarps * sizeof(TreeletScratch<T, TreeletCfg<T>::kMaxPrims>);
+        auto kernel = treelet_kernel<T>;
+        static bool configured = false;                      // (per instantiation)
+        if (!configured) {
+            BVH_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+        int per_sm = 1;
+        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTreeletWarps * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        const uint32_t max_blocks = (uint32_t)(sm_count * per_sm), want = (n / 3 + kTreeletWarps) / kTreeletWarps;
+        kernel<<<want < max_blocks ? want : max_blocks, kTreeletWarps * 32, smem, stream>>>(
+            p.treelets, treelet_words, treelet_words + 1, out.nodes, out.prim_ids, out.tris, leaf_src, centre_src, mode,
+            p.min_leaf, p.max_leaf, info);
         BVH_CUDA_TRY(cudaGetLastError());
     }
 
-    uint32_t host_info[4] = { 0, 0, 0, 0 };
+    uint32_t host_info[4] = { 0, 0, 0, 0 }, host_treelets = 0;
     BVH_CUDA_TRY(cudaMemcpyAsync(host_info, info, sizeof(host_info), cudaMemcpyDeviceToHost, stream));
+    if (treelets) BVH_CUDA_TRY(cudaMemcpyAsync(&host_treelets, treelet_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     BVH_CUDA_TRY(cudaStreamSynchronize(stream));
     out.depth = host_info[0] + (treelets ? host_info[2] : 0u);
+    out.treelets = host_treelets;
+    out.morton_bits = key_bits;
+    out.quality = options.quality;
     if (make_wide_tree(out, stream)) return -1;
     out.compact = false;
     return 0;
@@ -547,9 +560,11 @@ int build_lbvh(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const T* 
     // first_id must fit Index<32,4>: 2n-1 <= 2^28-1 for float (index.h:39)
     if (sizeof(T) == 4 && 2 * (uint64_t)n > ((uint64_t)1 << 28)) { set_error("build: too many primitives for a 32-bit index"); return -1; }
     BuildOptions opts = options;
-    if (const char* e = std::getenv("BVH_B200_SAH_TREELETS")) opts.sah_treelets = std::atoi(e) != 0;   // experiments only
+    opts.sah_treelets = options.quality >= 1;               // DefaultBuilder::Quality Medium / High (default_builder.h:21)
+    const int forced_treelets = tunables().sah_treelets.load(), forced_bits = tunables().morton_bits.load();
+    if (forced_treelets >= 0) opts.sah_treelets = forced_treelets != 0;                 // A/B experiments only
     int bits = options.morton_bits;
-    if (const char* e = std::getenv("BVH_B200_MORTON_BITS")) bits = std::atoi(e);      // test hook: 30 or 63
+    if (forced_bits != 0) bits = forced_bits;                                           // test hook: 30 or 63
     if (bits == 0) bits = n >= (1u << 22) ? 63 : 30;
     int rc;
     if (bits <= 30) rc = build_with_key<T, uint32_t>(out, d_verts, d_bboxes, d_centers, n, opts, 30, stream);

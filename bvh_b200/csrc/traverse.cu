@@ -344,20 +344,6 @@ trace_persistent_kernel(TraceArgs<T> a) {
     }
 }
 
-// Tunables of the persistent kernel; environment overrides exist for experiments only.
-struct Tuning { uint32_t inner_budget; int variant; uint32_t watchdog; bool use_wide; };
-const Tuning& tuning() {
-    static const Tuning t = [] {
-        Tuning v { 12u, 1, 1u << 26, false };
-        if (const char* e = getenv("BVH_B200_USE_WIDE")) v.use_wide = atoi(e) != 0;
-        if (const char* e = getenv("BVH_B200_WATCHDOG")) v.watchdog = (uint32_t)atol(e);
-        if (const char* e = getenv("BVH_B200_INNER_BUDGET")) { long k = atol(e); v.inner_budget = k <= 0 ? 0xFFFFFFFFu : (uint32_t)k; }
-        if (const char* e = getenv("BVH_B200_VARIANT")) v.variant = atoi(e);
-        return v;
-    }();
-    return t;
-}
-
 // ---- lane-pair kernel ------------------------------------------------------------------------------
 // Two adjacent lanes serve ONE ray: in an inner step lane 0 of the pair fetches and tests the left
 // child, lane 1 the right child (one 256-bit load each, both from the same 64-byte block), and the two
@@ -710,16 +696,16 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     if (entries < 16) entries = 16;
     args.stack_entries = entries;
     args.next_ray = nullptr;
-    args.inner_budget = tuning().inner_budget;
-    args.watchdog = tuning().watchdog;
+    args.inner_budget = tunables().inner_budget.load();
+    args.watchdog = tunables().watchdog.load();
     args.full_mask = 0xFFFFFFFFu;
-    args.variant = (flags & kTracePair) ? 2 : ((flags & (kTraceNoTma | kTraceTma)) ? 0 : tuning().variant);
+    args.variant = (flags & kTracePair) ? 2 : ((flags & (kTraceNoTma | kTraceTma)) ? 0 : tunables().variant.load());
     // the wide (compressed 4-wide) path: float, canonical tie-break, fast slab test, no statistics
     args.wide = nullptr; args.wide_entries = 0;
     if constexpr (sizeof(T) == 4) {
         const bool explicit_binary = (flags & (kTracePair | kTraceNoTma | kTraceTma | kTraceSimple)) != 0;
         const bool order_sensitive = (flags & (kTraceLastVisited | kTraceRobust)) != 0 || d_ray_stats != nullptr;
-        const bool want_wide = !order_sensitive && ((flags & kTraceWide) || (!explicit_binary && tuning().use_wide));
+        const bool want_wide = !order_sensitive && ((flags & kTraceWide) || (!explicit_binary && (tunables().use_wide.load() > 0)));
         if (want_wide && !bvh.wide) {                       // derived on first use
             if (rebuild_wide(const_cast<DeviceBvh<T>&>(bvh), stream, true)) return -1;
         }
@@ -730,7 +716,7 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
             args.variant = 3;
         }
     }
-    args.use_tma = (flags & kTraceTma) ? true : ((flags & kTraceNoTma) ? false : tuning().variant == 1);
+    args.use_tma = (flags & kTraceTma) ? true : ((flags & kTraceNoTma) ? false : tunables().variant.load() == 1);
     const bool simple = (flags & kTraceSimple) != 0, stats = d_ray_stats != nullptr;
     if (!bvh.scratch) {
         void* p = nullptr;

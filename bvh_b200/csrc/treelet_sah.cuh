@@ -1,75 +1,37 @@
-// bvh_b200/csrc/treelet_sah.cuh — SAH rebuild of the bottom of the LBVH ("treelets").  EXPERIMENTAL: validated
-// on the CPU emulation only (tests/test_host_emulation.py); off unless BuildOptions::sah_treelets is set.
+// bvh_b200/csrc/treelet_sah.cuh — SAH rebuild of the bottom of the LBVH ("treelets"): the second build pass of
+// DefaultBuilder::Quality Medium and High (Low keeps the plain LBVH).
 //
-// Why: measured on the emulation, the 11-23 % more traversal steps the LBVH needs compared with
-// the reference's SAH trees come from the bottom levels: keeping the LBVH above and rebuilding every maximal
-// subtree of at most 256 primitives with the reference's sweep-SAH rule recovers the reference's step counts
-// on the soup and about half of the gap on the height-field, while a SAH top level over LBVH subtrees
-// recovers nothing.
+// Why: measured, the 11-23 % more traversal steps the LBVH needs compared with the reference's SAH
+// trees come from the bottom levels: keeping the LBVH above and rebuilding every maximal subtree of at most
+// kMaxPrims primitives with the reference's sweep-SAH rule recovers the reference's step counts on the soup and
+// about half of the gap on the height-field, while a SAH top level over LBVH subtrees recovers nothing.
 //
-// What: for every maximal LBVH subtree with at most kMaxPrims primitives (found from the sorted keys alone,
-// treelet_probe), one thread block rebuilds the subtree top-down with the greedy rule of the reference's
-// SweepSahBuilder / TopDownSahBuilder (sweep_sah_builder.h:57-139, top_down_sah_builder.h:74-131): primitives
-// sorted once along each axis, per node the split minimising area(L)*|L| + area(R)*|R| over the three axes
-// and all positions, leaf when no split beats area*(count - 1) and count <= max_leaf_size, median split on
-// the largest axis otherwise, stable partition of the other two orders, larger-area child first (SATO).
-// All nodes of one LEVEL of the treelet are processed together: the three orders keep each node's primitives in
-// one contiguous segment, and prefix / suffix boxes, split costs, minima and partitions are segmented scans
-// over the whole array.  The subtree is written into the node slots the LBVH subtree owned (pairs l .. r-1 of the
-// sorted range [l, r]), primitives are re-ordered inside [l, r] only, and the subtree's box is unchanged, so
-// nothing above the treelet moves.
+// What: every maximal LBVH subtree of 3..kMaxPrims primitives (listed by the bottom-up pass itself, build_core.cuh
+// merge_into_parent) is rebuilt top-down by ONE WARP with the greedy rule of the reference's SweepSahBuilder /
+// TopDownSahBuilder (sweep_sah_builder.h:57-139, top_down_sah_builder.h:74-131): primitives sorted once along each
+// axis, per node the split minimising area(L)*|L| + area(R)*|R| over the three axes and all positions, leaf when no
+// split beats area*(count - 1) and count <= max_leaf_size, median split on the largest axis otherwise, stable
+// partition of the other two orders, larger-area child first (SATO).  All nodes of one LEVEL of the treelet are
+// processed together: the three orders keep each node's primitives in one contiguous segment, and prefix / suffix
+// boxes, split costs, minima and partitions are segmented scans over the whole array.  The subtree is written into
+// the node slots the LBVH subtree owned (pairs l .. r-1 of the sorted range [l, r]), primitives are re-ordered
+// inside [l, r] only, and the subtree's box is unchanged, so nothing above the treelet moves.
 //
 // The algorithm is written as PHASES over array positions, parametrised by an execution policy: on the device a
-// phase is a block-strided loop followed by __syncthreads(), in the host emulation a plain loop — the same
-// source, the same arithmetic (Real<T> ops, no contraction), hence the same tree.
+// phase is a lane-strided loop of the warp followed by __syncwarp() (the scratch of a treelet lives in the warp's
+// slice of shared memory), in the host emulation a plain loop — the same source, the same arithmetic (Real<T> ops,
+// no contraction), hence the same tree.  (Round 1 ran one 256-thread block per 256-primitive treelet: ~540
+// __syncthreads-separated phases per treelet, 4.3 ms per million triangles on the B200; with 64-primitive treelets
+// a warp covers the positions in two strides and a phase costs a __syncwarp.)
 #pragma once
 
 #include "build_core.cuh"
 
 namespace bvhb200 {
 
-template <typename T> struct TreeletCfg { static constexpr int kMaxPrims = sizeof(T) == 4 ? 256 : 128; };
-
-struct Treelet { uint32_t slot, l, r; };     // device slot of the subtree's root record, sorted range [l, r]
-
-// ---- finding the treelet roots ----------------------------------------------------------------------
-// The LBVH is the Cartesian tree of the boundary "distances" (build_core.cuh: Delta): inner node p (the split
-// between sorted primitives p and p+1) covers the maximal range around the boundary in which every other
-// boundary is more similar.  Returns the number of primitives of node p and its range, or 0 as soon as the
-// range exceeds `limit` primitives.
-template <typename K>
-BVH_HD uint32_t treelet_range(const K* __restrict__ keys, uint32_t n, uint32_t p, uint32_t limit, uint32_t& l, uint32_t& r) {
-    const Delta<K> dp = delta_at(keys, p);
-    l = p; r = p + 1;
-    while (l > 0 && delta_less(delta_at(keys, l - 1), dp)) { --l; if (r - l + 1 > limit) return 0; }
-    while (r + 1 < n && delta_less(delta_at(keys, r), dp)) { ++r; if (r - l + 1 > limit) return 0; }
-    return r - l + 1;
-}
-
-// Is inner node p the root of a treelet (at most `limit` primitives, parent larger or absent)?  On success
-// fills `out` (the slot is found by looking at the parent's two child records, which the SATO swap may have
-// exchanged).  Nodes of fewer than three primitives are left alone (the LBVH pass already decided them by the
-// same rule).
-template <typename T, typename K>
-BVH_HD bool treelet_probe(const DevNode<T>* __restrict__ nodes, const K* __restrict__ keys, uint32_t n, uint32_t p,
-                          uint32_t limit, Treelet& out) {
-    using U = typename Real<T>::UInt;
-    uint32_t l, r;
-    const uint32_t count = treelet_range(keys, n, p, limit, l, r);
-    if (count < 3) return false;
-    out.l = l; out.r = r;
-    if (l == 0 && r == n - 1) { out.slot = 1; return true; }            // the whole tree is one treelet
-    uint32_t parent, side;
-    choose_parent(keys, n, l, r, parent, side);
-    uint32_t pl, pr;
-    if (treelet_range(keys, n, parent, limit, pl, pr) != 0) return false;     // the parent is small enough itself
-    const U as_inner = make_index<U>((U)(2 * (size_t)p + 1), 0), as_leaf = make_index<U>((U)l, count);
-    for (uint32_t s = 0; s < 2; ++s) {
-        const U index = nodes[child_slot(parent, s)].index;
-        if (index == as_inner || (count <= kMaxLeafPrims && index == as_leaf)) { out.slot = (uint32_t)child_slot(parent, s); return true; }
-    }
-    return false;                                                        // unreachable for a consistent tree
-}
+// kMaxPrims: largest treelet; kChunk: positions scanned sequentially by one iteration of the blocked scans
+// (kMaxPrims / 32: one chunk per lane).
+template <typename T> struct TreeletCfg { static constexpr int kMaxPrims = 64; static constexpr int kChunk = kMaxPrims / 32; };
 
 // ---- execution policies --------------------------------------------------------------------------------
 struct HostExec {
@@ -85,10 +47,10 @@ struct HostExecReversed {
     static void atomic_max(uint32_t* p, uint32_t v) { HostExec::atomic_max(p, v); }
 };
 #if defined(__CUDACC__)
-struct BlockExec {
+struct WarpExec {
     template <typename F> static __device__ __forceinline__ void phase(uint32_t n, F f) {
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) f(i);
-        __syncthreads();
+        for (uint32_t i = threadIdx.x & 31u; i < n; i += 32u) f(i);
+        __syncwarp();
     }
     static __device__ __forceinline__ uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
     static __device__ __forceinline__ void atomic_max(uint32_t* p, uint32_t v) { atomicMax(p, v); }
@@ -96,13 +58,12 @@ struct BlockExec {
 #endif
 
 // ---- scratch of one treelet (shared memory on the device) ------------------------------------------
-// Segmented scans are BLOCKED: a chunk of kTreeletChunk consecutive positions is scanned sequentially by one
+// Segmented scans are BLOCKED: a chunk of kChunk consecutive positions is scanned sequentially by one
 // iteration, the chunk aggregates by a short data-parallel scan, and the carry is applied per position —
 // O(n) work per scan instead of the O(n log n) of a flat data-parallel scan.
-constexpr int kTreeletChunk = 8;
-
 template <typename T, int S> struct TreeletScratch {
-    static constexpr int NC = S / kTreeletChunk;
+    static constexpr int kChunk = S / 32 > 0 ? S / 32 : 1;
+    static constexpr int NC = S / kChunk;
     T box[6][S];                         // per PRIMITIVE (local index): minx,maxx,miny,maxy,minz,maxz
     T centre[3][S];
     uint32_t old_ids[S];                 // prim_ids[l + i] before the rebuild
@@ -126,8 +87,8 @@ template <typename T, int S> struct TreeletScratch {
     uint8_t side[S];                     // per PRIMITIVE: 1 = goes to the left part
     uint32_t counters[4];                // [0] next pair, [1] live segments, [2] treelet depth, [3] longest live segment
 };
-static_assert(sizeof(TreeletScratch<float, TreeletCfg<float>::kMaxPrims>) <= 48 * 1024, "static shared memory");
-static_assert(sizeof(TreeletScratch<double, TreeletCfg<double>::kMaxPrims>) <= 48 * 1024, "static shared memory");
+static_assert(sizeof(TreeletScratch<float, TreeletCfg<float>::kMaxPrims>) <= 48 * 1024, "one warp's slice of shared memory");
+static_assert(sizeof(TreeletScratch<double, TreeletCfg<double>::kMaxPrims>) <= 48 * 1024, "one warp's slice of shared memory");
 
 // Monotone map of a scalar to an unsigned integer (negative values reversed below the positive ones): a total
 // order even when a centre is a NaN, so the rank sort below always yields a permutation.
@@ -155,7 +116,7 @@ BVH_HD void treelet_rebuild(TreeletScratch<T, S>& w, const Treelet& t, DevNode<T
                             uint32_t min_leaf, uint32_t max_leaf, uint32_t* __restrict__ info, uint32_t lbvh_depth) {
     using R = Real<T>;
     using U = typename R::UInt;
-    constexpr uint32_t C = kTreeletChunk;
+    constexpr uint32_t C = TreeletScratch<T, S>::kChunk;
     const uint32_t n = t.r - t.l + 1, l = t.l;
     const uint32_t nc = (n + C - 1) / C;                     // chunks in use
     const T inf = treelet_inf<T>();

@@ -60,6 +60,19 @@ enum bvh_intersect_flags {
                                         tie-break and fast slab test only — otherwise the binary kernels are used) */
 };
 
+/* What bvhNN_get_property reports about a handle. */
+enum bvh_property {
+    BVH_PROP_DEPTH        = 0,  /* longest chain of inner nodes below the root (traversal stack bound) */
+    BVH_PROP_NODE_SLOTS   = 1,  /* device node slots allocated (slot 0 is padding) */
+    BVH_PROP_MORTON_BITS  = 2,  /* 30 or 63; 0 for a tree uploaded from the host mirror */
+    BVH_PROP_QUALITY      = 3,  /* bvh_build_quality the GPU build ran with */
+    BVH_PROP_TREELETS     = 4,  /* bottom subtrees rebuilt by the SAH treelet pass */
+    BVH_PROP_WIDE_NODES   = 5,  /* nodes of the compressed 4-wide companion tree (0: not derived) */
+    BVH_PROP_LAST_KERNEL  = 6,  /* traversal kernel of the last batched call: 1 persistent+TMA, 2 persistent,
+                                   3 simple, 4 statistics, 5 lane-pair, 6 wide */
+    BVH_PROP_STREAM       = 7   /* the cudaStream_t the handle's work is ordered on */
+};
+
 /* ---- runtime ------------------------------------------------------------------------------- */
 BVH_API const char* bvh_last_error(void);
 BVH_API int bvh_cuda_device_count(void);
@@ -74,6 +87,14 @@ BVH_API void bvh_cuda_reset_stream(void);
 /* Pinned host memory for ray / hit buffers (so that host<->device copies run at PCIe speed). */
 BVH_API void* bvh_host_alloc(size_t bytes);
 BVH_API void bvh_host_free(void* ptr);
+/* The library allocates device memory from a private stream-ordered pool per GPU and keeps freed blocks cached
+ * in it (rebuilds never go back to the driver); this hands the cached blocks of `device` back. */
+BVH_API int bvh_cuda_trim(int device);
+/* Process-wide switches for experiments, A/B measurements and tests (the defaults are the measured best):
+ * "morton_bits" 0|30|63, "sah_treelets" -1|0|1, "hierarchy" 0|64|128|256, "e2e_chunks", "variant" 0|1,
+ * "use_wide" -1|0|1, "inner_budget", "wide_budget", "watchdog".  Initial values come from the BVH_B200_<NAME>
+ * environment variables, read once when the library is first used. */
+BVH_API int bvh_set_option(const char* name, long value);
 
 #define BVH_B200_DECLARE(T, S)                                                                          \
     /* Fused prep + build + triangle permutation from raw vertices (prim_count x 9: p0 p1 p2). */        \
@@ -104,7 +125,9 @@ BVH_API void bvh_host_free(void* ptr);
     /* Wait for the handle's stream. */                                                                 \
     BVH_API int bvh##S##_sync(struct bvh##S* bvh);                                                      \
     /* Longest chain of inner nodes below the root (the traversal stack bound). */                      \
-    BVH_API size_t bvh##S##_get_depth(struct bvh##S* bvh);
+    BVH_API size_t bvh##S##_get_depth(struct bvh##S* bvh);                                              \
+    /* enum bvh_property; (size_t)-1 for an unknown property or a failed upload of an edited mirror. */  \
+    BVH_API size_t bvh##S##_get_property(struct bvh##S* bvh, int property);
 
 BVH_B200_DECLARE(float, 3f)
 BVH_B200_DECLARE(double, 3d)

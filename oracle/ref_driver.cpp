@@ -45,6 +45,8 @@ constexpr unsigned kAnyHit      = 1u << 0;
 constexpr unsigned kRobust      = 1u << 1;
 constexpr unsigned kTieLowestId = 1u << 2;   // canonical, tree-independent tie-break
                                              // otherwise: reference example semantics, last visited wins
+constexpr unsigned kDynamic     = 1u << 8;   // pool workers claim 4096-ray blocks from a shared counter instead
+                                             // of the executor's static n/threads split (bench.py's CPU arm)
 
 template <typename T>
 struct Types {
@@ -187,7 +189,24 @@ double trace(const Accel<T>* accel, const T* rays, size_t m, unsigned flags, int
         // The reference ships no multithreaded ray loop; this is its own executor (executor.h:51-61)
         // applied to rays, the closest faithful "own multithreaded CPU path" (SURVEY §8d).
         bvh::v2::ParallelExecutor executor(*pool);
-        executor.for_each(0, m, body);
+        if (flags & kDynamic) {
+            // Same pool, same executor, but every worker claims blocks of consecutive rays until the batch is
+            // drained: a camera image has rows of very different cost, and a static split leaves most threads
+            // idle while the slowest chunk finishes (run-to-run spread of 4x on 128-thread hosts).
+            constexpr size_t kBlockRays = 4096;
+            std::atomic<size_t> next { 0 };
+            const size_t workers = pool->get_thread_count();
+            bvh::v2::ParallelExecutor one_task_per_worker(*pool, 1);      // (the default threshold of 1024 would run it serially)
+            one_task_per_worker.for_each(0, workers, [&] (size_t, size_t) {
+                for (;;) {
+                    const size_t b = next.fetch_add(kBlockRays, std::memory_order_relaxed);
+                    if (b >= m) break;
+                    body(b, b + kBlockRays < m ? b + kBlockRays : m);
+                }
+            });
+        } else {
+            executor.for_each(0, m, body);
+        }
     } else {
         body(0, m);
     }

@@ -65,7 +65,15 @@ class HostEmul:
     def _s(dtype):
         return "3f" if np.dtype(dtype) == np.float32 else "3d"
 
-    def build(self, tris=None, bboxes=None, centers=None, min_leaf=1, max_leaf=8, morton_bits=30):
+    def build(self, tris=None, bboxes=None, centers=None, min_leaf=1, max_leaf=8, morton_bits=30, quality=None):
+        """``quality`` mirrors the library: "low" = plain LBVH, "medium" / "high" = + SAH treelet pass; None keeps
+        whatever set_treelets() selected."""
+        if quality is not None:
+            self.set_treelets(quality != "low")
+            try:
+                return self.build(tris, bboxes, centers, min_leaf, max_leaf, morton_bits)
+            finally:
+                self.set_treelets(False)
         src = tris if tris is not None else bboxes
         dtype, n = src.dtype, src.shape[0]
         s = self._s(dtype)

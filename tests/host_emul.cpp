@@ -61,6 +61,9 @@ uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t 
     BuildParams<T> p;
     p.nodes = nodes; p.flags = flags.data(); p.info = info; p.n = n;
     p.min_leaf = min_leaf; p.max_leaf = max_leaf;
+    std::vector<Treelet> list((size_t)n / 3 + 1);
+    uint32_t list_count = 0;
+    if (g_treelets && n > 2) { p.treelets = list.data(); p.treelet_count = &list_count; p.treelet_max = (uint32_t)TreeletCfg<T>::kMaxPrims; }
     auto leaf_box = [&] (uint32_t i, T bmin[3], T bmax[3]) {
         const uint32_t id = order[i];
         if (verts) {
@@ -109,14 +112,11 @@ uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t 
             }
         }
     }
-    if (g_treelets && n > 1) {
-        // the experimental second pass (treelet_sah.cuh): rebuild every maximal subtree of <= kMaxPrims primitives
+    if (g_treelets && n > 2) {
+        // the second pass (treelet_sah.cuh): rebuild every maximal subtree of 3..kMaxPrims primitives, as listed by
+        // the bottom-up pass above
         constexpr int S = TreeletCfg<T>::kMaxPrims;
-        std::vector<Treelet> list;
-        for (uint32_t q = 0; q + 1 < n; ++q) {
-            Treelet t;
-            if (treelet_probe<T, K>(nodes, sorted.data(), n, q, (uint32_t)S, t)) list.push_back(t);
-        }
+        list.resize(list_count);
         auto scratch = std::make_unique<TreeletScratch<T, S>>();
         const T* leaf_src = verts ? verts : bboxes;
         for (const Treelet& t : list) {

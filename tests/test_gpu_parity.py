@@ -82,21 +82,23 @@ def test_reference_tree_on_gpu(gpu_lib, name):
         assert open(out, "rb").read() == g["ref_serialized"].tobytes()
 
 
+@pytest.mark.parametrize("quality", ["low", "high"])
 @pytest.mark.parametrize("kind,n,dtype", [("soup", 20000, np.float32), ("grid", 20000, np.float32), ("soup", 8000, np.float64)])
-def test_gpu_tree_is_a_valid_reference_bvh(gpu_lib, oracle, emul, kind, n, dtype):
+def test_gpu_tree_is_a_valid_reference_bvh(gpu_lib, oracle, emul, kind, n, dtype, quality):
     """Download the GPU-built tree through the reference accessors: structure invariants hold, boxes are
     what the reference's refit computes, it equals the host emulation's tree node for node, and the
     oracle (reference algorithm) traversing it agrees with the GPU bit for bit, counters included."""
     api = gpu_lib
     tris = scenes.make_mesh(kind, n, dtype=dtype)
-    bvh = api.Bvh.build_triangles(tris)
+    bvh = api.Bvh.build_triangles(tris, quality=quality)
+    assert (bvh.get_property("treelets") > 0) == (quality != "low")
     bounds, index_values, prim_ids = bvh.arrays()
     tree = oracle.from_arrays(bounds, index_values, prim_ids)
     assert oracle.check_invariants(tree, 8) == 0
     before = tree.arrays()[0]
     oracle.refit(tree)
     assert (tree.arrays()[0] == before).all()
-    etree = emul.build(tris=tris)
+    etree = emul.build(tris=tris, quality=quality)
     eb, ei = emul.compact(etree)
     assert eb.shape == bounds.shape and (eb == bounds).all() and (ei == index_values).all()
     assert (etree["prim_ids"] == prim_ids).all()
@@ -119,12 +121,15 @@ def test_gpu_tree_is_a_valid_reference_bvh(gpu_lib, oracle, emul, kind, n, dtype
 def test_wide_morton_keys_match_the_emulation(gpu_lib, emul, monkeypatch, dtype):
     """The 63-bit Morton path (64-bit keys, 8 radix passes; the automatic choice from 2^22 primitives on),
     forced at a size the host emulation handles: same tree node for node."""
-    monkeypatch.setenv("BVH_B200_MORTON_BITS", "63")
     tris = scenes.soup(30000, seed=9).astype(dtype)
-    bvh = gpu_lib.Bvh.build_triangles(tris)
-    monkeypatch.delenv("BVH_B200_MORTON_BITS")
+    gpu_lib.set_option("morton_bits", 63)
+    try:
+        bvh = gpu_lib.Bvh.build_triangles(tris)
+    finally:
+        gpu_lib.set_option("morton_bits", 0)
+    assert bvh.get_property("morton_bits") == 63
     bounds, index_values, prim_ids = bvh.arrays()
-    etree = emul.build(tris=tris, morton_bits=63)
+    etree = emul.build(tris=tris, morton_bits=63, quality="high")
     eb, ei = emul.compact(etree)
     assert eb.shape == bounds.shape and (eb == bounds).all() and (ei == index_values).all()
     assert (etree["prim_ids"] == prim_ids).all()
@@ -556,27 +561,28 @@ def test_gather_entry_point_on_one_gpu(gpu_lib, dtype, flags_name):
             assert (local.cpu().numpy() == expect).all()
 
 
-@pytest.mark.skipif(os.environ.get("BVH_B200_EXPERIMENTAL") != "1",
-                    reason="the SAH treelet pass has not been validated on hardware yet (set BVH_B200_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("kind,n,dtype", [("soup", 20000, np.float32), ("grid", 20000, np.float32), ("soup", 6000, np.float64),
-                                           ("soup", 200, np.float32), ("soup", 3, np.float32)])
-def test_experimental_sah_treelets_match_the_emulation(gpu_lib, emul, monkeypatch, kind, n, dtype):
-    """BVH_B200_SAH_TREELETS=1: the device runs the same phase code as the host emulation, so the compacted
-    trees must be identical and the traversal results equal to the plain LBVH's."""
+                                           ("soup", 200, np.float32), ("soup", 64, np.float32), ("soup", 3, np.float32)])
+def test_sah_treelets_match_the_emulation(gpu_lib, emul, kind, n, dtype):
+    """Quality Medium / High = LBVH + SAH treelet pass: the device runs the same phase code as the host
+    emulation, so the compacted trees must be identical, Medium and High build the same tree, and the traversal
+    results equal the plain LBVH's (Quality Low)."""
     api = gpu_lib
     tris = (scenes.soup(n, seed=7) if kind == "soup" else scenes.make_mesh(kind, n)).astype(dtype)
     rays = scenes.make_primary(kind, 128, 128, dtype=dtype)
-    plain = api.Bvh.build_triangles(tris)
-    monkeypatch.setenv("BVH_B200_SAH_TREELETS", "1")
-    bvh = api.Bvh.build_triangles(tris)
-    monkeypatch.delenv("BVH_B200_SAH_TREELETS")
+    plain = api.Bvh.build_triangles(tris, quality="low")
+    assert plain.get_property("treelets") == 0
+    bvh = api.Bvh.build_triangles(tris)                      # library default: Quality High
+    medium = api.Bvh.build_triangles(tris, quality="medium")
+    assert bvh.get_property("treelets") > 0 and bvh.get_property("quality") == 2
     bounds, index_values, prim_ids = bvh.arrays()
-    try:
-        emul.set_treelets(True)
-        etree = emul.build(tris=tris)
-    finally:
-        emul.set_treelets(False)
+    for x, y in zip(medium.arrays(), (bounds, index_values, prim_ids)):
+        assert (x == y).all()
+    etree = emul.build(tris=tris, quality="high")
+    assert emul.lib.emul_last_treelet_count() == bvh.get_property("treelets")
     eb, ei = emul.compact(etree)
     assert eb.shape == bounds.shape and (eb == bounds).all() and (ei == index_values).all()
     assert (etree["prim_ids"] == prim_ids).all() and bvh.depth == etree["depth"]
-    assert_hits_equal(hits_tuple(bvh.intersect_rays(rays)), hits_tuple(plain.intersect_rays(rays)), "treelets vs plain LBVH")
+    for flags in (api.KERNEL_TMA, api.KERNEL_WIDE, api.KERNEL_SIMPLE):
+        assert_hits_equal(hits_tuple(bvh.intersect_rays(rays, flags=flags)), hits_tuple(plain.intersect_rays(rays, flags=flags)),
+                          f"treelets vs plain LBVH ({flags})")

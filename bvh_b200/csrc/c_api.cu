@@ -16,9 +16,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "engine.h"
+#include "reinsertion.h"
 
 namespace bvhb200 {
 
@@ -627,6 +629,22 @@ template <typename T> Handle2<T>* load_nodes2(FILE* file) {
     return h;
 }
 
+// bvhNN_optimize (reference c_api/bvh_impl.h:223-233): with a pool the search runs on the pool's thread count
+// (0 = hardware concurrency, thread_pool.h:82-86), without one it is serial (SequentialExecutor).
+static size_t optimizer_threads(size_t requested) {
+    if (requested != 0) return requested;
+    const unsigned hw = std::thread::hardware_concurrency();
+    return hw ? hw : 1;
+}
+template <typename T, int kDim, typename NodeVec>
+bool optimize_nodes(NodeVec& nodes, double ratio, size_t iters, size_t threads) {
+    using NodeT = typename NodeVec::value_type;
+    try {
+        if (!Reinserter<T, kDim, NodeT>(nodes, threads).run((T)ratio, iters)) { set_error("optimize: the node array is not a well-formed tree"); return false; }
+    } catch (const std::exception& e) { set_error(std::string("optimize: ") + e.what()); return false; }
+    return true;
+}
+
 } // namespace bvhb200
 
 using namespace bvhb200;
@@ -682,6 +700,25 @@ BVH_EXPORT int bvh_cuda_trim(int device) {
 
 // The pool is an API token only: CUDA streams do the work that ThreadPool does in the reference.
 struct bvh_thread_pool { size_t thread_count; };
+static size_t pool_threads(const bvh_thread_pool* pool) { return pool ? optimizer_threads(pool->thread_count) : 1; }
+BVH_EXPORT int bvh_optimize_nodes(void* nodes, size_t node_count, int dim, int is_double, double ratio, size_t iters, size_t threads) {
+    if (!nodes && node_count) { set_error("optimize: null node array"); return -1; }
+    if (dim != 2 && dim != 3) { set_error("optimize: dim must be 2 or 3"); return -1; }
+    // the Reinserter works on a std::vector; the caller's array is copied in and out (host memory, O(node_count))
+    auto run = [&] (auto tag_node, auto tag_scalar, auto tag_dim) {
+        using NodeT = decltype(tag_node); using T = decltype(tag_scalar); constexpr int D = decltype(tag_dim)::value;
+        std::vector<NodeT> v(static_cast<NodeT*>(nodes), static_cast<NodeT*>(nodes) + node_count);
+        if (!optimize_nodes<T, D>(v, ratio, iters, optimizer_threads(threads))) return -1;
+        std::memcpy(nodes, v.data(), node_count * sizeof(NodeT));
+        return 0;
+    };
+    try {
+        if (dim == 3) return is_double ? run(HostNode<double>{}, double{}, std::integral_constant<int, 3>{})
+                                       : run(HostNode<float>{}, float{}, std::integral_constant<int, 3>{});
+        return is_double ? run(HostNode2<double>{}, double{}, std::integral_constant<int, 2>{})
+                         : run(HostNode2<float>{}, float{}, std::integral_constant<int, 2>{});
+    } catch (const std::exception& e) { set_error(std::string("optimize: ") + e.what()); return -1; }
+}
 BVH_EXPORT struct bvh_thread_pool* bvh_thread_pool_create(size_t thread_count) { return new bvh_thread_pool { thread_count }; }
 BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete pool; }
 
@@ -758,7 +795,11 @@ BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete p
         if (download_mirror(*h)) return;                                                                           \
         refit_mirror(*h); h->maybe_edited = true; h->synced_hash = 0;                                              \
     }                                                                                                              \
-    BVH_EXPORT void bvh##S##_optimize(struct bvh_thread_pool*, struct bvh##S*) {}                                  \
+    BVH_EXPORT void bvh##S##_optimize(struct bvh_thread_pool* pool, struct bvh##S* bvh) {                          \
+        auto h = H(T, bvh);                                                                                        \
+        if (!h || download_mirror(*h)) return;                                                                     \
+        if (optimize_nodes<T, 3>(h->nodes, 0.05, 3, pool_threads(pool))) { h->maybe_edited = true; h->synced_hash = 0; } \
+    }                                                                                                              \
     BVH_EXPORT void bvh##S##_intersect_ray_any(const struct bvh##S* bvh, const struct bvh_ray##S* ray, const struct CALLBACK* cb) { \
         auto h = HC(T, bvh); if (!download_mirror(*h)) intersect_mirror<T, true, false>(*h, reinterpret_cast<const T*>(ray), cb); } \
     BVH_EXPORT void bvh##S##_intersect_ray_any_robust(const struct bvh##S* bvh, const struct bvh_ray##S* ray, const struct CALLBACK* cb) { \
@@ -893,7 +934,9 @@ BVH_IMPL_3D(double, 3d, bvh_intersect_callbackd)
     BVH_EXPORT void bvh##S##_append_node(struct bvh##S* bvh) { H2(T, bvh)->nodes.emplace_back(); }                 \
     BVH_EXPORT void bvh##S##_remove_last_node(struct bvh##S* bvh) { if (!H2(T, bvh)->nodes.empty()) H2(T, bvh)->nodes.pop_back(); } \
     BVH_EXPORT void bvh##S##_refit(struct bvh##S* bvh) { refit_nodes<T, 2>(H2(T, bvh)->nodes); }                   \
-    BVH_EXPORT void bvh##S##_optimize(struct bvh_thread_pool*, struct bvh##S*) {}                                  \
+    BVH_EXPORT void bvh##S##_optimize(struct bvh_thread_pool* pool, struct bvh##S* bvh) {                          \
+        if (bvh) optimize_nodes<T, 2>(H2(T, bvh)->nodes, 0.05, 3, pool_threads(pool));                             \
+    }                                                                                                              \
     BVH_EXPORT void bvh##S##_intersect_ray_any(const struct bvh##S* bvh, const struct bvh_ray##S* ray, const struct CALLBACK* cb) { \
         intersect_nodes<T, true, false, 2>(HC2(T, bvh)->nodes, reinterpret_cast<const T*>(ray), cb); }            \
     BVH_EXPORT void bvh##S##_intersect_ray_any_robust(const struct bvh##S* bvh, const struct bvh_ray##S* ray, const struct CALLBACK* cb) { \

@@ -788,12 +788,22 @@ public:
     }
 };
 
-/// Kept so that code calling the optimizer still compiles; the GPU-built tree is returned unchanged.
+/// Subtree reinsertion (reference reinsertion_optimizer.h): runs in the library on the caller's node array
+/// (bvh_optimize_nodes, include/bvh_b200.h) — host work, the tree is host data.
 template <typename Node>
 struct ReinsertionOptimizer {
-    struct Config { typename Node::Scalar batch_size_ratio = typename Node::Scalar(0.05); size_t max_iter_count = 3; };
-    static void optimize(ThreadPool&, Bvh<Node>&, const Config& = {}) {}
-    static void optimize(Bvh<Node>&, const Config& = {}) {}
+    using Scalar = typename Node::Scalar;
+    struct Config { Scalar batch_size_ratio = Scalar(0.05); size_t max_iter_count = 3; };
+    static void optimize(ThreadPool& pool, Bvh<Node>& bvh, const Config& config = {}) { run(bvh, config, pool.get_thread_count()); }
+    static void optimize(Bvh<Node>& bvh, const Config& config = {}) { run(bvh, config, 1); }
+private:
+    static void run(Bvh<Node>& bvh, const Config& config, size_t threads) {
+        static_assert(Node::index_bits == sizeof(Scalar) * CHAR_BIT && Node::prim_count_bits == 4 && std::is_trivially_copyable_v<Node>,
+                      "the library's optimizer supports the default index layout");
+        if (bvh_optimize_nodes(bvh.nodes.data(), bvh.nodes.size(), int(Node::dimension), sizeof(Scalar) == 8,
+                               double(config.batch_size_ratio), config.max_iter_count, threads ? threads : 1))
+            throw std::runtime_error(std::string("bvh::v2::ReinsertionOptimizer: ") + bvh_last_error());
+    }
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -95,6 +95,13 @@ BVH_API int bvh_cuda_trim(int device);
  * "use_wide" -1|0|1, "inner_budget", "wide_budget", "watchdog".  Initial values come from the BVH_B200_<NAME>
  * environment variables, read once when the library is first used. */
 BVH_API int bvh_set_option(const char* name, long value);
+/* Subtree reinsertion (reference ReinsertionOptimizer::optimize, reinsertion_optimizer.h:27-30,218-267) on a
+ * caller-owned node array in the reference layout: node_count nodes of Node<float|double, dim> (2*dim bounds as
+ * [min0,max0,...] + packed index; 20 / 28 / 40 / 56 bytes), root at 0.  This is what bvhNN_optimize runs on the
+ * handle's host mirror and what bvh::v2::ReinsertionOptimizer of <bvh/v2/reinsertion_optimizer.h> calls; it is
+ * host work by contract (the tree is host data) and needs no GPU.  threads = 0: all hardware threads, 1: serial. */
+BVH_API int bvh_optimize_nodes(void* nodes, size_t node_count, int dim, int is_double,
+                               double batch_size_ratio, size_t max_iter_count, size_t threads);
 
 #define BVH_B200_DECLARE(T, S)                                                                          \
     /* Fused prep + build + triangle permutation from raw vertices (prim_count x 9: p0 p1 p2). */        \

@@ -68,8 +68,10 @@ def parse_args():
     ap.add_argument("--kernel", default="auto", choices=["auto", "persistent", "wide", "simple"],
                     help="auto: the library's default choice for the flags of the config")
     ap.add_argument("--chunks", type=int, default=4, help="NCCL gather chunks per step when N > 1 and --gather nccl")
-    ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "peer", "nccl"],
-                    help="N > 1: fused peer-memory gather (multicast / peer stores) or NCCL all-gather")
+    ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "peer", "direct", "nccl"],
+                    help="N > 1: fused gather inside the traversal kernel — peer (= auto): a warp stages 32 records in shared memory and "
+                         "bulk-copies them to every rank; direct: one 16-byte store per record and rank; multicast: one multimem.st per "
+                         "record — or NCCL all-gather")
     ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind the rank to its GPU's NUMA node")
     return ap.parse_args()
 
@@ -439,10 +441,16 @@ def main():
     if world > 1 and args.gather != "nccl":
         try:
             from bvh_b200.multi_gpu import FusedGatherTracer
-            tracer = FusedGatherTracer(bvh, rays, hit_words, flags=api.DEVICE_POINTERS | base_flags | kflag, mode=args.gather)
-            gather_desc = (f"fused in the traversal kernel: hit records staged per warp and stored into all {world} ranks' symmetric-memory "
-                           f"buffers ({'multimem stores via the NVSwitch multicast address' if tracer.mode == 'multicast' else 'NVLink peer stores'}), "
-                           "symmetric-memory barrier per step")
+            if args.gather == "direct":
+                api.set_option("gather_staging", 0)
+            tracer = FusedGatherTracer(bvh, rays, hit_words, flags=api.DEVICE_POINTERS | base_flags | kflag,
+                                       mode="peer" if args.gather == "direct" else args.gather)
+            how = ("one multimem.st per record through the NVSwitch multicast address" if tracer.mode == "multicast" else
+                   "one 16-byte NVLink peer store per record and rank" if args.gather == "direct" else
+                   "each warp stages the records of 32 consecutive rays in shared memory and sends the 512-byte block to every rank "
+                   "with one cp.async.bulk (shared -> peer global over NVLink)")
+            gather_desc = (f"fused in the traversal kernel into all {world} ranks' symmetric-memory buffers (double-buffered): {how}; "
+                           "one symmetric-memory barrier per step")
         except Exception as exc:                 # no symmetric memory on this box: NCCL all-gather instead
             if args.gather != "auto":
                 raise
@@ -468,6 +476,8 @@ def main():
         ends[k].record()
     e1.record()
     barrier()
+    if hasattr(tracer, "check"):
+        tracer.check()                           # a fired kernel watchdog means stale records: fail, do not report
     clocks = sampler.summary()
     total_ms = max_over_ranks([e0.elapsed_time(e1)])[0]
     ms_per_step = total_ms / args.steps

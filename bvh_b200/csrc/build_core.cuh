@@ -147,6 +147,10 @@ template <typename T> struct BuildParams {
     Treelet* treelets = nullptr;
     uint32_t* treelet_count = nullptr;
     uint32_t treelet_max = 0;
+    // Liveness of the sibling pairs (pair p = the two children of split position p, reference indices 2p+1 and
+    // 2p+2): initialised to 1 for every p; a merge that collapses its subtree into a leaf clears the pairs the
+    // subtree owned.  The compaction pass (lbvh_build.cu compact_tree) keeps exactly the live pairs.  nullptr: off.
+    uint32_t* alive = nullptr;
 };
 
 template <typename T> BVH_HD void append_treelet(const BuildParams<T>& p, uint32_t slot, uint32_t l, uint32_t r) {
@@ -172,6 +176,19 @@ template <typename T> BVH_HD void write_node(DevNode<T>* dst, const T bmin[3], c
 #else
     *dst = n;
 #endif
+}
+
+// Compaction (lbvh_build.cu compact_* kernels; tests/host_emul.cpp): pair p moves to pair rank[p] = number of live
+// pairs before it, so an inner node whose children sit at reference indices 2p+1, 2p+2 now points at 2*rank[p]+1;
+// the spare word (cost + depth while building) is cleared.
+template <typename T> BVH_HD DevNode<T> compact_remap(DevNode<T> n, const uint32_t* __restrict__ rank) {
+    using U = typename Real<T>::UInt;
+    if (index_count(n.index) == 0) {
+        const uint32_t pair = (uint32_t)((index_first(n.index) - 1) >> 1);
+        n.index = make_index<U>((U)(2 * (size_t)rank[pair] + 1), 0);
+    }
+    n.pad = 0;
+    return n;
 }
 
 // Memory-ordering hooks: the device version uses __threadfence / atomicExch / L2 loads; the host
@@ -274,6 +291,10 @@ template <typename T> BVH_HD bool merge_into_parent(const BuildParams<T>& p, Cli
     const T leaf_cost = R::mul(area, (T)count);                   // get_leaf_cost, split_heuristic.h:30-33
     const uint32_t sub_depth = (s.depth > sib_depth ? s.depth : sib_depth) + 1;
     if (count <= p.max_leaf && (count <= p.min_leaf || leaf_cost <= split_cost)) {
+        if (p.alive) {                                      // the pairs of the collapsed subtree are dead
+            if (s.depth == 0 && sib_depth == 0) p.alive[parent] = 0;            // both children were leaves: only this pair
+            else for (uint32_t q = s.l; q < s.r; ++q) p.alive[q] = 0;
+        }
         s.index = make_index<U>((U)s.l, count);             // collapse the subtree into one leaf
         s.cost = leaf_cost; s.depth = 0;
     } else {

@@ -48,6 +48,7 @@ Tunables& tunables() {
         const long wbudget = env("BVH_B200_WIDE_BUDGET", 4);
         t.wide_budget = wbudget <= 0 ? 0xFFFFFFFFu : (uint32_t)wbudget;
         t.watchdog = (uint32_t)env("BVH_B200_WATCHDOG", 1l << 26);
+        t.gather_staging = (int)env("BVH_B200_GATHER_STAGING", 1);
     });
     return t;
 }
@@ -182,47 +183,31 @@ template <typename T> uint64_t mirror_hash(const Handle<T>& h) {
     return hash_bytes(h.prim_ids.data(), h.prim_ids.size() * sizeof(size_t), a);
 }
 
-// Device -> mirror.  The device array may contain dead slots (subtrees collapsed into leaves by the
-// builder); the mirror must be a dense array in which every node is reachable (the reference's
-// refit / reinsertion code walks all of `nodes`, bvh.h:184-218), so live nodes are re-emitted in
-// depth-first order: root at 0, children of a node adjacent, left child at an odd index (bvh.h:34-54).
+// Device -> mirror.  The device array is dense and in the reference's numbering (root at 0, children of a node
+// adjacent, left child at an odd index, bvh.h:34-54), shifted by one slot: the export kernels strip the padding
+// on the device and the records land in the mirror with one copy per array.
 template <typename T> int download_mirror(Handle<T>& h) {
-    using U = typename Real<T>::UInt;
     std::lock_guard<std::mutex> lock(h.mirror_mutex);       // concurrent bvhNN_intersect_ray* callers (bvh_impl.h:244)
     if (h.host_valid) return 0;
     if (!h.device_valid) { set_error("handle holds no BVH"); return -1; }
     BVH_ON_DEVICE(h.device);
-    std::vector<DevNode<T>> dev_nodes(h.dev.node_slots);
-    std::vector<uint32_t> dev_ids(h.dev.prim_count);
-    BVH_CUDA_TRY(cudaMemcpyAsync(dev_nodes.data(), h.dev.nodes, dev_nodes.size() * sizeof(DevNode<T>), cudaMemcpyDeviceToHost, h.stream));
-    BVH_CUDA_TRY(cudaMemcpyAsync(dev_ids.data(), h.dev.prim_ids, dev_ids.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, h.stream));
-    BVH_CUDA_TRY(cudaStreamSynchronize(h.stream));
-
-    h.nodes.clear();
-    h.nodes.reserve(2 * (size_t)h.dev.prim_count);
-    auto emit = [&] (const DevNode<T>& src) {
-        HostNode<T> n;
-        std::memcpy(n.bounds, src.bounds, sizeof(n.bounds));
-        n.index = src.index;
-        h.nodes.push_back(n);
-    };
-    emit(dev_nodes[1]);
-    std::vector<size_t> stack;                         // destination indices of inner nodes still to expand
-    if (index_count(h.nodes[0].index) == 0) stack.push_back(0);
-    while (!stack.empty()) {
-        const size_t dst = stack.back();
-        stack.pop_back();
-        const size_t first_src = (size_t)index_first(h.nodes[dst].index);     // reference index of the left child
-        const size_t first_dst = h.nodes.size();
-        emit(dev_nodes[first_src + 1]);
-        emit(dev_nodes[first_src + 2]);
-        h.nodes[dst].index = make_index<U>((U)first_dst, 0);
-        // right first so that the left subtree is laid out right after its parent pair
-        if (index_count(h.nodes[first_dst + 1].index) == 0) stack.push_back(first_dst + 1);
-        if (index_count(h.nodes[first_dst + 0].index) == 0) stack.push_back(first_dst + 0);
+    static_assert(sizeof(size_t) == sizeof(unsigned long long), "prim ids are copied as 64-bit words");
+    const size_t node_count = h.dev.node_slots - 1, prim_count = h.dev.prim_count;
+    void* d_nodes = nullptr; void* d_ids = nullptr;
+    if (device_alloc(&d_nodes, node_count * sizeof(HostNode<T>), h.stream)) return -1;
+    if (device_alloc(&d_ids, prim_count * sizeof(unsigned long long), h.stream)) { device_free(d_nodes, h.stream); return -1; }
+    int rc = export_reference_arrays(h.dev, d_nodes, static_cast<unsigned long long*>(d_ids), h.stream);
+    if (!rc) {
+        try { h.nodes.resize(node_count); h.prim_ids.resize(prim_count); }
+        catch (const std::exception&) { set_error("download: out of host memory"); rc = -1; }
     }
-    h.nodes.shrink_to_fit();
-    h.prim_ids.assign(dev_ids.begin(), dev_ids.end());
+    cudaError_t err = cudaSuccess;
+    if (!rc) err = cudaMemcpyAsync(h.nodes.data(), d_nodes, node_count * sizeof(HostNode<T>), cudaMemcpyDeviceToHost, h.stream);
+    if (!rc && err == cudaSuccess) err = cudaMemcpyAsync(h.prim_ids.data(), d_ids, prim_count * sizeof(size_t), cudaMemcpyDeviceToHost, h.stream);
+    if (!rc && err == cudaSuccess) err = cudaStreamSynchronize(h.stream);
+    device_free(d_nodes, h.stream); device_free(d_ids, h.stream);
+    if (rc) return -1;
+    if (err != cudaSuccess) { set_error(std::string("download: ") + cudaGetErrorString(err)); return -1; }
     h.host_valid = true;
     h.maybe_edited = false;
     h.synced_ids_hash = ids_hash(h);
@@ -687,6 +672,7 @@ BVH_EXPORT int bvh_set_option(const char* name, long value) {
     else if (n == "inner_budget") t.inner_budget = value <= 0 ? 0xFFFFFFFFu : (uint32_t)value;
     else if (n == "wide_budget") t.wide_budget = value <= 0 ? 0xFFFFFFFFu : (uint32_t)value;
     else if (n == "watchdog") t.watchdog = (uint32_t)value;
+    else if (n == "gather_staging") t.gather_staging = (int)value;
     else { set_error("set_option: unknown option " + n); return -1; }
     return 0;
 }

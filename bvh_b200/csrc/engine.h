@@ -47,6 +47,7 @@ struct Tunables {
     std::atomic<uint32_t> inner_budget { 12 };  // inner steps per lane per round
     std::atomic<uint32_t> wide_budget { 4 };    // same for the wide kernel
     std::atomic<uint32_t> watchdog { 1u << 26 };
+    std::atomic<int> gather_staging { 1 };      // fused gather: 1 warp-aggregated bulk stores, 0 one store per record and rank
 };
 Tunables& tunables();
 
@@ -68,7 +69,7 @@ template <typename T> struct DeviceBvh {
     uint32_t* prim_ids = nullptr;       // prim_ids[i] = original id of BVH-order primitive i
     DevTri<T>* tris = nullptr;          // nullptr until triangles are attached
     uint32_t depth = 0;                 // longest chain of inner nodes below the root (stack bound)
-    bool compact = false;               // true when every slot 1..node_slots-1 is a live node
+    bool compact = false;               // every slot 1..node_slots-1 is a live node (always true once a build / upload returned)
     // two device words owned by the traversal: [0] the persistent kernels' ray cursor, [1] a sticky status
     // word set by their watchdog (allocated on first use)
     mutable unsigned long long* scratch = nullptr;
@@ -109,6 +110,11 @@ int attach_triangles(DeviceBvh<T>& bvh, const T* d_verts, cudaStream_t stream);
 // triangles, inner boxes recomputed bottom-up (reference Bvh::refit, bvh.h:184-218).
 template <typename T>
 int refit_triangles(DeviceBvh<T>& bvh, const T* d_verts, cudaStream_t stream);
+
+// Writes the tree in the reference's own layout into device buffers the caller copies to the host: node_slots - 1
+// records of Node<T,3> (7 words each) and prim_count 64-bit primitive ids.  The device tree must be dense.
+template <typename T>
+int export_reference_arrays(const DeviceBvh<T>& bvh, void* d_nodes_out, unsigned long long* d_ids_out, cudaStream_t stream);
 
 template <typename T> void release(DeviceBvh<T>& bvh, cudaStream_t stream);
 

@@ -105,7 +105,7 @@ centre_bounds_kernel(const T* __restrict__ src, uint32_t n, int mode, MinMax3<T>
 template <typename T, typename K>
 __global__ void __launch_bounds__(kBlock)
 morton_kernel(const T* __restrict__ src, uint32_t n, int mode, const MinMax3<T>* __restrict__ partials,
-              uint32_t num_partials, K* __restrict__ keys, int* __restrict__ flags) {
+              uint32_t num_partials, K* __restrict__ keys, int* __restrict__ flags, uint32_t* __restrict__ alive) {
     using R = Real<T>;
     __shared__ MinMax3<T> warp_part[kBlock / 32];
     __shared__ GridXform<T> xform;
@@ -153,7 +153,7 @@ morton_kernel(const T* __restrict__ src, uint32_t n, int mode, const MinMax3<T>*
             for (int k = 0; k < 3; ++k) c[k] = __ldg(src + 3 * (size_t)i + k);
         }
         keys[i] = morton_key<T, K>(c, g);
-        if (i + 1 < n) flags[i] = -1;
+        if (i + 1 < n) { flags[i] = -1; alive[i] = 1u; }
     }
 }
 
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(kTreeletWarps * 32)
 treelet_kernel(const Treelet* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t* __restrict__ cursor,
                DevNode<T>* __restrict__ nodes, uint32_t* __restrict__ prim_ids, DevTri<T>* __restrict__ tris,
                const T* __restrict__ leaf_src, const T* __restrict__ centre_src, int leaf_mode, uint32_t min_leaf,
-               uint32_t max_leaf, uint32_t* __restrict__ info) {
+               uint32_t max_leaf, uint32_t* __restrict__ info, uint32_t* __restrict__ alive) {
     constexpr int S = TreeletCfg<T>::kMaxPrims;
     extern __shared__ __align__(16) unsigned char treelet_smem[];
     TreeletScratch<T, S>& scratch = reinterpret_cast<TreeletScratch<T, S>*>(treelet_smem)[threadIdx.x >> 5];
@@ -279,9 +279,139 @@ treelet_kernel(const Treelet* __restrict__ list, const uint32_t* __restrict__ li
         if ((threadIdx.x & 31u) == 0) i = atomicAdd(cursor, 1u);
         i = __shfl_sync(0xFFFFFFFFu, i, 0);
         if (i >= count) break;
-        treelet_rebuild<T, S, WarpExec>(scratch, list[i], nodes, prim_ids, tris, leaf_src, centre_src, leaf_mode, min_leaf, max_leaf, info, lbvh_depth);
+        treelet_rebuild<T, S, WarpExec>(scratch, list[i], nodes, prim_ids, tris, leaf_src, centre_src, leaf_mode, min_leaf, max_leaf, info, lbvh_depth, alive);
         __syncwarp();
     }
+}
+
+// ---- compaction of the node array ---------------------------------------------------------------------------
+// The bottom-up pass numbers the sibling pairs by split position (pair p at reference indices 2p+1, 2p+2) and
+// leaves dead pairs behind: the descendants of every subtree the SAH rule collapsed into a leaf, and the pairs a
+// rebuilt treelet no longer uses.  This pass keeps the live pairs, in the same (Morton) order: pair p moves to
+// pair rank(p) = number of live pairs before it, child references are renumbered, the spare word is cleared.
+// The result is the reference's dense array (every node reachable, bvh.h:17-23) shifted by one slot: what the
+// traversal reads (half the footprint, neighbouring lines hold neighbouring subtrees), what refit walks and what
+// the host mirror receives with one copy.  Three small kernels: live pairs per tile, scan of the tile counts,
+// ranks + scatter.
+constexpr int kCompactItems = 8;
+constexpr int kCompactTile = kBlock * kCompactItems;                // 2048 pairs per block
+
+__global__ void __launch_bounds__(kBlock)
+compact_count_kernel(const uint32_t* __restrict__ alive, uint32_t pairs, uint32_t* __restrict__ tile_counts) {
+    __shared__ uint32_t warp_sums[kBlock / 32];
+    uint32_t local = 0;
+    const uint32_t base = blockIdx.x * (uint32_t)kCompactTile;
+    #pragma unroll
+    for (int k = 0; k < kCompactItems; ++k) {
+        const uint32_t i = base + k * kBlock + threadIdx.x;
+        if (i < pairs) local += alive[i];
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xFFFFFFFFu, local, o);
+    if ((threadIdx.x & 31u) == 0) warp_sums[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < kBlock / 32; ++w) total += warp_sums[w];
+        tile_counts[blockIdx.x] = total;
+    }
+}
+
+// One block: exclusive scan of the tile counts in place; the total goes to info[3].
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(uint32_t* __restrict__ tile_counts, uint32_t tiles, uint32_t* __restrict__ info) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < tiles; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < tiles ? tile_counts[i] : 0u;
+        uint32_t incl = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (unsigned)o) incl += x; }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = warp_sums[lane];
+            uint32_t wi = w;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= (unsigned)o) wi += x; }
+            warp_sums[lane] = wi - w;                                // exclusive over the warps
+        }
+        __syncthreads();
+        const uint32_t before = carry + warp_sums[warp] + incl - v;
+        if (i < tiles) tile_counts[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) info[3] = carry;
+}
+
+// rank[p] = number of live pairs before p (written for every p: the scatter below looks up its children's).
+__global__ void __launch_bounds__(kBlock)
+compact_rank_kernel(const uint32_t* __restrict__ alive, uint32_t pairs, const uint32_t* __restrict__ tile_offsets,
+                    uint32_t* __restrict__ rank) {
+    __shared__ uint32_t warp_sums[kBlock / 32];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // thread t owns kCompactItems CONSECUTIVE pairs, so that its local prefix is a plain running sum
+    const uint32_t first = blockIdx.x * (uint32_t)kCompactTile + threadIdx.x * kCompactItems;
+    uint32_t a[kCompactItems], local = 0;
+    #pragma unroll
+    for (int k = 0; k < kCompactItems; ++k) { a[k] = first + k < pairs ? alive[first + k] : 0u; local += a[k]; }
+    uint32_t incl = local;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= (unsigned)o) incl += x; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t before = tile_offsets[blockIdx.x] + incl - local;
+    for (unsigned w = 0; w < warp; ++w) before += warp_sums[w];
+    #pragma unroll
+    for (int k = 0; k < kCompactItems; ++k) { if (first + k < pairs) rank[first + k] = before; before += a[k]; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+compact_scatter_kernel(const DevNode<T>* __restrict__ src, DevNode<T>* __restrict__ dst, const uint32_t* __restrict__ alive,
+                       const uint32_t* __restrict__ rank, uint32_t pairs) {
+    const uint32_t p = blockIdx.x * kBlock + threadIdx.x;
+    if (p == 0) {                                                    // slot 0 is padding, slot 1 the root
+        DevNode<T> zero;
+        for (int k = 0; k < 6; ++k) zero.bounds[k] = (T)0;
+        zero.index = 0; zero.pad = 0;
+        dst[0] = zero;
+        dst[1] = compact_remap(src[1], rank);
+    }
+    if (p >= pairs || alive[p] == 0u) return;
+    const size_t from = child_slot(p, 0), to = child_slot(rank[p], 0);
+    const DevNode<T> left = compact_remap(src[from], rank), right = compact_remap(src[from + 1], rank);
+    const uint4* l4 = reinterpret_cast<const uint4*>(&left);
+    const uint4* r4 = reinterpret_cast<const uint4*>(&right);
+    uint4* d = reinterpret_cast<uint4*>(dst + to);
+    constexpr int kParts = (int)(sizeof(DevNode<T>) / 16);
+    #pragma unroll
+    for (int k = 0; k < kParts; ++k) { d[k] = l4[k]; d[kParts + k] = r4[k]; }
+}
+
+// ---- export to the reference's layout (host mirror) ---------------------------------------------------------
+// The dense device array is the reference's node array shifted by one slot and padded by one word per node; this
+// writes the reference's own records (Node<T,3>: six bounds + index, 7 words of 4 / 8 bytes, node.h:31-37) and
+// size_t primitive ids (bvh.h:22), one word per thread (coalesced), ready for ONE device-to-host copy each.
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+export_nodes_kernel(const DevNode<T>* __restrict__ nodes, size_t node_count, typename Real<T>::UInt* __restrict__ out) {
+    using U = typename Real<T>::UInt;
+    const size_t w = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (w >= node_count * 7) return;
+    const size_t node = w / 7, k = w - node * 7;
+    out[w] = reinterpret_cast<const U*>(nodes + node + 1)[k];
+}
+__global__ void __launch_bounds__(kBlock)
+export_ids_kernel(const uint32_t* __restrict__ ids, size_t n, unsigned long long* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i < n) out[i] = ids[i];
 }
 
 template <typename T>
@@ -485,24 +615,23 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     const uint32_t num_tiles = (n + kRsTile - 1) / kRsTile;
 
     MinMax3<T>* partials; K* keys_a; K* keys_b; uint32_t* vals_b; uint32_t* tile_hist; int* flags;
-    uint32_t* info;
+    uint32_t* info; uint32_t* alive; DevNode<T>* sparse;
     if (scratch.alloc(&partials, grid) || scratch.alloc(&keys_a, n) || scratch.alloc(&keys_b, n) ||
         scratch.alloc(&vals_b, n) || scratch.alloc(&tile_hist, (size_t)num_tiles * kRsBins + kRsBins) ||
-        scratch.alloc(&flags, n) || scratch.alloc(&info, 4))
+        scratch.alloc(&flags, n) || scratch.alloc(&info, 4) || scratch.alloc(&alive, n) ||
+        scratch.alloc(&sparse, 2 * (size_t)n))          // slot 0 padding + 2n-1 nodes numbered by split position
         return -1;
 
     out.prim_count = n;
-    out.node_slots = 2 * (size_t)n;                     // slot 0 padding + 2n-1 reference nodes
-    if (device_alloc(reinterpret_cast<void**>(&out.nodes), out.node_slots * sizeof(DevNode<T>), stream)) return -1;
     if (device_alloc(reinterpret_cast<void**>(&out.prim_ids), (size_t)n * sizeof(uint32_t), stream)) return -1;
     if (d_verts && device_alloc(reinterpret_cast<void**>(&out.tris), (size_t)n * sizeof(DevTri<T>), stream)) return -1;
 
     centre_bounds_kernel<T><<<grid, kBlock, 0, stream>>>(centre_src, n, mode, partials);
-    morton_kernel<T, K><<<grid, kBlock, 0, stream>>>(centre_src, n, mode, partials, grid, keys_a, flags);
+    morton_kernel<T, K><<<grid, kBlock, 0, stream>>>(centre_src, n, mode, partials, grid, keys_a, flags, alive);
     BVH_CUDA_TRY(radix_sort_pairs<K>(keys_a, out.prim_ids, keys_b, vals_b, tile_hist, n, key_bits, stream));
 
     BuildParams<T> p;
-    p.nodes = out.nodes; p.flags = flags; p.info = info; p.n = n;
+    p.nodes = sparse; p.flags = flags; p.info = info; p.n = n; p.alive = alive;
     p.min_leaf = options.min_leaf < 1 ? 1 : options.min_leaf;
     p.max_leaf = options.max_leaf > kMaxLeafPrims ? kMaxLeafPrims : (options.max_leaf < 1 ? 1 : options.max_leaf);
     if (p.min_leaf > p.max_leaf) p.min_leaf = p.max_leaf;
@@ -513,9 +642,9 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
         Treelet* list;
         if (scratch.alloc(&list, (size_t)n / 3 + 1) || scratch.alloc(&treelet_words, 2)) return -1;
         BVH_CUDA_TRY(cudaMemsetAsync(treelet_words, 0, 2 * sizeof(uint32_t), stream));
-        BVH_CUDA_TRY(cudaMemsetAsync(info, 0, 4 * sizeof(uint32_t), stream));
         p.treelets = list; p.treelet_count = treelet_words; p.treelet_max = (uint32_t)TreeletCfg<T>::kMaxPrims;
     }
+    BVH_CUDA_TRY(cudaMemsetAsync(info, 0, 4 * sizeof(uint32_t), stream));
     launch_hierarchy<T, K>(p, keys_a, out.prim_ids, leaf_src, mode, out.tris, stream);
     BVH_CUDA_TRY(cudaGetLastError());
 
@@ -532,8 +661,21 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
         if (per_sm < 1) per_sm = 1;
         const uint32_t max_blocks = (uint32_t)(sm_count * per_sm), want = (n / 3 + kTreeletWarps) / kTreeletWarps;
         kernel<<<want < max_blocks ? want : max_blocks, kTreeletWarps * 32, smem, stream>>>(
-            p.treelets, treelet_words, treelet_words + 1, out.nodes, out.prim_ids, out.tris, leaf_src, centre_src, mode,
-            p.min_leaf, p.max_leaf, info);
+            p.treelets, treelet_words, treelet_words + 1, sparse, out.prim_ids, out.tris, leaf_src, centre_src, mode,
+            p.min_leaf, p.max_leaf, info, alive);
+        BVH_CUDA_TRY(cudaGetLastError());
+    }
+
+    // compaction: live pairs only, renumbered in order (the radix sort's buffers are free again: ranks and tile
+    // counts live in them)
+    const uint32_t pairs = n - 1;
+    uint32_t* rank = reinterpret_cast<uint32_t*>(keys_b);
+    uint32_t* tile_counts = vals_b;
+    if (pairs > 0) {
+        const uint32_t tiles = (pairs + kCompactTile - 1) / kCompactTile;
+        compact_count_kernel<<<tiles, kBlock, 0, stream>>>(alive, pairs, tile_counts);
+        compact_scan_kernel<<<1, 1024, 0, stream>>>(tile_counts, tiles, info);
+        compact_rank_kernel<<<tiles, kBlock, 0, stream>>>(alive, pairs, tile_counts, rank);
         BVH_CUDA_TRY(cudaGetLastError());
     }
 
@@ -545,8 +687,13 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     out.treelets = host_treelets;
     out.morton_bits = key_bits;
     out.quality = options.quality;
+    // the dense array: slot 0, the root, 2 x live pairs
+    out.node_slots = 2 * (size_t)(pairs > 0 ? host_info[3] : 0u) + 2;
+    if (device_alloc(reinterpret_cast<void**>(&out.nodes), out.node_slots * sizeof(DevNode<T>), stream)) return -1;
+    compact_scatter_kernel<T><<<(pairs + kBlock) / kBlock, kBlock, 0, stream>>>(sparse, out.nodes, alive, rank, pairs);
+    BVH_CUDA_TRY(cudaGetLastError());
+    out.compact = true;
     if (make_wide_tree(out, stream)) return -1;
-    out.compact = false;
     return 0;
 }
 
@@ -597,6 +744,17 @@ int refit_triangles(DeviceBvh<T>& bvh, const T* d_verts, cudaStream_t stream) {
     return make_wide_tree(bvh, stream);
 }
 
+template <typename T>
+int export_reference_arrays(const DeviceBvh<T>& bvh, void* d_nodes_out, unsigned long long* d_ids_out, cudaStream_t stream) {
+    using U = typename Real<T>::UInt;
+    if (!bvh.compact) { set_error("export: the device tree is not dense"); return -1; }
+    const size_t node_count = bvh.node_slots - 1, words = node_count * 7;
+    export_nodes_kernel<T><<<(unsigned)((words + kBlock - 1) / kBlock), kBlock, 0, stream>>>(bvh.nodes, node_count, static_cast<U*>(d_nodes_out));
+    export_ids_kernel<<<(unsigned)((bvh.prim_count + kBlock - 1) / kBlock), kBlock, 0, stream>>>(bvh.prim_ids, bvh.prim_count, d_ids_out);
+    BVH_CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 template <typename T> void release(DeviceBvh<T>& bvh, cudaStream_t stream) {
     device_free(bvh.nodes, stream); bvh.nodes = nullptr;
     device_free(bvh.prim_ids, stream); bvh.prim_ids = nullptr;
@@ -615,6 +773,8 @@ template int rebuild_wide<float>(DeviceBvh<float>&, cudaStream_t, bool);
 template int rebuild_wide<double>(DeviceBvh<double>&, cudaStream_t, bool);
 template int refit_triangles<float>(DeviceBvh<float>&, const float*, cudaStream_t);
 template int refit_triangles<double>(DeviceBvh<double>&, const double*, cudaStream_t);
+template int export_reference_arrays<float>(const DeviceBvh<float>&, void*, unsigned long long*, cudaStream_t);
+template int export_reference_arrays<double>(const DeviceBvh<double>&, void*, unsigned long long*, cudaStream_t);
 template void release<float>(DeviceBvh<float>&, cudaStream_t);
 template void release<double>(DeviceBvh<double>&, cudaStream_t);
 

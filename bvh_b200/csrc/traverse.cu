@@ -19,6 +19,7 @@
 // tree they visit nodes in the same order as the CPU code and produce bit-identical ids, t, u, v.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "engine.h"
 #include "traverse_core.cuh"
@@ -118,6 +119,7 @@ template <typename T> struct TraceArgs {
     bool use_tma;                     // persistent kernel: stage ray chunks with cp.async.bulk
     uint32_t inner_budget;            // persistent kernel: inner steps per lane per round (0xFFFFFFFF = unbounded)
     uint32_t full_mask;               // 0xFFFFFFFF passed at run time (see trace_pair_kernel)
+    bool stage_hits;                  // gather mode: warp-aggregated bulk stores (false: one store per record and rank)
     uint32_t* status;                 // device word set to 1 when a watchdog fired
     uint32_t watchdog;                // persistent kernels: trap after this many rounds of one warp (a hang becomes an error)
     int lowest_id;
@@ -169,6 +171,167 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+
+// ---- warp-aggregated hit stores of the fused multi-GPU gather ------------------------------------------
+// In gather mode every finished ray's record has to reach the gathered array of EVERY rank.  One 16-byte
+// store per rank and ray (round 1) puts world_size extra store instructions per ray on the pipe this kernel
+// is bound by (L1 LSU wavefronts).  Instead a warp stages the records of each GROUP of 32 consecutive rays
+// (512 contiguous bytes of the output) in shared memory; when the group's last ray retires ONE lane issues one
+// bulk asynchronous copy shared -> global per rank (cp.async.bulk, SASS UBLKCP: the copy is done by the TMA
+// unit, not by the LSU pipe).  A warp keeps kStageSlots groups open; when a new group needs a slot and all
+// are held by stragglers, the oldest is evicted: its finished records go out as plain per-record stores and
+// its unfinished rays switch to per-record stores.  Records of rays without a slot are stored directly.
+constexpr int kStageSlots = 2;
+constexpr uint32_t kNoTag = 0xFFFFFFFFu;
+
+__device__ __forceinline__ void bulk_copy_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <typename T> __host__ __device__ constexpr size_t stage_smem_bytes() {
+    return (size_t)(kTraceBlock / 32) * kStageSlots * 32 * sizeof(DevHit<T>);
+}
+
+template <typename T> struct HitStager {
+    DevHit<T>* buf;                 // this warp's kStageSlots x 32 records in shared memory (null: staging off)
+    // warp-uniform
+    uint32_t done[kStageSlots];     // bit i: record i of the slot's group is in the buffer
+    uint32_t want[kStageSlots];     // the records the group has (all ones, or fewer for the batch's tail)
+    uint32_t group[kStageSlots];    // ray index / 32 of the slot's group
+    uint32_t used, draining;        // bit s: slot s holds an open group / is being read by a bulk copy
+    uint32_t next;                  // slots are opened in cyclic order, so `next` is also the oldest one
+    uint32_t cur;                   // slot of the group rays are currently drawn from, kStageSlots: none
+    // per lane
+    uint32_t tag;                   // slot << 5 | index in the group of the lane's ray, kNoTag: direct stores
+    uint32_t pending;               // tag of the record written since the last account(), kNoTag: none
+
+    __device__ __forceinline__ void init(DevHit<T>* warp_buf) {
+        buf = warp_buf;
+        #pragma unroll
+        for (int s = 0; s < kStageSlots; ++s) { done[s] = 0; want[s] = 0; group[s] = 0; }
+        used = 0; draining = 0; next = 0; cur = kStageSlots; tag = kNoTag; pending = kNoTag;
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ void store_record_direct(const HitSinks<T>& sinks, unsigned long long i, const DevHit<T>& rec) {
+    using V = typename std::conditional<sizeof(T) == 4, uint4, ulonglong2>::type;
+    constexpr int kParts = (int)(sizeof(DevHit<T>) / 16);
+    const V* src = reinterpret_cast<const V*>(&rec);
+    if (sinks.local) {
+        V* d = reinterpret_cast<V*>(sinks.local + i);
+        #pragma unroll
+        for (int k = 0; k < kParts; ++k) __stcs(d + k, src[k]);
+    }
+    if (sizeof(T) == 4 && sinks.multicast) { multimem_store_v4(sinks.multicast + i, *reinterpret_cast<const uint4*>(&rec)); return; }
+    for (int p = 0; p < sinks.peer_count; ++p) {
+        V* d = reinterpret_cast<V*>(sinks.peer[p] + i);
+        #pragma unroll
+        for (int k = 0; k < kParts; ++k) d[k] = src[k];
+    }
+}
+
+// All lanes of the warp call these three together (converged code).
+template <typename T>
+__device__ __forceinline__ void stager_flush_full(HitStager<T>& st, const HitSinks<T>& sinks, int s, unsigned lane) {
+    __syncwarp();                                                   // the lanes' shared-memory records are visible to lane 0
+    if (lane == 0) {
+        fence_proxy_async_smem();                                   // ... and to the async proxy that reads them
+        const uint32_t count = 32u - (uint32_t)__clz(st.want[s]);  // want is a low mask
+        const uint32_t bytes = count * (uint32_t)sizeof(DevHit<T>);
+        const uint32_t src = smem_u32(st.buf + s * 32);
+        const unsigned long long first = (unsigned long long)st.group[s] * 32ull;
+        if (sinks.local) bulk_copy_s2g(sinks.local + first, src, bytes);
+        for (int p = 0; p < sinks.peer_count; ++p) bulk_copy_s2g(sinks.peer[p] + first, src, bytes);
+        bulk_commit();
+    }
+    st.used &= ~(1u << s);
+    st.draining |= 1u << s;
+}
+
+template <typename T>
+__device__ __forceinline__ void stager_evict(HitStager<T>& st, const HitSinks<T>& sinks, int s, unsigned lane) {
+    __syncwarp();
+    if ((st.done[s] >> lane) & 1u)
+        store_record_direct(sinks, (unsigned long long)st.group[s] * 32ull + lane, st.buf[s * 32 + lane]);
+    if (st.tag != kNoTag && (int)(st.tag >> 5) == s) st.tag = kNoTag;       // the group's unfinished rays store directly
+    st.used &= ~(1u << s);
+    __syncwarp();                                                   // the buffer is free for the next group
+}
+
+// A new group of `count` rays (ray index = 32 * group_id ...) starts being drawn: give it a slot.
+template <typename T>
+__device__ __forceinline__ void stager_open(HitStager<T>& st, const HitSinks<T>& sinks, unsigned long long group_id,
+                                            uint32_t count, unsigned lane) {
+    st.cur = kStageSlots;
+    if (!st.buf || group_id > 0xFFFFFFFFull) return;
+    constexpr uint32_t kAll = (1u << kStageSlots) - 1u;
+    if (((st.used | st.draining) & kAll) == kAll && st.draining != 0u) {
+        if (lane == 0) bulk_wait_read_all();                        // the bulk copies have read their buffers
+        __syncwarp();
+        st.draining = 0;
+    }
+    int s = (int)st.next;
+    if (((st.used | st.draining) >> s) & 1u) {                      // the next slot in cyclic order is not free
+        #pragma unroll
+        for (int k = 0; k < kStageSlots; ++k) if ((((st.used | st.draining) >> k) & 1u) == 0u) s = k;
+    }
+    if ((st.used >> s) & 1u) {                                      // every slot is held by stragglers: evict the oldest
+        #pragma unroll
+        for (int k = 0; k < kStageSlots; ++k) if (k == s) stager_evict(st, sinks, k, lane);
+    }
+    #pragma unroll
+    for (int k = 0; k < kStageSlots; ++k) if (k == s) {
+        st.done[k] = 0; st.want[k] = count >= 32u ? 0xFFFFFFFFu : ((1u << count) - 1u); st.group[k] = (uint32_t)group_id;
+    }
+    st.used |= 1u << s;
+    st.next = (uint32_t)(s + 1 == kStageSlots ? 0 : s + 1);
+    st.cur = (uint32_t)s;
+}
+
+// Books the records written since the last call; flushes groups that became complete.
+template <typename T>
+__device__ __forceinline__ void stager_account(HitStager<T>& st, const HitSinks<T>& sinks, unsigned lane) {
+    if (!st.buf) return;
+    if (__ballot_sync(0xFFFFFFFFu, st.pending != kNoTag) == 0u) return;
+    #pragma unroll
+    for (int s = 0; s < kStageSlots; ++s) {
+        const uint32_t mine = (st.pending != kNoTag && (int)(st.pending >> 5) == s) ? (1u << (st.pending & 31u)) : 0u;
+        const uint32_t bits = __reduce_or_sync(0xFFFFFFFFu, mine);
+        if (bits != 0u) {
+            st.done[s] |= bits;
+            if (st.done[s] == st.want[s]) stager_flush_full(st, sinks, s, lane);
+        }
+    }
+    st.pending = kNoTag;
+}
+
+// One finished ray (divergent code): into the lane's staging slot, or straight to the sinks.
+template <typename T>
+__device__ __forceinline__ void stager_retire(HitStager<T>& st, const HitSinks<T>& sinks, unsigned long long i, const DevHit<T>& rec) {
+    if (st.tag != kNoTag) {
+        st.buf[(st.tag >> 5) * 32 + (st.tag & 31u)] = rec;
+        st.pending = st.tag;
+        st.tag = kNoTag;
+    } else {
+        store_record_direct(sinks, i, rec);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ DevHit<T> make_record(const HitState<T>& h, T tmax, const uint32_t* __restrict__ prim_ids) {
+    DevHit<T> rec;
+    const bool was_hit = h.slot != kInvalidId;
+    rec.prim_id = was_hit ? (decltype(rec.prim_id))prim_ids[h.slot] : (decltype(rec.prim_id))~(decltype(rec.prim_id))0;
+    rec.t = was_hit ? h.t : tmax;
+    rec.u = was_hit ? h.u : (T)0;
+    rec.v = was_hit ? h.v : (T)0;
+    return rec;
+}
+
 __device__ __forceinline__ void read_ray_smem(const DevRay<float>* p, RayCtx<float>& r) {
     const float4* q = reinterpret_cast<const float4*>(p);
     const float4 a = q[0], b = q[1];
@@ -192,8 +355,8 @@ template <typename T> __host__ __device__ constexpr size_t tma_smem_bytes() {
 // asynchronous copy (cp.async.bulk, SASS UBLKCP) signalled through an mbarrier, double-buffered, so
 // that the ray fetch of the refill path never waits on DRAM; kTma = false reads rays with streaming
 // 128-bit loads.
-template <typename T, bool kAny, bool kRobust, bool kTma>
-__global__ void __launch_bounds__(kTraceBlock, sizeof(T) == 4 ? 8 : 4)
+template <typename T, bool kAny, bool kRobust, bool kTma, bool kGather>
+__global__ void __launch_bounds__(kTraceBlock, sizeof(T) == 4 ? (kGather ? 7 : 8) : 4)
 trace_persistent_kernel(TraceArgs<T> a) {
     using U = typename Real<T>::UInt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -228,6 +391,17 @@ trace_persistent_kernel(TraceArgs<T> a) {
             mbar_arrive_expect_tx(bar, cnt * (uint32_t)sizeof(DevRay<T>));
             bulk_copy_g2s(smem_u32(b == 0 ? ray_buf0 : ray_buf1), a.rays + base, cnt * (uint32_t)sizeof(DevRay<T>), bar);
         }
+    };
+
+    // gather mode: hit records leave through the warp's staging slots (HitStager above)
+    HitStager<T> stager;
+    if (kGather) {
+        unsigned char* stage_base = smem_raw + (size_t)a.stack_entries * kTraceBlock * sizeof(U) + (kTma ? tma_smem_bytes<T>() : 0);
+        stager.init((a.hits.multicast || !a.stage_hits) ? nullptr : reinterpret_cast<DevHit<T>*>(stage_base) + (size_t)warp * kStageSlots * 32);
+    }
+    auto retire = [&] (unsigned long long index, const HitState<T>& h, T tmax) {
+        if (kGather) stager_retire(stager, a.hits, index, make_record(h, tmax, a.prim_ids));
+        else store_hit(a.hits, index, h, tmax, a.prim_ids);
     };
 
     if (kTma) {
@@ -267,6 +441,7 @@ trace_persistent_kernel(TraceArgs<T> a) {
                 if (cur_count == 0) { exhausted = true; break; }
                 const uint32_t cur_bar = cur == 0 ? bar0 : bar1, cur_phase = cur == 0 ? phase0 : phase1;
                 while (!mbar_try_wait(cur_bar, cur_phase)) { }
+                if (kGather && buf_pos == 0) stager_open(stager, a.hits, (cur == 0 ? base0 : base1) >> 5, cur_count, lane);
                 const unsigned avail = cur_count - buf_pos, want = __popc(idle);
                 take = want < avail ? want : avail;
                 if (!has_ray && rank < take) {
@@ -290,7 +465,13 @@ trace_persistent_kernel(TraceArgs<T> a) {
                     chunk_pos = base;
                     chunk_end = base + kChunkRays < a.n ? base + kChunkRays : a.n;
                 }
-                const unsigned avail = (unsigned)(chunk_end - chunk_pos), want = __popc(idle);
+                unsigned avail = (unsigned)(chunk_end - chunk_pos);
+                const unsigned want = __popc(idle);
+                if (kGather) {                              // one staging group = 32 consecutive rays: never draw across a boundary
+                    const unsigned in_group = (unsigned)(chunk_pos & 31ull);
+                    if (in_group == 0) stager_open(stager, a.hits, chunk_pos >> 5, avail < 32u ? avail : 32u, lane);
+                    if (avail > 32u - in_group) avail = 32u - in_group;
+                }
                 take = want < avail ? want : avail;
                 if (!has_ray && rank < take) {
                     ray_index = chunk_pos + rank;
@@ -302,8 +483,9 @@ trace_persistent_kernel(TraceArgs<T> a) {
             if (got) {
                 tmax_in = r.tmax;
                 hit.slot = kInvalidId; hit.t = r.tmax; hit.u = (T)0; hit.v = (T)0;
+                if (kGather) stager.tag = stager.cur < (uint32_t)kStageSlots ? (stager.cur << 5) | (uint32_t)(ray_index & 31ull) : kNoTag;
                 if (ray_interval_is_nan(r)) {
-                    store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);     // can never hit: retire as a miss
+                    retire(ray_index, hit, tmax_in);                             // can never hit: retire as a miss
                 } else {
                     ray_prologue<T, kRobust>(r);
                     top = root_index;
@@ -311,6 +493,7 @@ trace_persistent_kernel(TraceArgs<T> a) {
                     has_ray = true;
                 }
             }
+            if (kGather) stager_account(stager, a.hits, lane);      // (a NaN ray may just have been retired)
             idle = __ballot_sync(kFull, !has_ray);
         }
         if (__ballot_sync(kFull, has_ray) == 0u) {
@@ -326,7 +509,7 @@ trace_persistent_kernel(TraceArgs<T> a) {
                 --budget;
                 if (!inner_step<T, kAny, kRobust>(a.nodes, r, top, stack)) { has_ray = false; break; }
             }
-            if (!has_ray) store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
+            if (!has_ray) retire(ray_index, hit, tmax_in);
         }
         __syncwarp();
 
@@ -334,14 +517,16 @@ trace_persistent_kernel(TraceArgs<T> a) {
         if (has_ray && index_count(top) != 0) {
             leaf_step<T>(a.tris, a.prim_ids, lowest_id, top, r, hit, nullptr);
             if ((kAny && hit.slot != kInvalidId) || stack.empty()) {
-                store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
+                retire(ray_index, hit, tmax_in);
                 has_ray = false;
             } else {
                 top = stack.pop();
             }
         }
         __syncwarp();
+        if (kGather) stager_account(stager, a.hits, lane);
     }
+    if (kGather && stager.buf && lane == 0) bulk_wait_all();         // the last bulk stores have left shared memory and landed
 }
 
 // ---- lane-pair kernel ------------------------------------------------------------------------------
@@ -494,8 +679,8 @@ trace_pair_kernel(TraceArgs<T> a) {
 // padded inverse direction so that rounding can only enlarge a box), visits the hit children nearest
 // first and pushes the others far-to-near.  Leaves are the binary tree's leaves: same BVH-order triangle
 // array, same exact triangle test and canonical tie-break as every other kernel.
-template <bool kAny>
-__global__ void __launch_bounds__(kTraceBlock, 8)
+template <bool kAny, bool kGather>
+__global__ void __launch_bounds__(kTraceBlock, kGather ? 7 : 8)
 trace_wide_kernel(TraceArgs<float> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -503,6 +688,15 @@ trace_wide_kernel(TraceArgs<float> a) {
     const unsigned lt_mask = (1u << lane) - 1u;
     SmemStack<uint32_t> stack { reinterpret_cast<uint32_t*>(smem_raw) + threadIdx.x, kTraceBlock, 0 };
     const uint32_t inner_budget = a.inner_budget;
+    HitStager<float> stager;
+    if (kGather) {
+        unsigned char* stage_base = smem_raw + (size_t)a.wide_entries * kTraceBlock * sizeof(uint32_t);
+        stager.init((a.hits.multicast || !a.stage_hits) ? nullptr : reinterpret_cast<DevHit<float>*>(stage_base) + (size_t)(threadIdx.x >> 5) * kStageSlots * 32);
+    }
+    auto retire = [&] (unsigned long long index, const HitState<float>& h, float tmax) {
+        if (kGather) stager_retire(stager, a.hits, index, make_record(h, tmax, a.prim_ids));
+        else store_hit(a.hits, index, h, tmax, a.prim_ids);
+    };
 
     unsigned long long chunk_pos = 0, chunk_end = 0;
     bool exhausted = false;
@@ -529,7 +723,13 @@ trace_wide_kernel(TraceArgs<float> a) {
                 chunk_pos = base;
                 chunk_end = base + kChunkRays < a.n ? base + kChunkRays : a.n;
             }
-            const unsigned avail = (unsigned)(chunk_end - chunk_pos), want = __popc(idle);
+            unsigned avail = (unsigned)(chunk_end - chunk_pos);
+            const unsigned want = __popc(idle);
+            if (kGather) {                                  // one staging group = 32 consecutive rays
+                const unsigned in_group = (unsigned)(chunk_pos & 31ull);
+                if (in_group == 0) stager_open(stager, a.hits, chunk_pos >> 5, avail < 32u ? avail : 32u, lane);
+                if (avail > 32u - in_group) avail = 32u - in_group;
+            }
             const unsigned take = want < avail ? want : avail;
             const unsigned rank = __popc(idle & lt_mask);
             if (!has_ray && rank < take) {
@@ -537,8 +737,9 @@ trace_wide_kernel(TraceArgs<float> a) {
                 load_ray(a.rays, ray_index, r);
                 tmax_in = r.tmax;
                 hit.slot = kInvalidId; hit.t = r.tmax; hit.u = 0.f; hit.v = 0.f;
+                if (kGather) stager.tag = stager.cur < (uint32_t)kStageSlots ? (stager.cur << 5) | (uint32_t)(ray_index & 31ull) : kNoTag;
                 if (ray_interval_is_nan(r)) {
-                    store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
+                    retire(ray_index, hit, tmax_in);
                 } else {
                     wide_ray_setup(r);
                     top = 0;                                    // wide node 0, inner
@@ -547,6 +748,7 @@ trace_wide_kernel(TraceArgs<float> a) {
                 }
             }
             chunk_pos += take;
+            if (kGather) stager_account(stager, a.hits, lane);
             idle = __ballot_sync(kFull, !has_ray);
         }
         if (__ballot_sync(kFull, has_ray) == 0u) {
@@ -570,7 +772,7 @@ trace_wide_kernel(TraceArgs<float> a) {
                 }
                 if (!wide_step<kAny>(w, r, top, stack)) { has_ray = false; break; }
             }
-            if (!has_ray) store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
+            if (!has_ray) retire(ray_index, hit, tmax_in);
         }
         __syncwarp();
 
@@ -578,14 +780,16 @@ trace_wide_kernel(TraceArgs<float> a) {
         if (has_ray && index_count(top) != 0) {
             leaf_step<float>(a.tris, a.prim_ids, true, top, r, hit, nullptr);
             if ((kAny && hit.slot != kInvalidId) || stack.empty()) {
-                store_hit(a.hits, ray_index, hit, tmax_in, a.prim_ids);
+                retire(ray_index, hit, tmax_in);
                 has_ray = false;
             } else {
                 top = stack.pop();
             }
         }
         __syncwarp();
+        if (kGather) stager_account(stager, a.hits, lane);
     }
+    if (kGather && stager.buf && lane == 0) bulk_wait_all();
 }
 
 
@@ -596,23 +800,29 @@ int configure_smem(KernelT kernel, size_t smem_bytes) {
     return 0;
 }
 
+// One resident wave of persistent CTAs (148 SMs x occupancy), never more than the batch can feed.
+template <typename KernelT, typename T>
+int launch_persistent(KernelT kernel, const TraceArgs<T>& args, size_t smem, unsigned rays_per_warp, int device, cudaStream_t stream) {
+    if (smem > 200 * 1024) { set_error("trace: tree too deep for the shared-memory stack"); return -1; }
+    if (configure_smem(kernel, smem)) return -1;
+    int sm_count = 148, per_sm = 1;
+    BVH_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceBlock, smem));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long grid = (unsigned long long)sm_count * per_sm;
+    const unsigned long long max_useful = (args.n + rays_per_warp - 1) / rays_per_warp / (kTraceBlock / 32) + 1;
+    if (grid > max_useful) grid = max_useful;
+    BVH_CUDA_TRY(cudaMemsetAsync(args.next_ray, 0, sizeof(unsigned long long), stream));
+    kernel<<<(unsigned)grid, kTraceBlock, smem, stream>>>(args);
+    return 0;
+}
+
 template <typename T, bool kAny>
-int launch_wide(const TraceArgs<T>& args, int device, cudaStream_t stream) {
+int launch_wide(const TraceArgs<T>& args, bool gather, int device, cudaStream_t stream) {
     if constexpr (sizeof(T) == 4) {
-        auto kernel = trace_wide_kernel<kAny>;
         const size_t smem = (size_t)args.wide_entries * kTraceBlock * sizeof(uint32_t);
-        if (smem > 200 * 1024) { set_error("trace: wide tree too deep for the shared-memory stack"); return -1; }
-        if (configure_smem(kernel, smem)) return -1;
-        int sm_count = 148, per_sm = 1;
-        BVH_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
-        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceBlock, smem));
-        if (per_sm < 1) per_sm = 1;
-        unsigned long long grid = (unsigned long long)sm_count * per_sm;
-        const unsigned long long max_useful = (args.n + 31) / 32 / (kTraceBlock / 32) + 1;
-        if (grid > max_useful) grid = max_useful;
-        BVH_CUDA_TRY(cudaMemsetAsync(args.next_ray, 0, sizeof(unsigned long long), stream));
-        kernel<<<(unsigned)grid, kTraceBlock, smem, stream>>>(args);
-        return 0;
+        if (gather) return launch_persistent(trace_wide_kernel<kAny, true>, args, smem + stage_smem_bytes<T>(), 32, device, stream);
+        return launch_persistent(trace_wide_kernel<kAny, false>, args, smem, 32, device, stream);
     } else {
         set_error("trace: the wide kernel is float-only");
         return -1;
@@ -620,7 +830,7 @@ int launch_wide(const TraceArgs<T>& args, int device, cudaStream_t stream) {
 }
 
 template <typename T, bool kAny, bool kRobust>
-int launch(const TraceArgs<T>& args, bool simple, bool stats, int device, cudaStream_t stream) {
+int launch(const TraceArgs<T>& args, bool simple, bool stats, bool gather, int device, cudaStream_t stream) {
     using U = typename Real<T>::UInt;
     const size_t smem = (size_t)args.stack_entries * kTraceBlock * sizeof(U);
     if (smem > 200 * 1024) { set_error("trace: tree too deep for the shared-memory stack"); return -1; }
@@ -635,34 +845,17 @@ int launch(const TraceArgs<T>& args, bool simple, bool stats, int device, cudaSt
             trace_simple_kernel<T, kAny, kRobust, false><<<(unsigned)blocks, kTraceBlock, smem, stream>>>(args);
         }
     } else if (args.variant == 3) {
-        if (launch_wide<T, kAny>(args, device, stream)) return -1;
+        if (launch_wide<T, kAny>(args, gather, device, stream)) return -1;
     } else if (args.variant == 2) {
-        auto kernel = trace_pair_kernel<T, kAny, kRobust>;
-        const size_t pair_smem = smem / 2;                                     // one stack per lane pair
-        if (configure_smem(kernel, pair_smem)) return -1;
-        int sm_count = 148, per_sm = 1;
-        BVH_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
-        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceBlock, pair_smem));
-        if (per_sm < 1) per_sm = 1;
-        unsigned long long grid = (unsigned long long)sm_count * per_sm;
-        const unsigned long long max_useful = (args.n + 15) / 16 / (kTraceBlock / 32) + 1;
-        if (grid > max_useful) grid = max_useful;
-        BVH_CUDA_TRY(cudaMemsetAsync(args.next_ray, 0, sizeof(unsigned long long), stream));
-        kernel<<<(unsigned)grid, kTraceBlock, pair_smem, stream>>>(args);
+        if (launch_persistent(trace_pair_kernel<T, kAny, kRobust>, args, smem / 2, 16, device, stream)) return -1;   // one stack per lane pair
     } else {
-        const bool tma = args.use_tma;
-        auto kernel = tma ? trace_persistent_kernel<T, kAny, kRobust, true> : trace_persistent_kernel<T, kAny, kRobust, false>;
-        const size_t total_smem = smem + (tma ? tma_smem_bytes<T>() : 0);
-        if (configure_smem(kernel, total_smem)) return -1;
-        int sm_count = 148, per_sm = 1;
-        BVH_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
-        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceBlock, total_smem));
-        if (per_sm < 1) per_sm = 1;
-        unsigned long long grid = (unsigned long long)sm_count * per_sm;      // one resident wave
-        const unsigned long long max_useful = (args.n + 31) / 32 / (kTraceBlock / 32) + 1;
-        if (grid > max_useful) grid = max_useful;
-        BVH_CUDA_TRY(cudaMemsetAsync(args.next_ray, 0, sizeof(unsigned long long), stream));
-        kernel<<<(unsigned)grid, kTraceBlock, total_smem, stream>>>(args);
+        const size_t tma = args.use_tma ? tma_smem_bytes<T>() : 0, stage = gather ? stage_smem_bytes<T>() : 0;
+        int rc;
+        if (args.use_tma) rc = gather ? launch_persistent(trace_persistent_kernel<T, kAny, kRobust, true, true>, args, smem + tma + stage, 32, device, stream)
+                                      : launch_persistent(trace_persistent_kernel<T, kAny, kRobust, true, false>, args, smem + tma, 32, device, stream);
+        else              rc = gather ? launch_persistent(trace_persistent_kernel<T, kAny, kRobust, false, true>, args, smem + stage, 32, device, stream)
+                                      : launch_persistent(trace_persistent_kernel<T, kAny, kRobust, false, false>, args, smem, 32, device, stream);
+        if (rc) return -1;
     }
     BVH_CUDA_TRY(cudaGetLastError());
     return 0;
@@ -699,6 +892,7 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     args.inner_budget = tunables().inner_budget.load();
     args.watchdog = tunables().watchdog.load();
     args.full_mask = 0xFFFFFFFFu;
+    args.stage_hits = tunables().gather_staging.load() != 0;
     args.variant = (flags & kTracePair) ? 2 : ((flags & (kTraceNoTma | kTraceTma)) ? 0 : tunables().variant.load());
     // the wide (compressed 4-wide) path: float, canonical tie-break, fast slab test, no statistics
     args.wide = nullptr; args.wide_entries = 0;
@@ -728,10 +922,14 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     args.status = reinterpret_cast<uint32_t*>(bvh.scratch + 1);
     int rc;
     const bool any = (flags & kTraceAnyHit) != 0, robust = (flags & kTraceRobust) != 0;
-    if (any) rc = robust ? launch<T, true, true>(args, simple, stats, bvh.device, stream)
-                         : launch<T, true, false>(args, simple, stats, bvh.device, stream);
-    else     rc = robust ? launch<T, false, true>(args, simple, stats, bvh.device, stream)
-                         : launch<T, false, false>(args, simple, stats, bvh.device, stream);
+    const bool staged = gather != nullptr;                  // gather mode: the kernels with warp-aggregated hit stores
+    if (args.variant == 3) args.inner_budget = tunables().wide_budget.load();
+    bvh.last_kernel = stats ? kKernelStats : simple ? kKernelSimple : args.variant == 3 ? kKernelWide : args.variant == 2 ? kKernelPair
+                    : args.use_tma ? kKernelPersistentTma : kKernelPersistent;
+    if (any) rc = robust ? launch<T, true, true>(args, simple, stats, staged, bvh.device, stream)
+                         : launch<T, true, false>(args, simple, stats, staged, bvh.device, stream);
+    else     rc = robust ? launch<T, false, true>(args, simple, stats, staged, bvh.device, stream)
+                         : launch<T, false, false>(args, simple, stats, staged, bvh.device, stream);
     return rc;
 }
 

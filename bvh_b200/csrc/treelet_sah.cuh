@@ -85,7 +85,7 @@ template <typename T, int S> struct TreeletScratch {
     uint8_t best_axis[S], split[S], seg_depth[S];
     uint32_t dst_slot[S], left_slot[S], right_slot[S];
     uint8_t side[S];                     // per PRIMITIVE: 1 = goes to the left part
-    uint32_t counters[4];                // [0] next pair, [1] live segments, [2] treelet depth, [3] longest live segment
+    uint32_t counters[4];                // [0] unused, [1] live segments, [2] treelet depth, [3] longest live segment
 };
 static_assert(sizeof(TreeletScratch<float, TreeletCfg<float>::kMaxPrims>) <= 48 * 1024, "one warp's slice of shared memory");
 static_assert(sizeof(TreeletScratch<double, TreeletCfg<double>::kMaxPrims>) <= 48 * 1024, "one warp's slice of shared memory");
@@ -113,7 +113,8 @@ template <typename T, int S, typename Exec>
 BVH_HD void treelet_rebuild(TreeletScratch<T, S>& w, const Treelet& t, DevNode<T>* __restrict__ nodes,
                             uint32_t* __restrict__ prim_ids, DevTri<T>* __restrict__ tris,
                             const T* __restrict__ leaf_src, const T* __restrict__ centre_src, int leaf_mode,
-                            uint32_t min_leaf, uint32_t max_leaf, uint32_t* __restrict__ info, uint32_t lbvh_depth) {
+                            uint32_t min_leaf, uint32_t max_leaf, uint32_t* __restrict__ info, uint32_t lbvh_depth,
+                            uint32_t* __restrict__ alive = nullptr) {
     using R = Real<T>;
     using U = typename R::UInt;
     constexpr uint32_t C = TreeletScratch<T, S>::kChunk;
@@ -145,6 +146,7 @@ BVH_HD void treelet_rebuild(TreeletScratch<T, S>& w, const Treelet& t, DevNode<T
         }
         for (int k = 0; k < 3; ++k) { w.box[2 * k][i] = bmin[k]; w.box[2 * k + 1][i] = bmax[k]; w.centre[k][i] = c[k]; }
         w.seg_begin[i] = 0; w.seg_end[i] = (uint16_t)n;
+        if (alive && i + 1 < n) alive[l + i] = 0u;           // the subtree's pairs: the splits below mark the ones they use
         if (i == 0) {
             w.dst_slot[0] = t.slot; w.seg_depth[0] = 0;
             w.counters[0] = 0; w.counters[1] = 1; w.counters[2] = 0; w.counters[3] = n;
@@ -316,7 +318,10 @@ BVH_HD void treelet_rebuild(TreeletScratch<T, S>& w, const Treelet& t, DevNode<T
             }
             const T bmin[3] = { w.nbox[0][pos], w.nbox[2][pos], w.nbox[4][pos] }, bmax[3] = { w.nbox[1][pos], w.nbox[3][pos], w.nbox[5][pos] };
             if (do_split) {
-                const uint32_t pair = l + Exec::atomic_add(&w.counters[0], 1u);          // one of the pairs l .. r-1 the LBVH subtree owned
+                // one of the pairs l .. r-1 the LBVH subtree owned: the one of the split boundary, as in the LBVH numbering
+                // (every inner node of a tree over a contiguous range splits at a different boundary)
+                const uint32_t pair = l + (uint32_t)w.best_pos[pos] - 1u;
+                if (alive) alive[pair] = 1u;
                 const bool swap = w.best_larea[pos] < w.best_rarea[pos];                 // SATO, top_down_sah_builder.h:101-108
                 w.left_slot[pos]  = (uint32_t)child_slot(pair, swap ? 1 : 0);
                 w.right_slot[pos] = (uint32_t)child_slot(pair, swap ? 0 : 1);

@@ -86,38 +86,72 @@ class FusedGatherTracer:
 
     The gathered hit array lives in symmetric memory (``torch.distributed._symmetric_memory``): every rank
     holds the same (world * local_count, words) buffer and knows the address of each peer's copy.  One
-    launch of the traversal kernel (``bvhNN_intersect_rays_gather``) traces this rank's shard and stores
-    each finished ray's 16-byte record straight into the shard's slot of EVERY rank's buffer — one multimem
-    store through the NVSwitch multicast address when the fabric offers it, otherwise one peer store per
-    rank — so the transfer rides along with the traversal instead of following it as an NCCL call.  A
-    symmetric-memory barrier at the end of the step orders the remote stores before anyone reads.
+    launch of the traversal kernel (``bvhNN_intersect_rays_gather``) traces this rank's shard and delivers
+    every hit record into the shard's slot of EVERY rank's buffer while it runs: a warp stages the records of
+    32 consecutive rays in shared memory and one lane sends the 512-byte block to each rank with a bulk
+    asynchronous copy (``cp.async.bulk`` shared -> peer global), or — ``mode="multicast"`` — every record
+    goes out as one ``multimem.st`` through the NVSwitch multicast address.  A symmetric-memory barrier at the
+    end of the step orders the remote stores before anyone reads.
+
+    Ordering (what a caller may rely on):
+      * the kernel runs on the BVH handle's stream; ``step()`` makes it wait for the work already enqueued on
+        torch's current stream and makes the current stream wait for the kernel before the barrier, so the
+        barrier is ordered after the kernel's peer stores whichever stream the handle owns;
+      * the gathered array is double-buffered: step k writes buffer k % 2, so a peer still reading the records
+        of step k - 1 is never overwritten — the barrier that ends step k is only passed by ranks that are done
+        with the buffer step k + 1 will write;
+      * ``check()`` waits for the handle's stream and raises if a kernel watchdog fired (stale records).
     """
 
-    def __init__(self, bvh, rays: torch.Tensor, hit_words: int, group=None, flags: int = 0, mode: str = "auto"):
+    def __init__(self, bvh, rays: torch.Tensor, hit_words: int, group=None, flags: int = 0, mode: str = "auto",
+                 buffers: int = 2):
         import torch.distributed._symmetric_memory as symm_mem
         self.bvh, self.rays, self.flags = bvh, rays, flags
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.local_count = rays.shape[0]
-        self.gathered = symm_mem.empty((self.world * self.local_count, hit_words), dtype=torch.int32, device=rays.device)
-        self.handle = symm_mem.rendezvous(self.gathered, self.group)
-        self.peers = [int(p) for p in self.handle.buffer_ptrs]
-        multicast = int(getattr(self.handle, "multicast_ptr", 0) or 0)
-        # Measured on B200 / NVSwitch (profiles/r01_gather_modes.txt): with two ranks the multicast store is the
-        # faster form (5227 vs 5155 Mrays/s), with four it is the slower one (8846 vs 10049) — "auto" follows that.
-        if mode == "peer" or (mode == "auto" and self.world > 2):
-            multicast = 0
-        if mode == "multicast" and not multicast:
+        self.buffers = []
+        for _ in range(max(1, buffers)):
+            gathered = symm_mem.empty((self.world * self.local_count, hit_words), dtype=torch.int32, device=rays.device)
+            handle = symm_mem.rendezvous(gathered, self.group)
+            self.buffers.append((gathered, handle, [int(p) for p in handle.buffer_ptrs],
+                                 int(getattr(handle, "multicast_ptr", 0) or 0)))
+        has_multicast = all(b[3] for b in self.buffers)
+        # "auto": staged bulk copies to every peer.  Round 1 measured per-record stores only (multicast ahead at two
+        # ranks, peer stores ahead at four: profiles/r01_gather_modes.txt); the staged form replaces world_size
+        # store instructions per ray by one bulk copy per rank and 32 rays.
+        if mode == "multicast" and not has_multicast:
             raise RuntimeError("no multicast address for the symmetric buffer on this fabric")
-        self.multicast = multicast
-        self.mode = "multicast" if multicast else "peer"
+        self.mode = "multicast" if mode == "multicast" else "peer"
         self.bounds = [(0, self.local_count)]
+        self.steps = 0
+        lib_stream = int(bvh.get_property("stream"))
+        self.lib_stream = None
+        if lib_stream != int(torch.cuda.current_stream(rays.device).cuda_stream):
+            self.lib_stream = torch.cuda.ExternalStream(lib_stream, device=rays.device)
+        self._select(0)
+
+    def _select(self, k: int) -> None:
+        self.gathered, self.handle, self.peers, multicast = self.buffers[k % len(self.buffers)]
+        self.multicast = multicast if self.mode == "multicast" else 0
         self.local = self.gathered[self.rank * self.local_count:(self.rank + 1) * self.local_count]
 
     def step(self) -> None:
+        self._select(self.steps)
+        self.steps += 1
+        current = torch.cuda.current_stream(self.rays.device)
+        if self.lib_stream is not None:
+            self.lib_stream.wait_stream(current)            # e.g. the previous step's barrier, the caller's ray upload
         self.bvh.intersect_rays_gather(self.rays.data_ptr(), self.local_count, self.peers,
                                        self.rank * self.local_count, multicast_ptr=self.multicast, flags=self.flags)
+        if self.lib_stream is not None:
+            current.wait_stream(self.lib_stream)            # the barrier below must follow the kernel's peer stores
         self.handle.barrier(channel=0)
 
+    def check(self) -> None:
+        """Waits for the handle's stream; raises ``BvhError`` if the traversal kernel's watchdog fired."""
+        self.bvh.sync()
+
     def global_hits(self) -> torch.Tensor:
+        """The gathered records of the most recent step."""
         return self.gathered

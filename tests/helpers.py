@@ -46,7 +46,7 @@ class HostEmul:
             getattr(L, f"emul_build{s}").restype = C.c_uint32
             getattr(L, f"emul_build{s}").argtypes = [P, P, P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, P, P, P, P]
             getattr(L, f"emul_compact{s}").restype = C.c_size_t
-            getattr(L, f"emul_compact{s}").argtypes = [P, P, P, C.c_size_t]
+            getattr(L, f"emul_compact{s}").argtypes = [P, C.c_size_t, P, P, C.c_size_t]
             getattr(L, f"emul_trace{s}").argtypes = [P, P, P, P, C.c_size_t, C.c_uint, P, P, P, P, P]
             getattr(L, f"emul_from_reference{s}").argtypes = [P, P, C.c_size_t, P]
             getattr(L, f"emul_precompute{s}").argtypes = [P, P, C.c_size_t, P]
@@ -56,6 +56,7 @@ class HostEmul:
         L.emul_set_block.argtypes = [C.c_int, C.c_int]
         L.emul_set_treelets.argtypes = [C.c_int]
         L.emul_last_treelet_count.restype = C.c_int
+        L.emul_last_node_slots.restype = C.c_size_t
         L.emul_morton30.restype = C.c_uint32
         L.emul_morton30.argtypes = [C.c_uint32] * 3
         L.emul_morton63.restype = C.c_uint64
@@ -84,7 +85,8 @@ class HostEmul:
         depth = C.c_uint32(0)
         getattr(self.lib, f"emul_build{s}")(_ptr(tris), _ptr(bboxes), _ptr(centers), n, min_leaf, max_leaf, morton_bits,
                                             _ptr(nodes), _ptr(ids), _ptr(dtris), C.byref(depth))
-        return dict(nodes=nodes, prim_ids=ids, tris=dtris, depth=depth.value, dtype=dtype, n=n)
+        # the emulation compacts like the device build: `slots` dense device slots (slot 0 padding, slot 1 the root)
+        return dict(nodes=nodes, prim_ids=ids, tris=dtris, depth=depth.value, dtype=dtype, n=n, slots=self.lib.emul_last_node_slots())
 
     def set_treelets(self, on, reversed_phases: bool = False):
         """Experimental second build pass: SAH rebuild of the LBVH's bottom subtrees (treelet_sah.cuh);
@@ -99,7 +101,7 @@ class HostEmul:
         n, dtype = tree["n"], tree["dtype"]
         bounds = np.zeros((2 * n, 6), dtype)
         index_values = np.zeros(2 * n, np.uint64)
-        cnt = getattr(self.lib, f"emul_compact{self._s(dtype)}")(_ptr(tree["nodes"]), _ptr(bounds), _ptr(index_values), 2 * n)
+        cnt = getattr(self.lib, f"emul_compact{self._s(dtype)}")(_ptr(tree["nodes"]), tree["slots"], _ptr(bounds), _ptr(index_values), 2 * n)
         return bounds[:cnt].copy(), index_values[:cnt].copy()
 
     def from_reference(self, bounds, index_values, prim_ids, tris):
@@ -113,7 +115,7 @@ class HostEmul:
         ids = np.ascontiguousarray(prim_ids, dtype=np.uint32)
         dtris = aligned_zeros((ids.shape[0], 12), dtype)
         getattr(self.lib, f"emul_precompute{s}")(_ptr(np.ascontiguousarray(tris)), _ptr(ids), ids.shape[0], _ptr(dtris))
-        return dict(nodes=nodes, prim_ids=ids, tris=dtris, depth=None, dtype=dtype, n=ids.shape[0])
+        return dict(nodes=nodes, prim_ids=ids, tris=dtris, depth=None, dtype=dtype, n=ids.shape[0], slots=n_nodes + 1)
 
     def wide_build(self, tree):
         """Collapse the (float) binary tree into the compressed 4-wide tree; returns (wide nodes, levels)."""

@@ -30,6 +30,7 @@ template <typename U> struct HostStack {
 };
 
 static int g_block_leaves = 0, g_block_order = 0, g_treelets = 0, g_last_treelets = 0;
+static size_t g_last_slots = 0;
 
 template <typename T, typename K>
 uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t n, uint32_t min_leaf, uint32_t max_leaf,
@@ -61,6 +62,8 @@ uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t 
     BuildParams<T> p;
     p.nodes = nodes; p.flags = flags.data(); p.info = info; p.n = n;
     p.min_leaf = min_leaf; p.max_leaf = max_leaf;
+    std::vector<uint32_t> alive(n, 1u);                      // morton_kernel initialises the liveness of every pair
+    p.alive = alive.data();
     std::vector<Treelet> list((size_t)n / 3 + 1);
     uint32_t list_count = 0;
     if (g_treelets && n > 2) { p.treelets = list.data(); p.treelet_count = &list_count; p.treelet_max = (uint32_t)TreeletCfg<T>::kMaxPrims; }
@@ -122,40 +125,44 @@ uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t 
         for (const Treelet& t : list) {
             if (g_treelets == 2)          // iterations of every phase in descending order (hazard check)
                 treelet_rebuild<T, S, HostExecReversed>(*scratch, t, nodes, prim_ids, verts ? tris : nullptr, leaf_src, centers, verts ? 0 : 1,
-                                                        min_leaf, max_leaf, info, info[0]);
+                                                        min_leaf, max_leaf, info, info[0], alive.data());
             else
                 treelet_rebuild<T, S, HostExec>(*scratch, t, nodes, prim_ids, verts ? tris : nullptr, leaf_src, centers, verts ? 0 : 1,
-                                                min_leaf, max_leaf, info, info[0]);
+                                                min_leaf, max_leaf, info, info[0], alive.data());
         }
         g_last_treelets = (int)list.size();
+    }
+    // compaction (lbvh_build.cu compact_*_kernel): the live pairs, in order of split position
+    {
+        const uint32_t pairs = n - 1;
+        std::vector<uint32_t> rank(n, 0u);
+        uint32_t live = 0;
+        for (uint32_t q = 0; q < pairs; ++q) { rank[q] = live; live += alive[q]; }
+        std::vector<DevNode<T>> dense(2 * (size_t)live + 2);
+        std::memset(dense.data(), 0, sizeof(DevNode<T>));
+        dense[1] = compact_remap(nodes[1], rank.data());
+        for (uint32_t q = 0; q < pairs; ++q) {
+            if (!alive[q]) continue;
+            dense[child_slot(rank[q], 0)] = compact_remap(nodes[child_slot(q, 0)], rank.data());
+            dense[child_slot(rank[q], 1)] = compact_remap(nodes[child_slot(q, 1)], rank.data());
+        }
+        std::memset(nodes, 0, 2 * (size_t)n * sizeof(DevNode<T>));
+        std::memcpy(nodes, dense.data(), dense.size() * sizeof(DevNode<T>));
+        g_last_slots = dense.size();
     }
     *depth_out = info[0] + info[2];
     return info[1];
 }
 
-// dense reference layout out of the sparse device array (same walk as c_api.cu download_mirror)
+// reference layout out of the dense device array (slot = reference index + 1): what c_api.cu download_mirror copies
 template <typename T>
-size_t emul_compact(const DevNode<T>* dev, T* bounds, uint64_t* index_values, size_t cap) {
-    using U = typename Real<T>::UInt;
-    struct Out { T b[6]; U index; };
-    std::vector<Out> out;
-    auto emit = [&] (const DevNode<T>& s) { Out o; std::memcpy(o.b, s.bounds, sizeof o.b); o.index = s.index; out.push_back(o); };
-    emit(dev[1]);
-    std::vector<size_t> stack;
-    if (index_count(out[0].index) == 0) stack.push_back(0);
-    while (!stack.empty()) {
-        size_t dst = stack.back(); stack.pop_back();
-        size_t first_src = (size_t)index_first(out[dst].index), first_dst = out.size();
-        emit(dev[first_src + 1]); emit(dev[first_src + 2]);
-        out[dst].index = make_index<U>((U)first_dst, 0);
-        if (index_count(out[first_dst + 1].index) == 0) stack.push_back(first_dst + 1);
-        if (index_count(out[first_dst].index) == 0) stack.push_back(first_dst);
+size_t emul_compact(const DevNode<T>* dev, size_t slots, T* bounds, uint64_t* index_values, size_t cap) {
+    const size_t count = slots - 1;
+    if (count <= cap) for (size_t i = 0; i < count; ++i) {
+        std::memcpy(bounds + 6 * i, dev[i + 1].bounds, 6 * sizeof(T));
+        index_values[i] = dev[i + 1].index;
     }
-    if (out.size() <= cap) for (size_t i = 0; i < out.size(); ++i) {
-        std::memcpy(bounds + 6 * i, out[i].b, sizeof out[i].b);
-        index_values[i] = out[i].index;
-    }
-    return out.size();
+    return count;
 }
 
 template <typename T>
@@ -271,8 +278,8 @@ void emul_wide_trace_impl(const WideNode* wide, const DevTri<float>* tris, const
                            int morton_bits, void* nodes, uint32_t* prim_ids, void* tris, uint32_t* depth) { \
         if (morton_bits <= 30) return emul_build<T, uint32_t>(verts, bboxes, centers, n, min_leaf, max_leaf, (DevNode<T>*)nodes, prim_ids, (DevTri<T>*)tris, depth); \
         return emul_build<T, uint64_t>(verts, bboxes, centers, n, min_leaf, max_leaf, (DevNode<T>*)nodes, prim_ids, (DevTri<T>*)tris, depth); } \
-    size_t emul_compact##S(const void* dev, T* bounds, uint64_t* index_values, size_t cap) { \
-        return emul_compact<T>((const DevNode<T>*)dev, bounds, index_values, cap); } \
+    size_t emul_compact##S(const void* dev, size_t slots, T* bounds, uint64_t* index_values, size_t cap) { \
+        return emul_compact<T>((const DevNode<T>*)dev, slots, bounds, index_values, cap); } \
     void emul_trace##S(const void* nodes, const void* tris, const uint32_t* prim_ids, const T* rays, size_t m, unsigned flags, \
                        uint32_t* ids, T* ts, T* us, T* vs, uint32_t* stats) { \
         emul_trace<T>((const DevNode<T>*)nodes, (const DevTri<T>*)tris, prim_ids, rays, m, flags, ids, ts, us, vs, stats); } \
@@ -293,6 +300,7 @@ EMUL_API(float, 3f)
 EMUL_API(double, 3d)
 void emul_set_treelets(int on) { g_treelets = on; }
 int emul_last_treelet_count() { return g_last_treelets; }
+size_t emul_last_node_slots() { return g_last_slots; }
 void emul_set_block(int leaves, int order) { g_block_leaves = leaves; g_block_order = order; }
 uint32_t emul_morton30(uint32_t x, uint32_t y, uint32_t z) { return MortonTraits<uint32_t>::encode(x, y, z); }
 uint64_t emul_morton63(uint64_t x, uint64_t y, uint64_t z) { return MortonTraits<uint64_t>::encode(x, y, z); }

@@ -526,7 +526,8 @@ def test_gpu_refit_after_vertices_move(gpu_lib, oracle, dtype):
     assert_hits_equal(hits_tuple(bvh.intersect_rays(rays, flags=api.ROBUST)), oracle.brute_force(moved, rays), "refit trace")
 
 
-@pytest.mark.parametrize("dtype,flags_name", [(np.float32, None), (np.float32, "ANY_HIT"), (np.float64, None)])
+@pytest.mark.parametrize("dtype,flags_name", [(np.float32, None), (np.float32, "ANY_HIT"), (np.float64, None),
+                                              (np.float32, "KERNEL_WIDE"), (np.float32, "KERNEL_NO_TMA"), (np.float32, "KERNEL_TMA")])
 def test_gather_entry_point_on_one_gpu(gpu_lib, dtype, flags_name):
     """bvhNN_intersect_rays_gather with both "ranks" on one device: the shard's records must land, identical to
     the plain batched call, in the shard's slot of every gathered array (and nowhere else), and in the local
@@ -536,7 +537,10 @@ def test_gather_entry_point_on_one_gpu(gpu_lib, dtype, flags_name):
     tris = scenes.soup(20000, seed=2).astype(dtype)
     bvh = api.Bvh.build_triangles(tris)
     rays = scenes.make_primary("soup", 301, 211, dtype=dtype)          # 63 511 rays: a ragged last chunk
+    if flags_name in ("KERNEL_WIDE", "KERNEL_TMA"):                    # incoherent order: stragglers hold staging slots (evictions)
+        rays = np.ascontiguousarray(rays[np.random.default_rng(5).permutation(rays.shape[0])])
     rays[5, 6] = np.nan                                                # a ray retired in the refill path
+    rays[40, 7] = np.nan
     flags = getattr(api, flags_name) if flags_name else 0
     want = bvh.intersect_rays(rays, flags=flags)
     m = rays.shape[0]

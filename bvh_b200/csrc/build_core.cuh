@@ -132,7 +132,7 @@ template <> struct AuxPack<double> {
     static BVH_HD uint32_t depth(uint64_t w) { return (uint32_t)w; }
 };
 
-// A bottom subtree handed to the SAH treelet pass (treelet_sah.cuh): device slot of its root record and the
+// A bottom subtree handed to the SAH treelet pass (treelet_warp.cuh): device slot of its root record and the
 // range [l, r] of sorted primitives it covers.
 struct Treelet { uint32_t slot, l, r; };
 

@@ -56,7 +56,7 @@ struct BuildOptions {
     uint32_t max_leaf = 8;
     int quality = 2;                // DefaultBuilder::Quality (default_builder.h:21); see DESIGN.md
     int morton_bits = 0;            // 0 = auto, 30 or 63
-    bool sah_treelets = false;      // EXPERIMENTAL (treelet_sah.cuh): SAH rebuild of the LBVH's bottom subtrees
+    bool sah_treelets = false;      // treelet_warp.cuh: SAH rebuild of the bottom subtrees (Quality Medium / High)
 };
 
 // The device-resident BVH: reference-layout nodes (shifted by one slot, padded), BVH-order

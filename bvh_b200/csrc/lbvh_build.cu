@@ -20,7 +20,7 @@
 #include "build_core.cuh"
 #include "engine.h"
 #include "radix_sort.cuh"
-#include "treelet_sah.cuh"
+#include "treelet_warp.cuh"
 #include "wide_bvh.cuh"
 
 namespace bvhb200 {
@@ -258,11 +258,11 @@ void launch_hierarchy(const BuildParams<T>& p, const K* keys, const uint32_t* va
 #undef BVH_LAUNCH_H
 }
 
-// ---- second pass of Quality Medium / High: SAH rebuild of the bottom subtrees (treelet_sah.cuh) -------------
+// ---- second pass of Quality Medium / High: SAH rebuild of the bottom subtrees (treelet_warp.cuh) ------------
 // The treelets were listed by the hierarchy kernel (build_core.cuh merge_into_parent).  One WARP per treelet:
-// warps claim list entries from a global cursor (treelets differ in size), the scratch of a treelet is the
-// warp's slice of the block's dynamic shared memory.
-constexpr int kTreeletWarps = 3;          // 3 x 14.4 KB of scratch per block: 5 blocks = 15 warps per SM
+// warps claim list entries from a global cursor (treelets differ in size); the working set of a treelet is in the
+// warp's registers plus a 3.3 KB (float) slice of the block's shared memory.
+constexpr int kTreeletWarps = 8;
 
 template <typename T>
 __global__ void __launch_bounds__(kTreeletWarps * 32)
@@ -270,17 +270,15 @@ treelet_kernel(const Treelet* __restrict__ list, const uint32_t* __restrict__ li
                DevNode<T>* __restrict__ nodes, uint32_t* __restrict__ prim_ids, DevTri<T>* __restrict__ tris,
                const T* __restrict__ leaf_src, const T* __restrict__ centre_src, int leaf_mode, uint32_t min_leaf,
                uint32_t max_leaf, uint32_t* __restrict__ info, uint32_t* __restrict__ alive) {
-    constexpr int S = TreeletCfg<T>::kMaxPrims;
-    extern __shared__ __align__(16) unsigned char treelet_smem[];
-    TreeletScratch<T, S>& scratch = reinterpret_cast<TreeletScratch<T, S>*>(treelet_smem)[threadIdx.x >> 5];
+    __shared__ TreeletShared<T> shared[kTreeletWarps];
+    TreeletShared<T>& mine = shared[threadIdx.x >> 5];
     const uint32_t count = *list_count, lbvh_depth = info[0];
     for (;;) {
         uint32_t i = 0;
         if ((threadIdx.x & 31u) == 0) i = atomicAdd(cursor, 1u);
         i = __shfl_sync(0xFFFFFFFFu, i, 0);
         if (i >= count) break;
-        treelet_rebuild<T, S, WarpExec>(scratch, list[i], nodes, prim_ids, tris, leaf_src, centre_src, leaf_mode, min_leaf, max_leaf, info, lbvh_depth, alive);
-        __syncwarp();
+        treelet_rebuild<T, DeviceLanes>(mine, list[i], nodes, prim_ids, tris, leaf_src, centre_src, leaf_mode, min_leaf, max_leaf, info, lbvh_depth, alive);
     }
 }
 
@@ -649,18 +647,12 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     BVH_CUDA_TRY(cudaGetLastError());
 
     if (treelets) {
-        constexpr size_t smem = kTreeletWarps * sizeof(TreeletScratch<T, TreeletCfg<T>::kMaxPrims>);
         auto kernel = treelet_kernel<T>;
-        static bool configured = false;                      // (per instantiation)
-        if (!configured) {
-            BVH_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
-        }
         int per_sm = 1;
-        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTreeletWarps * 32, smem));
+        BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTreeletWarps * 32, 0));
         if (per_sm < 1) per_sm = 1;
         const uint32_t max_blocks = (uint32_t)(sm_count * per_sm), want = (n / 3 + kTreeletWarps) / kTreeletWarps;
-        kernel<<<want < max_blocks ? want : max_blocks, kTreeletWarps * 32, smem, stream>>>(
+        kernel<<<want < max_blocks ? want : max_blocks, kTreeletWarps * 32, 0, stream>>>(
             p.treelets, treelet_words, treelet_words + 1, sparse, out.prim_ids, out.tris, leaf_src, centre_src, mode,
             p.min_leaf, p.max_leaf, info, alive);
         BVH_CUDA_TRY(cudaGetLastError());

@@ -129,7 +129,7 @@ template <typename T, bool kAny, bool kRobust, bool kStats>
 __global__ void __launch_bounds__(kTraceBlock)
 trace_simple_kernel(TraceArgs<T> a) {
     using U = typename Real<T>::UInt;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned long long i = (unsigned long long)blockIdx.x * kTraceBlock + threadIdx.x;
     if (i >= a.n) return;
     SmemStack<U> stack { reinterpret_cast<U*>(smem_raw) + threadIdx.x, kTraceBlock, 0 };

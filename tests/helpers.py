@@ -29,7 +29,7 @@ def build_host_emul() -> str:
     out_dir = os.path.join(ROOT, "tests", "_build")
     out = os.path.join(out_dir, "libhost_emul.so")
     csrc = os.path.join(ROOT, "bvh_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("core.cuh", "build_core.cuh", "traverse_core.cuh", "treelet_sah.cuh", "wide_bvh.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("core.cuh", "build_core.cuh", "traverse_core.cuh", "treelet_warp.cuh", "wide_bvh.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(out_dir, exist_ok=True)
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC",
@@ -89,7 +89,7 @@ class HostEmul:
         return dict(nodes=nodes, prim_ids=ids, tris=dtris, depth=depth.value, dtype=dtype, n=n, slots=self.lib.emul_last_node_slots())
 
     def set_treelets(self, on, reversed_phases: bool = False):
-        """Experimental second build pass: SAH rebuild of the LBVH's bottom subtrees (treelet_sah.cuh);
+        """Experimental second build pass: SAH rebuild of the LBVH's bottom subtrees (treelet_warp.cuh);
         ``reversed_phases`` runs the iterations of every phase in descending order (hazard check)."""
         self.lib.emul_set_treelets((2 if reversed_phases else 1) if on else 0)
 

@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "build_core.cuh"
-#include "treelet_sah.cuh"
+#include "treelet_warp.cuh"
 #include "traverse_core.cuh"
 #include "wide_bvh.cuh"
 
@@ -116,19 +116,18 @@ uint32_t emul_build(const T* verts, const T* bboxes, const T* centers, uint32_t 
         }
     }
     if (g_treelets && n > 2) {
-        // the second pass (treelet_sah.cuh): rebuild every maximal subtree of 3..kMaxPrims primitives, as listed by
+        // the second pass (treelet_warp.cuh): rebuild every maximal subtree of 3..kMaxPrims primitives, as listed by
         // the bottom-up pass above
-        constexpr int S = TreeletCfg<T>::kMaxPrims;
         list.resize(list_count);
-        auto scratch = std::make_unique<TreeletScratch<T, S>>();
+        auto shared = std::make_unique<TreeletShared<T>>();
         const T* leaf_src = verts ? verts : bboxes;
         for (const Treelet& t : list) {
-            if (g_treelets == 2)          // iterations of every phase in descending order (hazard check)
-                treelet_rebuild<T, S, HostExecReversed>(*scratch, t, nodes, prim_ids, verts ? tris : nullptr, leaf_src, centers, verts ? 0 : 1,
-                                                        min_leaf, max_leaf, info, info[0], alive.data());
+            if (g_treelets == 2)          // lanes in descending order inside every step (shared-memory hazard check)
+                treelet_rebuild<T, HostLanesReversed>(*shared, t, nodes, prim_ids, verts ? tris : nullptr, leaf_src, centers, verts ? 0 : 1,
+                                                      min_leaf, max_leaf, info, info[0], alive.data());
             else
-                treelet_rebuild<T, S, HostExec>(*scratch, t, nodes, prim_ids, verts ? tris : nullptr, leaf_src, centers, verts ? 0 : 1,
-                                                min_leaf, max_leaf, info, info[0], alive.data());
+                treelet_rebuild<T, HostLanes>(*shared, t, nodes, prim_ids, verts ? tris : nullptr, leaf_src, centers, verts ? 0 : 1,
+                                              min_leaf, max_leaf, info, info[0], alive.data());
         }
         g_last_treelets = (int)list.size();
     }

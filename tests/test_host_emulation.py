@@ -236,7 +236,7 @@ def test_block_local_phase_builds_the_same_tree(emul, kind, n, dtype):
 @pytest.mark.parametrize("kind,n,dtype", [("soup", 20000, np.float32), ("grid", 20000, np.float32), ("soup", 6000, np.float64),
                                            ("soup", 200, np.float32), ("soup", 3, np.float32), ("soup", 2, np.float32), ("soup", 1, np.float32)])
 def test_sah_treelet_pass_keeps_results_and_saves_steps(emul, oracle, kind, n, dtype):
-    """The experimental second build pass (treelet_sah.cuh: SAH rebuild of every maximal LBVH subtree of at most
+    """The experimental second build pass (treelet_warp.cuh: SAH rebuild of every maximal LBVH subtree of at most
     256 / 128 primitives) must leave a valid reference-layout BVH that answers every ray like the plain LBVH
     (canonical tie-break), with the recorded depth still bounding the traversal stack, and with fewer steps."""
     tris = (scenes.soup(n, seed=7) if kind == "soup" else scenes.make_mesh(kind, n)).astype(dtype)

@@ -47,6 +47,7 @@ struct Tunables {
     std::atomic<uint32_t> inner_budget { 12 };  // inner steps per lane per round
     std::atomic<uint32_t> wide_budget { 4 };    // same for the wide kernel
     std::atomic<uint32_t> watchdog { 1u << 26 };
+    std::atomic<int> sort_onesweep { 1 };       // build: 1 one-sweep radix sort (one kernel per pass), 0 histogram / scan / scatter per pass
     std::atomic<int> gather_staging { 1 };      // fused gather: 1 warp-aggregated bulk stores, 0 one store per record and rank
 };
 Tunables& tunables();
@@ -77,6 +78,7 @@ template <typename T> struct DeviceBvh {
     WideNode* wide = nullptr;
     uint32_t wide_depth = 0;            // number of wide levels (bounds the fast path's stack)
     uint32_t wide_count = 0;
+    bool wide_unavailable = false;      // the binary tree is too deep for the wide collapse: binary kernels only
     // provenance, reported through bvhNN_get_property
     int morton_bits = 0;                // 30 / 63; 0 when the tree was uploaded from a host mirror
     int quality = -1;                   // DefaultBuilder::Quality the build ran with (-1: not built here)

@@ -105,10 +105,14 @@ centre_bounds_kernel(const T* __restrict__ src, uint32_t n, int mode, MinMax3<T>
 template <typename T, typename K>
 __global__ void __launch_bounds__(kBlock)
 morton_kernel(const T* __restrict__ src, uint32_t n, int mode, const MinMax3<T>* __restrict__ partials,
-              uint32_t num_partials, K* __restrict__ keys, int* __restrict__ flags, uint32_t* __restrict__ alive) {
+              uint32_t num_partials, K* __restrict__ keys, int* __restrict__ flags, uint32_t* __restrict__ alive,
+              uint32_t* __restrict__ digit_totals, int passes) {
     using R = Real<T>;
     __shared__ MinMax3<T> warp_part[kBlock / 32];
     __shared__ GridXform<T> xform;
+    // digit histograms of every radix pass, counted while the keys are produced (radix_sort.cuh, one-sweep variant)
+    __shared__ uint32_t digit_hist[8 * 256];
+    if (digit_totals) for (int k = threadIdx.x; k < passes * 256; k += kBlock) digit_hist[k] = 0;
     {
         T mn[3] = { R::max(), R::max(), R::max() };
         T mx[3] = { R::neg(R::max()), R::neg(R::max()), R::neg(R::max()) };
@@ -152,8 +156,14 @@ morton_kernel(const T* __restrict__ src, uint32_t n, int mode, const MinMax3<T>*
             #pragma unroll
             for (int k = 0; k < 3; ++k) c[k] = __ldg(src + 3 * (size_t)i + k);
         }
-        keys[i] = morton_key<T, K>(c, g);
+        const K key = morton_key<T, K>(c, g);
+        keys[i] = key;
         if (i + 1 < n) { flags[i] = -1; alive[i] = 1u; }
+        if (digit_totals) for (int pass = 0; pass < passes; ++pass) atomicAdd(&digit_hist[pass * 256 + ((uint32_t)(key >> (8 * pass)) & 255u)], 1u);
+    }
+    if (digit_totals) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < passes * 256; k += kBlock) { const uint32_t c = digit_hist[k]; if (c) atomicAdd(digit_totals + k, c); }
     }
 }
 
@@ -583,7 +593,7 @@ struct Scratch {
 // Collapses the binary tree of `bvh` into its wide companion (float trees only) and records the wide
 // depth.  Synchronises the stream.
 template <typename T> int make_wide_tree(DeviceBvh<T>& bvh, cudaStream_t stream, bool force = false) {
-    if (sizeof(T) != 4) return 0;
+    if (sizeof(T) != 4 || bvh.wide_unavailable) return 0;
     if (!force && !wide_enabled() && !bvh.wide) return 0;        // not wanted yet (a stale one is always refreshed)
     Scratch scratch(stream);
     uint32_t* counters; uint2* fa; uint2* fb;
@@ -595,6 +605,14 @@ template <typename T> int make_wide_tree(DeviceBvh<T>& bvh, cudaStream_t stream,
     BVH_CUDA_TRY(cudaStreamSynchronize(stream));
     bvh.wide_depth = host_counters[63];
     bvh.wide_count = host_counters[0];
+    const uint32_t rounds = bvh.depth + 1 < (uint32_t)kWideMaxLevels ? bvh.depth + 1 : (uint32_t)kWideMaxLevels;
+    if (host_counters[1 + rounds] != 0) {
+        // the collapse stopped at its level limit with nodes still waiting: their wide records were never written.
+        // Such a (degenerate, very deep) tree is traced with the binary kernels only.
+        device_free(bvh.wide, stream);
+        bvh.wide = nullptr; bvh.wide_depth = 0; bvh.wide_count = 0;
+        bvh.wide_unavailable = true;
+    }
     return 0;
 }
 
@@ -625,8 +643,18 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     if (d_verts && device_alloc(reinterpret_cast<void**>(&out.tris), (size_t)n * sizeof(DevTri<T>), stream)) return -1;
 
     centre_bounds_kernel<T><<<grid, kBlock, 0, stream>>>(centre_src, n, mode, partials);
-    morton_kernel<T, K><<<grid, kBlock, 0, stream>>>(centre_src, n, mode, partials, grid, keys_a, flags, alive);
-    BVH_CUDA_TRY(radix_sort_pairs<K>(keys_a, out.prim_ids, keys_b, vals_b, tile_hist, n, key_bits, stream));
+    if (tunables().sort_onesweep.load() != 0) {
+        const int passes = radix_passes(key_bits);
+        uint32_t* state;
+        const size_t words = onesweep_state_words(n, passes);
+        if (scratch.alloc(&state, words)) return -1;
+        BVH_CUDA_TRY(cudaMemsetAsync(state, 0, words * sizeof(uint32_t), stream));
+        morton_kernel<T, K><<<grid, kBlock, 0, stream>>>(centre_src, n, mode, partials, grid, keys_a, flags, alive, state + 64, passes);
+        BVH_CUDA_TRY(radix_sort_onesweep<K>(keys_a, out.prim_ids, keys_b, vals_b, state, n, key_bits, stream));
+    } else {
+        morton_kernel<T, K><<<grid, kBlock, 0, stream>>>(centre_src, n, mode, partials, grid, keys_a, flags, alive, nullptr, 0);
+        BVH_CUDA_TRY(radix_sort_pairs<K>(keys_a, out.prim_ids, keys_b, vals_b, tile_hist, n, key_bits, stream));
+    }
 
     BuildParams<T> p;
     p.nodes = sparse; p.flags = flags; p.info = info; p.n = n; p.alive = alive;
@@ -752,7 +780,7 @@ template <typename T> void release(DeviceBvh<T>& bvh, cudaStream_t stream) {
     device_free(bvh.prim_ids, stream); bvh.prim_ids = nullptr;
     device_free(bvh.tris, stream); bvh.tris = nullptr;
     device_free(bvh.scratch, stream); bvh.scratch = nullptr;
-    device_free(bvh.wide, stream); bvh.wide = nullptr;
+    device_free(bvh.wide, stream); bvh.wide = nullptr; bvh.wide_unavailable = false;
     bvh.prim_count = 0; bvh.node_slots = 0;
 }
 

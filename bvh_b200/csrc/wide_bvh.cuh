@@ -101,7 +101,14 @@ BVH_HD void wide_encode(const DevNode<float>* __restrict__ nodes, const uint32_t
             lo[a] = robust_min(nodes[slot[c]].bounds[2 * a], lo[a]);
             hi[a] = robust_max(nodes[slot[c]].bounds[2 * a + 1], hi[a]);
         }
-    for (int a = 0; a < 3; ++a) { w.origin[a] = lo[a]; w.exp[a] = wide_cell_exponent(hi[a] - lo[a]); }
+    for (int a = 0; a < 3; ++a) {
+        w.origin[a] = lo[a];
+        uint8_t e = wide_cell_exponent(hi[a] - lo[a]);
+        // hi - lo and origin + 255 * cell are both rounded: make sure cell 255 really reaches the far side, so that
+        // wide_quantize can always round a child's upper bound outwards (the wide tree must stay conservative)
+        while (e != 0 && e < 254 && lo[a] + 255.f * wide_cell_size(e) < hi[a]) ++e;
+        w.exp[a] = e;
+    }
     w.count = (uint8_t)used;
     w.pad[0] = w.pad[1] = 0;
     for (int c = 0; c < 4; ++c) {
@@ -145,14 +152,42 @@ BVH_HD float wide_fmin(float a, float b) {
 #endif
 }
 
-// Byte c of a packed word as a float: a plain int-to-float conversion (I2F, on the XU pipe).  Measured
-// alternative (run 20): one PRMT dropping the byte into the mantissa of 2^23 plus an exact subtraction takes
-// XU from 80 % to 6 % of peak but adds an issue slot per value to a kernel that is issue-bound afterwards —
-// 2.68-2.72 instead of 3.00 Grays/s on soup-1M.  The conversions stay on the otherwise idle XU pipe.
-BVH_HD float wide_byte_to_float(uint32_t word, int c) { return (float)((word >> (8 * c)) & 0xFFu); }
+// Byte c of a packed word as the float 32768 + byte: ONE byte permute drops the byte into mantissa bits 8..15 of
+// 2^15 (0x47000000), where a unit has weight 1 — no int-to-float conversion (I2F runs on the XU pipe at a quarter
+// of the FMA rate, and the 24 conversions per node were what bound the first version of this kernel, ncu round 1:
+// XU 80 % of peak).  The offset is taken out again by the per-node constant: t = fma(32768 + q, s, b - 32768 s).
+BVH_HD float wide_byte_plus_32768(uint32_t word, int c) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(word, 0x47000000u, 0x7604u | ((uint32_t)c << 4)));
+#else
+    return Real<float>::from_bits(0x47000000u | (((word >> (8 * c)) & 0xFFu) << 8));
+#endif
+}
+// b - 32768 * s rounded DOWN (near planes) / UP (far planes): the one rounding this adds can only move a plane
+// outwards.  Host emulation: round-to-nearest fma corrected by comparing with the exact value in double
+// (a float product is exact in double; the sum is exact whenever the exponents are within 2^29 of each other,
+// and otherwise the correction is decided by the sign of the smaller operand).
+BVH_HD float wide_fma_down(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rd(a, b, c);
+#else
+    const float r = __builtin_fmaf(a, b, c);
+    const double exact = (double)a * (double)b + (double)c;
+    return ((double)r > exact && r == r) ? __builtin_nextafterf(r, -__builtin_inff()) : r;
+#endif
+}
+BVH_HD float wide_fma_up(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_ru(a, b, c);
+#else
+    const float r = __builtin_fmaf(a, b, c);
+    const double exact = (double)a * (double)b + (double)c;
+    return ((double)r < exact && r == r) ? __builtin_nextafterf(r, __builtin_inff()) : r;
+#endif
+}
 
 // One inner step through the wide node whose 16 words are in w (layout of WideNode).  Dequantises the four
-// child boxes straight into ray-parameter space, t = q * (cell * inv_dir) + (origin - org) * inv_dir,
+// child boxes straight into ray-parameter space, t = (32768 + q) * (cell * inv_dir) + ((origin - org) * inv_dir - 32768 * cell * inv_dir),
 // visits the nearest hit child next and pushes the others far-to-near (any-hit: no ordering).  Returns
 // false when nothing was hit and the stack is empty.
 template <bool kAny, typename Stack>
@@ -162,8 +197,8 @@ BVH_HD bool wide_step(const uint32_t (&w)[16], const RayCtx<float>& r, uint32_t&
     for (int k = 0; k < 3; ++k) {
         const float cell = R::from_bits(((w[3] >> (8 * k)) & 0xFFu) << 23);
         const float d = R::sub(R::from_bits(w[k]), r.org[k]);
-        s[k] = R::mul(cell, r.inv_dir[k]);  b[k] = R::mul(d, r.inv_dir[k]);
-        sp[k] = R::mul(cell, r.aux[k]);     bp[k] = R::mul(d, r.aux[k]);
+        s[k] = R::mul(cell, r.inv_dir[k]);  b[k] = wide_fma_down(-32768.f, s[k], R::mul(d, r.inv_dir[k]));
+        sp[k] = R::mul(cell, r.aux[k]);     bp[k] = wide_fma_up(-32768.f, sp[k], R::mul(d, r.aux[k]));
     }
     uint32_t qn[3], qf[3];
     for (int k = 0; k < 3; ++k) {
@@ -176,8 +211,8 @@ BVH_HD bool wide_step(const uint32_t (&w)[16], const RayCtx<float>& r, uint32_t&
     for (int c = 0; c < 4; ++c) {
         float tn = r.tmin, tf = r.tmax;
         for (int k = 0; k < 3; ++k) {
-            tn = wide_fmax(R::fma(wide_byte_to_float(qn[k], c), s[k], b[k]), tn);
-            tf = wide_fmin(R::fma(wide_byte_to_float(qf[k], c), sp[k], bp[k]), tf);
+            tn = wide_fmax(R::fma(wide_byte_plus_32768(qn[k], c), s[k], b[k]), tn);
+            tf = wide_fmin(R::fma(wide_byte_plus_32768(qf[k], c), sp[k], bp[k]), tf);
         }
         ref[c] = w[10 + c];
         t0[c] = (tn <= tf) ? tn : inf;                                   // +inf marks a miss

@@ -1,29 +1,31 @@
-# round 2, GPU run 2: compaction + staged gather + optimizer on the GPU suite; wide kernel on the treelet tree; c3 / c5 lines; ncu of the treelet pass
+# round 2, GPU run 2: compaction + warp treelets + one-sweep sort + staged gather + optimizer on the GPU suite; wide kernel
+# on the treelet tree; c3 / c5 lines; launch list; ncu of the treelet pass and of the default traversal kernel
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2b_pytest.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r2b_pytest.log 2>&1
 echo "pytest rc=$? $(tail -1 gpurun_out/r2b_pytest.log)"
 grep -E "^(FAILED|ERROR)" gpurun_out/r2b_pytest.log | head -20
 B="--steps 10 --warmup 3 --no-cpu-baseline --no-e2e"
+line() { echo "$1: rc=$? $(grep -o '"value": [0-9.]*' $2 | head -2 | tr '\n' ' ') $(grep -o '"ms": [0-9.]*' $2) $(grep -o '"inner_steps_per_ray": [0-9.]*' $2)"; }
 for mesh in soup grid; do
-  for k in auto wide; do
-    timeout 300 python bench.py --mesh $mesh --kernel $k $B > gpurun_out/r2b_bench_${mesh}_$k.log 2>&1
-    echo "$mesh high $k rc=$? $(grep -o '"value": [0-9.]*' gpurun_out/r2b_bench_${mesh}_$k.log | head -2 | tr '\n' ' ') $(grep -o '"ms": [0-9.]*' gpurun_out/r2b_bench_${mesh}_$k.log)"
+  for k in auto wide persistent; do
+    timeout 300 python bench.py --mesh $mesh --kernel $k $B > gpurun_out/r2b_bench_${mesh}_$k.log 2>&1; line "$mesh high $k" gpurun_out/r2b_bench_${mesh}_$k.log
   done
 done
 for wb in 2 3 6; do
-  BVH_B200_WIDE_BUDGET=$wb timeout 300 python bench.py --kernel wide $B > gpurun_out/r2b_bench_soup_wide_b$wb.log 2>&1
-  echo "soup wide budget $wb: $(grep -o '"value": [0-9.]*' gpurun_out/r2b_bench_soup_wide_b$wb.log | head -1)"
+  BVH_B200_WIDE_BUDGET=$wb timeout 300 python bench.py --kernel wide $B > gpurun_out/r2b_bench_soup_wide_b$wb.log 2>&1; line "soup wide budget $wb" gpurun_out/r2b_bench_soup_wide_b$wb.log
 done
-timeout 300 python bench.py --quality low --kernel wide $B > gpurun_out/r2b_bench_soup_low_wide.log 2>&1
-echo "soup low wide: $(grep -o '"value": [0-9.]*' gpurun_out/r2b_bench_soup_low_wide.log | head -1)"
+timeout 300 python bench.py --quality low --kernel wide $B > gpurun_out/r2b_bench_soup_low_wide.log 2>&1; line "soup low wide" gpurun_out/r2b_bench_soup_low_wide.log
+timeout 300 python bench.py --quality low --kernel persistent $B > gpurun_out/r2b_bench_soup_low_bin.log 2>&1; line "soup low binary" gpurun_out/r2b_bench_soup_low_bin.log
+BVH_B200_SORT_ONESWEEP=0 timeout 300 python bench.py --quality low --kernel persistent $B > gpurun_out/r2b_bench_soup_low_sort3.log 2>&1; line "soup low 3-kernel sort" gpurun_out/r2b_bench_soup_low_sort3.log
 for c in c3 c5; do
   for k in auto wide; do
     [ $c = c5 ] && [ $k = wide ] && continue
-    timeout 400 python bench.py --config $c --kernel $k --steps 10 --warmup 3 --no-e2e > gpurun_out/r2b_bench_${c}_$k.log 2>&1
-    echo "$c $k rc=$? $(grep -o '"value": [0-9.]*' gpurun_out/r2b_bench_${c}_$k.log | head -3 | tr '\n' ' ')"
+    timeout 400 python bench.py --config $c --kernel $k --steps 10 --warmup 3 --no-e2e > gpurun_out/r2b_bench_${c}_$k.log 2>&1; line "$c $k" gpurun_out/r2b_bench_${c}_$k.log
   done
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r2b_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r2b_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:treelet_kernel -s 2 -c 1 -o gpurun_out/r2b_treelet python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r2b_ncu_treelet.log 2>&1
 echo "ncu treelet rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:trace_wide_kernel -s 1 -c 1 -o gpurun_out/r2b_wide python bench.py --kernel wide --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r2b_ncu_wide.log 2>&1
+echo "ncu wide rc=$?"

@@ -590,3 +590,61 @@ def test_sah_treelets_match_the_emulation(gpu_lib, emul, kind, n, dtype):
     for flags in (api.KERNEL_TMA, api.KERNEL_WIDE, api.KERNEL_SIMPLE):
         assert_hits_equal(hits_tuple(bvh.intersect_rays(rays, flags=flags)), hits_tuple(plain.intersect_rays(rays, flags=flags)),
                           f"treelets vs plain LBVH ({flags})")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n,dtype,bits", [("soup", 300_000, np.float32, 30), ("grid", 50_000, np.float32, 63), ("soup", 2049, np.float64, 30)])
+def test_build_switches_give_the_same_tree(gpu_lib, kind, n, dtype, bits):
+    """The one-sweep radix sort (one kernel per pass, decoupled look-back) and the three-kernel passes must order the
+    primitives identically, and the hierarchy kernel's block-local phase must not change the tree: node arrays and
+    primitive order equal for every combination of the build switches."""
+    api = gpu_lib
+    tris = scenes.make_mesh(kind, n, dtype=dtype)
+    api.set_option("morton_bits", bits)
+    try:
+        trees = []
+        for onesweep, hierarchy in ((1, 128), (0, 128), (1, 0), (1, 64)):
+            api.set_option("sort_onesweep", onesweep)
+            api.set_option("hierarchy", hierarchy)
+            for _ in range(2):                                   # twice: the look-back must not depend on timing
+                bvh = api.Bvh.build_triangles(tris)
+                b, ix, ids = bvh.arrays()
+                trees.append((b.tobytes(), ix.tobytes(), ids.tobytes()))
+        assert all(t == trees[0] for t in trees[1:])
+    finally:
+        api.set_option("morton_bits", 0)
+        api.set_option("sort_onesweep", 1)
+        api.set_option("hierarchy", 128)
+
+
+@pytest.mark.gpu
+def test_optimize_on_a_gpu_built_tree(gpu_lib, oracle):
+    """bvh3f_optimize on a GPU-built tree (reference ReinsertionOptimizer on the host mirror, re-uploaded before the
+    next batched call): the SAH cost of the tree goes down, the invariants hold, batched results do not change."""
+    import ctypes as C
+    api = gpu_lib
+    tris = scenes.soup(60_000, seed=9)
+    rays = scenes.make_primary("soup", 300, 300)
+    bvh = api.Bvh.build_triangles(tris, quality="low")
+
+    def sah(bounds, index_values):
+        d = bounds[:, 1::2].astype(np.float64) - bounds[:, 0::2]
+        area = (d[:, 0] + d[:, 1]) * d[:, 2] + d[:, 0] * d[:, 1]
+        count = (index_values & 15).astype(np.float64)
+        return float(np.where(count > 0, area * count, area).sum() / area[0])
+
+    before_hits = bvh.intersect_rays(rays)
+    b0, i0, ids0 = bvh.arrays()
+    L = api.lib()
+    pool = L.bvh_thread_pool_create(0)
+    L.bvh3f_optimize(C.c_void_p(pool), bvh.handle)
+    L.bvh_thread_pool_destroy(C.c_void_p(pool))
+    b1, i1, ids1 = bvh.arrays()
+    assert sah(b1, i1) < sah(b0, i0) and np.array_equal(ids0, ids1) and b1.shape == b0.shape
+    tree = oracle.from_arrays(b1, i1, ids1)
+    assert oracle.check_invariants(tree, 8) == 0
+    after_hits = bvh.intersect_rays(rays)                       # re-uploads the edited mirror
+    assert np.array_equal(after_hits, before_hits)
+    st_before = api.Bvh.build_triangles(tris, quality="low").intersect_rays(rays, stats=True)[1]
+    st_after = bvh.intersect_rays(rays, stats=True)[1]
+    assert st_after["inner_steps"].sum() < st_before["inner_steps"].sum()

@@ -703,6 +703,10 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     BVH_CUDA_TRY(cudaMemcpyAsync(host_info, info, sizeof(host_info), cudaMemcpyDeviceToHost, stream));
     if (treelets) BVH_CUDA_TRY(cudaMemcpyAsync(&host_treelets, treelet_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     BVH_CUDA_TRY(cudaStreamSynchronize(stream));
+    // The depth travels through the hierarchy pass in 7 bits of the node's spare word (AuxPack).  It cannot get
+    // there: distinct keys split within 63 levels, a run of equal keys is balanced by the index tie-break
+    // (<= 28 more levels for 2^27 primitives).  A saturated value would under-size the traversal stacks: refuse.
+    if (host_info[0] >= 127u) { set_error("build: tree depth exceeds what the build pass can track (127 levels)"); return -1; }
     out.depth = host_info[0] + (treelets ? host_info[2] : 0u);
     out.treelets = host_treelets;
     out.morton_bits = key_bits;

@@ -648,3 +648,27 @@ def test_optimize_on_a_gpu_built_tree(gpu_lib, oracle):
     st_before = api.Bvh.build_triangles(tris, quality="low").intersect_rays(rays, stats=True)[1]
     st_after = bvh.intersect_rays(rays, stats=True)[1]
     assert st_after["inner_steps"].sum() < st_before["inner_steps"].sum()
+
+
+@pytest.mark.gpu
+def test_identical_triangles_with_wide_keys(gpu_lib, oracle):
+    """10^5 copies of one triangle plus a few others, 63-bit keys: every key of the run is equal, the index tie-break
+    must balance the run (depth ~ log2 n, far from the 127 levels the build pass can track), the per-ray entry points
+    (whose stack grows beyond the reference's 64 entries when needed) and the batched ones agree with brute force."""
+    api = gpu_lib
+    base = scenes.soup(8, seed=3)
+    tris = np.concatenate([np.repeat(base[:1], 100_000, axis=0), base[1:]]).astype(np.float32)
+    api.set_option("morton_bits", 63)
+    try:
+        bvh = api.Bvh.build_triangles(tris, quality="low")
+        assert bvh.get_property("morton_bits") == 63 and bvh.depth < 40
+        rays = scenes.make_primary("soup", 24, 24)
+        hits = bvh.intersect_rays(rays)
+        bf = oracle.brute_force(tris, rays)
+        assert_hits_equal(hits_tuple(hits), bf, "identical triangles")
+        assert (hits["prim_id"][hits["prim_id"] < 100_000] == 0).all()      # lowest id among the identical ones
+        b, ix, ids = bvh.arrays()
+        tree = oracle.from_arrays(b, ix, ids)
+        assert oracle.check_invariants(tree, 8) == 0
+    finally:
+        api.set_option("morton_bits", 0)

@@ -50,6 +50,7 @@ Tunables& tunables() {
         t.watchdog = (uint32_t)env("BVH_B200_WATCHDOG", 1l << 26);
         t.gather_staging = (int)env("BVH_B200_GATHER_STAGING", 1);
         t.sort_onesweep = (int)env("BVH_B200_SORT_ONESWEEP", 1);
+        t.speculate = (int)env("BVH_B200_SPECULATE", 0);
     });
     return t;
 }
@@ -675,6 +676,7 @@ BVH_EXPORT int bvh_set_option(const char* name, long value) {
     else if (n == "watchdog") t.watchdog = (uint32_t)value;
     else if (n == "gather_staging") t.gather_staging = (int)value;
     else if (n == "sort_onesweep") t.sort_onesweep = (int)value;
+    else if (n == "speculate") t.speculate = (int)value;
     else { set_error("set_option: unknown option " + n); return -1; }
     return 0;
 }

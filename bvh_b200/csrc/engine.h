@@ -47,6 +47,7 @@ struct Tunables {
     std::atomic<uint32_t> inner_budget { 12 };  // inner steps per lane per round
     std::atomic<uint32_t> wide_budget { 4 };    // same for the wide kernel
     std::atomic<uint32_t> watchdog { 1u << 26 };
+    std::atomic<int> speculate { 0 };           // wide kernel: speculative descent past the first leaf of a round
     std::atomic<int> sort_onesweep { 1 };       // build: 1 one-sweep radix sort (one kernel per pass), 0 histogram / scan / scatter per pass
     std::atomic<int> gather_staging { 1 };      // fused gather: 1 warp-aggregated bulk stores, 0 one store per record and rank
 };

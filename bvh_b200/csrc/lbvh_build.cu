@@ -698,6 +698,12 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
         compact_rank_kernel<<<tiles, kBlock, 0, stream>>>(alive, pairs, tile_counts, rank);
         BVH_CUDA_TRY(cudaGetLastError());
     }
+    // The dense array is allocated for the worst case (2n slots; the live part sits at its front, so the traversal's
+    // footprint is the dense one): its exact size is only known on the device, and waiting for it would put a host
+    // round trip into the middle of the build.
+    if (device_alloc(reinterpret_cast<void**>(&out.nodes), 2 * (size_t)n * sizeof(DevNode<T>), stream)) return -1;
+    compact_scatter_kernel<T><<<(pairs + kBlock) / kBlock, kBlock, 0, stream>>>(sparse, out.nodes, alive, rank, pairs);
+    BVH_CUDA_TRY(cudaGetLastError());
 
     uint32_t host_info[4] = { 0, 0, 0, 0 }, host_treelets = 0;
     BVH_CUDA_TRY(cudaMemcpyAsync(host_info, info, sizeof(host_info), cudaMemcpyDeviceToHost, stream));
@@ -711,11 +717,7 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     out.treelets = host_treelets;
     out.morton_bits = key_bits;
     out.quality = options.quality;
-    // the dense array: slot 0, the root, 2 x live pairs
-    out.node_slots = 2 * (size_t)(pairs > 0 ? host_info[3] : 0u) + 2;
-    if (device_alloc(reinterpret_cast<void**>(&out.nodes), out.node_slots * sizeof(DevNode<T>), stream)) return -1;
-    compact_scatter_kernel<T><<<(pairs + kBlock) / kBlock, kBlock, 0, stream>>>(sparse, out.nodes, alive, rank, pairs);
-    BVH_CUDA_TRY(cudaGetLastError());
+    out.node_slots = 2 * (size_t)(pairs > 0 ? host_info[3] : 0u) + 2;      // slot 0, the root, 2 x live pairs
     out.compact = true;
     if (make_wide_tree(out, stream)) return -1;
     return 0;

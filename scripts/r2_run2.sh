@@ -16,6 +16,8 @@ for wb in 2 3 6; do
 done
 timeout 300 python bench.py --quality low --kernel wide $B > gpurun_out/r2b_bench_soup_low_wide.log 2>&1; line "soup low wide" gpurun_out/r2b_bench_soup_low_wide.log
 timeout 300 python bench.py --quality low --kernel persistent $B > gpurun_out/r2b_bench_soup_low_bin.log 2>&1; line "soup low binary" gpurun_out/r2b_bench_soup_low_bin.log
+BVH_B200_SPECULATE=1 timeout 300 python bench.py --kernel wide $B > gpurun_out/r2b_bench_soup_wide_spec.log 2>&1; line "soup wide speculate" gpurun_out/r2b_bench_soup_wide_spec.log
+BVH_B200_SPECULATE=1 timeout 300 python bench.py --mesh grid --kernel wide $B > gpurun_out/r2b_bench_grid_wide_spec.log 2>&1; line "grid wide speculate" gpurun_out/r2b_bench_grid_wide_spec.log
 BVH_B200_SORT_ONESWEEP=0 timeout 300 python bench.py --quality low --kernel persistent $B > gpurun_out/r2b_bench_soup_low_sort3.log 2>&1; line "soup low 3-kernel sort" gpurun_out/r2b_bench_soup_low_sort3.log
 for c in c3 c5; do
   for k in auto wide; do

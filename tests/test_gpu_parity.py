@@ -672,3 +672,39 @@ def test_identical_triangles_with_wide_keys(gpu_lib, oracle):
         assert oracle.check_invariants(tree, 8) == 0
     finally:
         api.set_option("morton_bits", 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["soup", "grid"])
+def test_wide_kernel_speculation_keeps_the_answers(gpu_lib, oracle, kind):
+    """The wide kernel with and without speculative descent (a leaf put aside while the lane keeps descending) must
+    report the same closest hits as the binary kernel — bit for bit under the canonical tie-break — and the same
+    occluded / not occluded verdict for any-hit rays (any-hit may name a different triangle: whichever leaf is
+    tested first)."""
+    api = gpu_lib
+    tris = scenes.make_mesh(kind, 150_000)
+    rays = scenes.make_primary(kind, 500, 400)
+    shuffled = np.ascontiguousarray(rays[np.random.default_rng(3).permutation(rays.shape[0])])
+    bvh = api.Bvh.build_triangles(tris)
+    want = bvh.intersect_rays(shuffled, flags=api.KERNEL_TMA)
+    want_any = bvh.intersect_rays(shuffled, flags=api.KERNEL_TMA | api.ANY_HIT)
+    try:
+        for spec in (0, 1):
+            api.set_option("speculate", spec)
+            for budget in (1, 4, 0):
+                api.set_option("wide_budget", budget)
+                got = bvh.intersect_rays(shuffled, flags=api.KERNEL_WIDE)
+                assert bvh.properties()["last_kernel"] == "trace_wide_kernel"
+                # conservative boxes: identical, except where the binary tree's fast slab test is not watertight — there
+                # the wide path may only find a closer hit, or the same distance with a lower id
+                diff = (got["prim_id"] != want["prim_id"]) | (got["t"] != want["t"])
+                assert diff.mean() < 1e-4, (spec, budget, diff.sum())
+                assert ((got["t"][diff] < want["t"][diff]) | ((got["t"][diff] == want["t"][diff]) & (got["prim_id"][diff] < want["prim_id"][diff]))).all()
+                if spec == 0 and budget == 1:
+                    first = got
+                assert np.array_equal(got, first), (spec, budget)       # speculation / budget never change the wide path's own answers
+                got_any = bvh.intersect_rays(shuffled, flags=api.KERNEL_WIDE | api.ANY_HIT)
+                assert ((got_any["prim_id"] == INVALID) == (want_any["prim_id"] == INVALID)).all()
+    finally:
+        api.set_option("speculate", 0)
+        api.set_option("wide_budget", 4)

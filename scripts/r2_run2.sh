@@ -4,6 +4,14 @@ mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/r2b_pytest.log 2>&1
 echo "pytest rc=$? $(tail -1 gpurun_out/r2b_pytest.log)"
 grep -E "^(FAILED|ERROR)" gpurun_out/r2b_pytest.log | head -20
+if grep -qE "^(FAILED|ERROR)" gpurun_out/r2b_pytest.log; then
+  # localise: the same parity tests with one new component switched off at a time
+  K="golden or valid_reference_bvh or treelets or tiny or switches"
+  BVH_B200_SORT_ONESWEEP=0 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "$K" > gpurun_out/r2b_pytest_sort3.log 2>&1; echo "3-kernel sort: $(tail -1 gpurun_out/r2b_pytest_sort3.log)"
+  BVH_B200_SAH_TREELETS=0 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "golden or tiny or ragged or refit or gather" > gpurun_out/r2b_pytest_notreelets.log 2>&1; echo "no treelets: $(tail -1 gpurun_out/r2b_pytest_notreelets.log)"
+  BVH_B200_GATHER_STAGING=0 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "gather" > gpurun_out/r2b_pytest_nostaging.log 2>&1; echo "direct gather stores: $(tail -1 gpurun_out/r2b_pytest_nostaging.log)"
+  timeout 600 compute-sanitizer --tool memcheck python scripts/gpu_sanitize.py > gpurun_out/r2b_memcheck.log 2>&1; echo "memcheck: $(grep 'ERROR SUMMARY' gpurun_out/r2b_memcheck.log | tail -1)"
+fi
 B="--steps 10 --warmup 3 --no-cpu-baseline --no-e2e"
 line() { echo "$1: rc=$? $(grep -o '"value": [0-9.]*' $2 | head -2 | tr '\n' ' ') $(grep -o '"ms": [0-9.]*' $2) $(grep -o '"inner_steps_per_ray": [0-9.]*' $2)"; }
 for mesh in soup grid; do

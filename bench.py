@@ -72,6 +72,7 @@ def parse_args():
                     help="N > 1: fused gather inside the traversal kernel — peer (= auto): a warp stages 32 records in shared memory and "
                          "bulk-copies them to every rank; direct: one 16-byte store per record and rank; multicast: one multimem.st per "
                          "record — or NCCL all-gather")
+    ap.add_argument("--sort-rays", action="store_true", help="BVH_SORT_RAYS: traverse the batch in the Morton order of the ray origins")
     ap.add_argument("--no-numa", action="store_true", help="N > 1: do not bind the rank to its GPU's NUMA node")
     return ap.parse_args()
 
@@ -379,6 +380,8 @@ def main():
     peak_gbs, peak_src = hbm_peak()
     base_flags = api.ANY_HIT if cfg["any_hit"] else 0
     kflag = {"auto": 0, "persistent": api.KERNEL_TMA, "wide": api.KERNEL_WIDE, "simple": api.KERNEL_SIMPLE}[args.kernel]
+    if args.sort_rays:
+        kflag |= api.SORT_RAYS
 
     # ---- build: K timed LBVH builds from device-resident vertices ----------------------------------
     def build():
@@ -536,6 +539,7 @@ def main():
             "scaling": cfg["scaling"], "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
             "config": {"workload": workload, "bvh": f"{props.get('pipeline', 'LBVH')} built on the GPU, replicated per rank",
                        "kernel": kernel_name, "tie_break": "lowest original id (canonical)",
+                       "ray_order": "Morton order of the origins (device radix sort inside every step)" if args.sort_rays else "as given",
                        "l2": f"inputs larger than L2: {n_rays * ray_bytes / 1e6:.0f} MB of rays + {n_rays * hit_bytes / 1e6:.0f} MB of hits streamed per step, no flush needed",
                        "hit_fraction": hit_frac, "inner_steps_per_ray": s_inner, "leaves_per_ray": s_leaves, "tri_tests_per_ray": s_tri,
                        "stats_rays": n_rays, "gather": gather_desc, "hits_checksum": checksum,

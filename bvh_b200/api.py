@@ -25,6 +25,7 @@ KERNEL_NO_TMA = 1 << 9
 KERNEL_TMA = 1 << 10
 KERNEL_PAIR = 1 << 11
 KERNEL_WIDE = 1 << 12
+SORT_RAYS = 1 << 13
 KERNELS = (KERNEL_PAIR, KERNEL_NO_TMA, KERNEL_TMA, KERNEL_SIMPLE)
 INVALID_ID = 0xFFFFFFFF
 

@@ -445,6 +445,7 @@ static unsigned translate_flags(unsigned flags) {
     if (flags & BVH_KERNEL_TMA) tf |= kTraceTma;
     if (flags & BVH_KERNEL_PAIR) tf |= kTracePair;
     if (flags & BVH_KERNEL_WIDE) tf |= kTraceWide;
+    if (flags & BVH_SORT_RAYS) tf |= kTraceSortRays;
     return tf;
 }
 

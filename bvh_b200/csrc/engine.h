@@ -130,6 +130,7 @@ enum TraceFlags : unsigned {
     kTraceTma         = 1u << 10,  // persistent one-lane-per-ray kernel, ray chunks staged by bulk async copy (TMA)
     kTracePair        = 1u << 11,  // persistent lane-pair kernel (two lanes per ray)
     kTraceWide        = 1u << 12,  // persistent kernel over the compressed 4-wide tree
+    kTraceSortRays    = 1u << 13,  // traverse the batch in the Morton order of the ray origins (results stay in the caller's order)
 };
 
 // Fused multi-GPU gather: besides (or instead of) the local hit array, every finished ray's record is

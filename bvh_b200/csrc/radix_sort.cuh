@@ -48,7 +48,7 @@ rs_tile_hist_kernel(const K* __restrict__ keys, uint32_t n, int shift,
 // One warp per digit: exclusive scan of that digit's per-tile counts (a contiguous row of the
 // digit-major histogram), in place, plus the digit's total.  The 256 totals are scanned by every
 // scatter block itself.
-__global__ void __launch_bounds__(kRsScanWarps * 32)
+static __global__ void __launch_bounds__(kRsScanWarps * 32)
 rs_scan_bins_kernel(uint32_t* __restrict__ tile_hist, uint32_t num_tiles, uint32_t* __restrict__ bin_totals) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t bin = blockIdx.x * kRsScanWarps + (threadIdx.x >> 5);

@@ -21,7 +21,9 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include "build_core.cuh"
 #include "engine.h"
+#include "radix_sort.cuh"
 #include "traverse_core.cuh"
 #include "wide_bvh.cuh"
 
@@ -119,6 +121,7 @@ template <typename T> struct TraceArgs {
     bool use_tma;                     // persistent kernel: stage ray chunks with cp.async.bulk
     uint32_t inner_budget;            // persistent kernel: inner steps per lane per round (0xFFFFFFFF = unbounded)
     uint32_t full_mask;               // 0xFFFFFFFF passed at run time (see trace_pair_kernel)
+    const uint32_t* order;            // ray reordering: the ray drawn at position p is rays[order[p]] (null: identity)
     bool speculate;                   // wide kernel: put the first leaf of a round aside and keep descending
     bool stage_hits;                  // gather mode: warp-aggregated bulk stores (false: one store per record and rank)
     uint32_t* status;                 // device word set to 1 when a watchdog fired
@@ -476,6 +479,7 @@ trace_persistent_kernel(TraceArgs<T> a) {
                 take = want < avail ? want : avail;
                 if (!has_ray && rank < take) {
                     ray_index = chunk_pos + rank;
+                    if (a.order) ray_index = a.order[ray_index];
                     load_ray(a.rays, ray_index, r);
                     got = true;
                 }
@@ -736,6 +740,7 @@ trace_wide_kernel(TraceArgs<float> a) {
             const unsigned rank = __popc(idle & lt_mask);
             if (!has_ray && rank < take) {
                 ray_index = chunk_pos + rank;
+                if (a.order) ray_index = a.order[ray_index];
                 load_ray(a.rays, ray_index, r);
                 tmax_in = r.tmax;
                 hit.slot = kInvalidId; hit.t = r.tmax; hit.u = 0.f; hit.v = 0.f;
@@ -814,6 +819,71 @@ trace_wide_kernel(TraceArgs<float> a) {
     if (kGather && stager.buf && lane == 0) bulk_wait_all();
 }
 
+
+// ---- ray reordering (BVH_SORT_RAYS) ---------------------------------------------------------------------------
+// Incoherent batches (ambient occlusion, diffuse bounces) arrive in an order unrelated to space: the 32 rays of a
+// warp start in 32 different places, every node fetch is its own cache line and the lanes never agree on a branch.
+// With this flag the batch is traversed in the Morton order of the ray ORIGINS: one kernel computes 30-bit keys
+// against the root box (counting the radix digits on the way), the one-sweep radix sort of the build
+// (radix_sort.cuh) orders ray indices by key, and the persistent kernels draw ray order[p] at position p.  Rays are
+// not moved (a 32-byte ray is one sector wherever it lies) and every hit record goes to its ray's own slot, so the
+// caller sees the same result in the same place.
+template <typename T>
+__global__ void __launch_bounds__(256)
+ray_key_kernel(const DevRay<T>* __restrict__ rays, uint32_t n, const DevNode<T>* __restrict__ nodes,
+               uint32_t* __restrict__ keys, uint32_t* __restrict__ digit_totals) {
+    __shared__ uint32_t digit_hist[4 * 256];
+    for (int k = threadIdx.x; k < 4 * 256; k += 256) digit_hist[k] = 0;
+    __syncthreads();
+    const DevNode<T> root = nodes[1];
+    float lo[3], scale[3];
+    #pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = (float)root.bounds[2 * k];
+        const float extent = (float)root.bounds[2 * k + 1] - lo[k];
+        scale[k] = extent > 0.f ? 1024.f / extent : 0.f;
+    }
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        uint32_t q[3];
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float c = ((float)rays[i].org[k] - lo[k]) * scale[k];
+            q[k] = c > 0.f ? (c < 1023.f ? (uint32_t)c : 1023u) : 0u;           // (a NaN origin lands in cell 0)
+        }
+        const uint32_t key = MortonTraits<uint32_t>::encode(q[0], q[1], q[2]);
+        keys[i] = key;
+        #pragma unroll
+        for (int pass = 0; pass < 4; ++pass) atomicAdd(&digit_hist[pass * 256 + ((key >> (8 * pass)) & 255u)], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 4 * 256; k += 256) { const uint32_t c = digit_hist[k]; if (c) atomicAdd(digit_totals + k, c); }
+}
+
+// Scratch of one reordered call (freed, stream-ordered, when the call has been enqueued).
+struct RayOrderScratch {
+    cudaStream_t stream;
+    void* ptrs[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+    explicit RayOrderScratch(cudaStream_t s) : stream(s) {}
+    ~RayOrderScratch() { for (void* p : ptrs) device_free(p, stream); }
+};
+
+template <typename T>
+int make_ray_order(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, uint32_t n, RayOrderScratch& scratch, const uint32_t** order, cudaStream_t stream) {
+    const size_t words = onesweep_state_words(n, 4);
+    for (int k = 0; k < 4; ++k) if (device_alloc(&scratch.ptrs[k], (size_t)n * sizeof(uint32_t), stream)) return -1;
+    if (device_alloc(&scratch.ptrs[4], words * sizeof(uint32_t), stream)) return -1;
+    uint32_t* keys_a = static_cast<uint32_t*>(scratch.ptrs[0]); uint32_t* keys_b = static_cast<uint32_t*>(scratch.ptrs[1]);
+    uint32_t* vals_a = static_cast<uint32_t*>(scratch.ptrs[2]); uint32_t* vals_b = static_cast<uint32_t*>(scratch.ptrs[3]);
+    uint32_t* state = static_cast<uint32_t*>(scratch.ptrs[4]);
+    BVH_CUDA_TRY(cudaMemsetAsync(state, 0, words * sizeof(uint32_t), stream));
+    int sm_count = 148;
+    BVH_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, bvh.device));
+    const uint32_t want = (n + 255) / 256, cap = (uint32_t)sm_count * 4;
+    ray_key_kernel<T><<<want < cap ? want : cap, 256, 0, stream>>>(d_rays, n, bvh.nodes, keys_a, state + 64);
+    BVH_CUDA_TRY(radix_sort_onesweep<uint32_t>(keys_a, vals_a, keys_b, vals_b, state, n, 30, stream));
+    *order = vals_a;                                          // four passes: the result is back in buffer A
+    return 0;
+}
 
 template <typename KernelT>
 int configure_smem(KernelT kernel, size_t smem_bytes) {
@@ -943,6 +1013,14 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     }
     args.next_ray = bvh.scratch;
     args.status = reinterpret_cast<uint32_t*>(bvh.scratch + 1);
+    // ray reordering: persistent kernels without bulk-copied ray chunks (a chunk is no longer contiguous); not in
+    // gather mode (its staging groups are runs of consecutive ray indices), not for the diagnostic kernels
+    RayOrderScratch order_scratch(stream);
+    args.order = nullptr;
+    if ((flags & kTraceSortRays) && !gather && !simple && !stats && args.variant != 2 && n >= (1u << 16) && n < 0xFFFFFFFFull) {
+        if (make_ray_order(bvh, d_rays, (uint32_t)n, order_scratch, &args.order, stream)) return -1;
+        args.use_tma = false;
+    }
     int rc;
     const bool any = (flags & kTraceAnyHit) != 0, robust = (flags & kTraceRobust) != 0;
     const bool staged = gather != nullptr;                  // gather mode: the kernels with warp-aggregated hit stores

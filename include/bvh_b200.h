@@ -56,8 +56,10 @@ enum bvh_intersect_flags {
     BVH_KERNEL_NO_TMA    = 1u << 9,  /* persistent, one lane per ray, rays read with streaming loads */
     BVH_KERNEL_TMA       = 1u << 10, /* persistent, one lane per ray, ray chunks staged with cp.async.bulk (TMA) */
     BVH_KERNEL_PAIR      = 1u << 11, /* persistent, two lanes per ray (one child box each) */
-    BVH_KERNEL_WIDE      = 1u << 12  /* persistent, compressed 4-wide tree derived from the binary one (float; canonical
+    BVH_KERNEL_WIDE      = 1u << 12, /* persistent, compressed 4-wide tree derived from the binary one (float; canonical
                                         tie-break and fast slab test only — otherwise the binary kernels are used) */
+    BVH_SORT_RAYS        = 1u << 13  /* incoherent batches: traverse the rays in the Morton order of their origins (device
+                                        radix sort of ray indices, ~1 ms per 10M rays); hits[i] still answers rays[i] */
 };
 
 /* What bvhNN_get_property reports about a handle. */

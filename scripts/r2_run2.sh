@@ -33,6 +33,9 @@ for c in c3 c5; do
     timeout 400 python bench.py --config $c --kernel $k --steps 10 --warmup 3 --no-e2e > gpurun_out/r2b_bench_${c}_$k.log 2>&1; line "$c $k" gpurun_out/r2b_bench_${c}_$k.log
   done
 done
+for k in auto wide; do
+  timeout 400 python bench.py --config c3 --kernel $k --sort-rays --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r2b_bench_c3_${k}_sorted.log 2>&1; line "c3 $k sorted rays" gpurun_out/r2b_bench_c3_${k}_sorted.log
+done
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 300 --csv --log-file gpurun_out/r2b_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r2b_ncu_launches.log 2>&1
 echo "ncu launches rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:treelet_kernel -s 2 -c 1 -o gpurun_out/r2b_treelet python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/r2b_ncu_treelet.log 2>&1

@@ -708,3 +708,25 @@ def test_wide_kernel_speculation_keeps_the_answers(gpu_lib, oracle, kind):
     finally:
         api.set_option("speculate", 0)
         api.set_option("wide_budget", 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_sorted_ray_order_keeps_the_answers(gpu_lib, dtype):
+    """BVH_SORT_RAYS traverses an incoherent batch in the Morton order of its origins; hits[i] must still answer
+    rays[i], bit for bit (closest hit, both kernels) and verdict for verdict (any-hit), NaN origins included."""
+    api = gpu_lib
+    tris = scenes.soup(100_000, seed=4).astype(dtype)
+    rays = scenes.incoherent_rays(tris.astype(np.float32), 200_003, seed=8).astype(dtype)
+    rays[17, 0] = np.nan
+    bvh = api.Bvh.build_triangles(tris)
+    base = bvh.intersect_rays(rays)
+    got = bvh.intersect_rays(rays, flags=api.SORT_RAYS)
+    assert np.array_equal(got.view(np.uint8), base.view(np.uint8))
+    occluded = bvh.intersect_rays(rays, flags=api.ANY_HIT)["prim_id"] != (INVALID if dtype == np.float32 else 0xFFFFFFFFFFFFFFFF)
+    got_any = bvh.intersect_rays(rays, flags=api.ANY_HIT | api.SORT_RAYS)["prim_id"] != (INVALID if dtype == np.float32 else 0xFFFFFFFFFFFFFFFF)
+    assert np.array_equal(got_any, occluded)
+    if dtype == np.float32:
+        wide = bvh.intersect_rays(rays, flags=api.KERNEL_WIDE)
+        wide_sorted = bvh.intersect_rays(rays, flags=api.KERNEL_WIDE | api.SORT_RAYS)
+        assert np.array_equal(wide_sorted.view(np.uint8), wide.view(np.uint8))

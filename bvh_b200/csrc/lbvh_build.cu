@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <string>
 
+#include <cooperative_groups.h>
 #include <cuda/atomic>
 
 #include "build_core.cuh"
@@ -550,14 +551,62 @@ __global__ void wide_init_kernel(uint2* frontier, uint32_t* counters) {
 // Builds (or rebuilds, after a refit) bvh.wide from the binary tree.  `levels` bounds the number of
 // collapse rounds (binary depth + 1 is always enough).  Leaves the number of wide levels in counters[63]
 // of the returned scratch, which the caller reads back together with its other results.
+// All levels in ONE cooperative launch: the grid walks the frontiers level by level with a grid-wide barrier in
+// between (the per-level launches of the first version cost ~10 us each, 0.28 ms per million triangles; a barrier
+// is ~2 us).  counters[1 + L] = size of frontier L is complete when the barrier after level L - 1 has been passed.
+__global__ void __launch_bounds__(kBlock)
+wide_collapse_all_kernel(const DevNode<float>* __restrict__ nodes, WideNode* __restrict__ wide,
+                         uint2* __restrict__ frontier_a, uint2* __restrict__ frontier_b, uint32_t* __restrict__ counters, int max_levels) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const uint32_t stride = gridDim.x * kBlock;
+    for (int level = 0; level < max_levels; ++level) {
+        const uint32_t count = *reinterpret_cast<volatile uint32_t*>(counters + 1 + level);
+        if (count == 0) break;                                          // (the same value for every thread of the grid)
+        const uint2* frontier_in = (level & 1) ? frontier_b : frontier_a;
+        uint2* frontier_out = (level & 1) ? frontier_a : frontier_b;
+        for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < count; i += stride) {
+            if (i == 0) atomicMax(&counters[63], (uint32_t)level + 1);
+            const uint2 item = frontier_in[i];
+            uint32_t slot[4];
+            const int used = wide_gather_children(nodes, item.x, slot);
+            WideNode w;
+            bool is_inner[4];
+            wide_encode(nodes, slot, used, w, is_inner);
+            for (int c = 0; c < used; ++c) {
+                if (!is_inner[c]) continue;
+                const uint32_t wide_index = atomicAdd(&counters[0], 1u);
+                w.child[c] = wide_index << kPrimCountBits;
+                frontier_out[atomicAdd(&counters[2 + level], 1u)] = make_uint2(slot[c], wide_index);
+            }
+            const uint4* src = reinterpret_cast<const uint4*>(&w);
+            uint4* dst = reinterpret_cast<uint4*>(wide + item.y);
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = src[k];
+        }
+        grid.sync();
+    }
+}
+
 int build_wide(DeviceBvh<float>& bvh, uint32_t levels, uint32_t* d_counters, uint2* d_frontier_a, uint2* d_frontier_b,
                cudaStream_t stream) {
     const uint32_t n = bvh.prim_count;
     if (!bvh.wide && device_alloc(reinterpret_cast<void**>(&bvh.wide), (size_t)(n ? n : 1) * sizeof(WideNode), stream)) return -1;
     wide_init_kernel<<<1, 64, 0, stream>>>(d_frontier_a, d_counters);
     if (levels > (uint32_t)kWideMaxLevels) levels = kWideMaxLevels;
+    int cooperative = 0, sm_count = 148, per_sm = 0;
+    cudaDeviceGetAttribute(&cooperative, cudaDevAttrCooperativeLaunch, bvh.device);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, bvh.device);
+    if (cooperative && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wide_collapse_all_kernel, kBlock, 0) == cudaSuccess && per_sm > 0) {
+        if (per_sm > 4) per_sm = 4;                                       // plenty for the widest frontier, cheaper barriers
+        const DevNode<float>* nodes = bvh.nodes; WideNode* wide = bvh.wide;
+        int max_levels = (int)levels;
+        void* args[] = { &nodes, &wide, &d_frontier_a, &d_frontier_b, &d_counters, &max_levels };
+        BVH_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(wide_collapse_all_kernel), dim3((unsigned)(sm_count * per_sm)), dim3(kBlock), args, 0, stream));
+        return 0;
+    }
+    cudaGetLastError();
     uint64_t bound = 1;
-    for (uint32_t level = 0; level < levels; ++level) {
+    for (uint32_t level = 0; level < levels; ++level) {                   // no cooperative launch: one launch per level
         const uint64_t items = bound < n ? bound : n;                     // frontier L has at most min(4^L, n) items
         const unsigned blocks = (unsigned)((items + kBlock - 1) / kBlock);
         wide_collapse_kernel<<<blocks, kBlock, 0, stream>>>(bvh.nodes, bvh.wide, (level & 1) ? d_frontier_b : d_frontier_a,
@@ -572,7 +621,7 @@ inline int build_wide(DeviceBvh<double>&, uint32_t, uint32_t*, uint2*, uint2*, c
 // The wide tree is derived lazily, the first time a trace asks for it (trace_rays), unless the
 // environment asks for it at build time (experiments: BVH_B200_USE_WIDE=1 makes it the default path).
 bool wide_enabled() {
-    return tunables().use_wide.load() > 0;
+    return tunables().use_wide.load() != 0;                  // -1 (auto) and 1: derive the wide tree with the build
 }
 
 struct Scratch {
@@ -592,20 +641,10 @@ struct Scratch {
 
 // Collapses the binary tree of `bvh` into its wide companion (float trees only) and records the wide
 // depth.  Synchronises the stream.
-template <typename T> int make_wide_tree(DeviceBvh<T>& bvh, cudaStream_t stream, bool force = false) {
-    if (sizeof(T) != 4 || bvh.wide_unavailable) return 0;
-    if (!force && !wide_enabled() && !bvh.wide) return 0;        // not wanted yet (a stale one is always refreshed)
-    Scratch scratch(stream);
-    uint32_t* counters; uint2* fa; uint2* fb;
-    const size_t cap = bvh.prim_count ? bvh.prim_count : 1;
-    if (scratch.alloc(&counters, 64) || scratch.alloc(&fa, cap) || scratch.alloc(&fb, cap)) return -1;
-    if (build_wide(bvh, bvh.depth + 1, counters, fa, fb, stream)) return -1;
-    uint32_t host_counters[64];
-    BVH_CUDA_TRY(cudaMemcpyAsync(host_counters, counters, sizeof(host_counters), cudaMemcpyDeviceToHost, stream));
-    BVH_CUDA_TRY(cudaStreamSynchronize(stream));
+// After the counters of a wide collapse limited to `rounds` levels came back: depth and size, or the fallback.
+template <typename T> void finish_wide_tree(DeviceBvh<T>& bvh, const uint32_t (&host_counters)[64], uint32_t rounds, cudaStream_t stream) {
     bvh.wide_depth = host_counters[63];
     bvh.wide_count = host_counters[0];
-    const uint32_t rounds = bvh.depth + 1 < (uint32_t)kWideMaxLevels ? bvh.depth + 1 : (uint32_t)kWideMaxLevels;
     if (host_counters[1 + rounds] != 0) {
         // the collapse stopped at its level limit with nodes still waiting: their wide records were never written.
         // Such a (degenerate, very deep) tree is traced with the binary kernels only.
@@ -613,6 +652,21 @@ template <typename T> int make_wide_tree(DeviceBvh<T>& bvh, cudaStream_t stream,
         bvh.wide = nullptr; bvh.wide_depth = 0; bvh.wide_count = 0;
         bvh.wide_unavailable = true;
     }
+}
+
+template <typename T> int make_wide_tree(DeviceBvh<T>& bvh, cudaStream_t stream, bool force = false) {
+    if (sizeof(T) != 4 || bvh.wide_unavailable) return 0;
+    if (!force && !wide_enabled() && !bvh.wide) return 0;        // not wanted yet (a stale one is always refreshed)
+    Scratch scratch(stream);
+    uint32_t* counters; uint2* fa; uint2* fb;
+    const size_t cap = bvh.prim_count ? bvh.prim_count : 1;
+    if (scratch.alloc(&counters, 64) || scratch.alloc(&fa, cap) || scratch.alloc(&fb, cap)) return -1;
+    const uint32_t rounds = bvh.depth + 1 < (uint32_t)kWideMaxLevels ? bvh.depth + 1 : (uint32_t)kWideMaxLevels;
+    if (build_wide(bvh, rounds, counters, fa, fb, stream)) return -1;
+    uint32_t host_counters[64];
+    BVH_CUDA_TRY(cudaMemcpyAsync(host_counters, counters, sizeof(host_counters), cudaMemcpyDeviceToHost, stream));
+    BVH_CUDA_TRY(cudaStreamSynchronize(stream));
+    finish_wide_tree(bvh, host_counters, rounds, stream);
     return 0;
 }
 
@@ -705,8 +759,20 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     compact_scatter_kernel<T><<<(pairs + kBlock) / kBlock, kBlock, 0, stream>>>(sparse, out.nodes, alive, rank, pairs);
     BVH_CUDA_TRY(cudaGetLastError());
 
+    // the compressed 4-wide companion tree of the default traversal path, derived in the same stream before the one
+    // host round trip of the build (float trees; the level limit replaces the depth, which is still on the device)
+    const bool with_wide = sizeof(T) == 4 && wide_enabled();
+    uint32_t* wide_counters = nullptr;
+    uint32_t host_wide[64] = {};
+    if (with_wide) {
+        uint2* fa; uint2* fb;
+        if (scratch.alloc(&wide_counters, 64) || scratch.alloc(&fa, n) || scratch.alloc(&fb, n)) return -1;
+        if (build_wide(out, (uint32_t)kWideMaxLevels, wide_counters, fa, fb, stream)) return -1;
+    }
+
     uint32_t host_info[4] = { 0, 0, 0, 0 }, host_treelets = 0;
     BVH_CUDA_TRY(cudaMemcpyAsync(host_info, info, sizeof(host_info), cudaMemcpyDeviceToHost, stream));
+    if (with_wide) BVH_CUDA_TRY(cudaMemcpyAsync(host_wide, wide_counters, sizeof(host_wide), cudaMemcpyDeviceToHost, stream));
     if (treelets) BVH_CUDA_TRY(cudaMemcpyAsync(&host_treelets, treelet_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     BVH_CUDA_TRY(cudaStreamSynchronize(stream));
     // The depth travels through the hierarchy pass in 7 bits of the node's spare word (AuxPack).  It cannot get
@@ -719,7 +785,7 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     out.quality = options.quality;
     out.node_slots = 2 * (size_t)(pairs > 0 ? host_info[3] : 0u) + 2;      // slot 0, the root, 2 x live pairs
     out.compact = true;
-    if (make_wide_tree(out, stream)) return -1;
+    if (with_wide) finish_wide_tree(out, host_wide, (uint32_t)kWideMaxLevels, stream);
     return 0;
 }
 

@@ -992,7 +992,7 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     if constexpr (sizeof(T) == 4) {
         const bool explicit_binary = (flags & (kTracePair | kTraceNoTma | kTraceTma | kTraceSimple)) != 0;
         const bool order_sensitive = (flags & (kTraceLastVisited | kTraceRobust)) != 0 || d_ray_stats != nullptr;
-        const bool want_wide = !order_sensitive && ((flags & kTraceWide) || (!explicit_binary && (tunables().use_wide.load() > 0)));
+        const bool want_wide = !order_sensitive && ((flags & kTraceWide) || (!explicit_binary && (tunables().use_wide.load() != 0)));
         if (want_wide && !bvh.wide && !bvh.wide_unavailable) {      // derived on first use
             if (rebuild_wide(const_cast<DeviceBvh<T>&>(bvh), stream, true)) return -1;
         }

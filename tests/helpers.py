@@ -163,3 +163,23 @@ def assert_hits_equal(got, want, what=""):
 def hits_tuple(hits):
     """structured bvh_hit array -> (ids, t, u, v) with 32-bit ids"""
     return hits["prim_id"].astype(np.uint32), hits["t"], hits["u"], hits["v"]
+
+
+def assert_hits_conservative(got, want, tris, rays, oracle, what="", max_fraction=1e-5):
+    """The default traversal path (compressed 4-wide tree) against an exact binary traversal of the reference's
+    algorithm (`want` = (ids, t, u, v)).  The wide boxes enclose the binary ones, the triangle test and the
+    tie-break are the same, so the results are identical except where the binary traversal itself misses a true hit
+    because the reference's FAST slab test is not watertight (a hit point exactly on a box face).  There — and only
+    there — the wide path may report a closer hit, or the same distance with a lower id, and that hit must be real."""
+    g = hits_tuple(got) if not isinstance(got, tuple) else got
+    bits = lambda a: np.asarray(a).view(np.uint32 if np.asarray(a).dtype.itemsize == 4 else np.uint64)
+    same = (np.asarray(g[0]).astype(np.uint64) == np.asarray(want[0]).astype(np.uint64))
+    for k in (1, 2, 3):
+        same &= bits(g[k]) == bits(want[k])
+    bad = np.nonzero(~same)[0]
+    assert bad.size <= max(2, max_fraction * same.size), f"{what}: {bad.size} of {same.size} rays differ"
+    for i in bad:
+        assert g[0][i] != INVALID, f"{what}: ray {i} lost its hit"
+        assert g[1][i] < want[1][i] or (g[1][i] == want[1][i] and g[0][i] < want[0][i]), f"{what}: ray {i} is not closer"
+        one = oracle.brute_force(tris[int(g[0][i]):int(g[0][i]) + 1], rays[i:i + 1])
+        assert one[0][0] == 0 and one[1][0] == g[1][i] and one[2][0] == g[2][i] and one[3][0] == g[3][i], f"{what}: ray {i}: not a real hit"

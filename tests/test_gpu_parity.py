@@ -11,7 +11,7 @@ import pytest
 from bvh_b200 import scenes
 from oracle.pyoracle import ANY_HIT as O_ANY, ROBUST as O_ROBUST, TIE_LOWEST_ID as O_LOWEST
 from tests.conftest import golden
-from tests.helpers import INVALID, assert_hits_equal, hits_tuple
+from tests.helpers import INVALID, assert_hits_conservative, assert_hits_equal, hits_tuple
 
 pytestmark = pytest.mark.gpu
 
@@ -158,7 +158,7 @@ def test_ten_million_triangles_config4(gpu_lib, oracle):
     oracle.set_triangles(tree, tris)
     sample = np.sort(np.random.RandomState(4).choice(rays.shape[0], 5000, replace=False))
     want = oracle.trace(tree, rays[sample], flags=O_LOWEST)
-    assert_hits_equal(hits_tuple(hits[sample]), want, "soup-10M sample vs oracle")
+    assert_hits_conservative(hits[sample], want, tris, rays[sample], oracle, "soup-10M sample vs oracle")
 
 
 def test_build_from_boxes_and_centres(gpu_lib, oracle):
@@ -331,7 +331,9 @@ def test_full_size_properties(gpu_lib, oracle, kind):
     bvh = api.Bvh.build_triangles(tris)
     rays = scenes.make_primary(kind, 3163, 3163)
     m = rays.shape[0]
-    hits = bvh.intersect_rays(rays)
+    hits = bvh.intersect_rays(rays, flags=api.KERNEL_TMA)          # the exact binary traversal: the base of the comparisons
+    default = bvh.intersect_rays(rays)                              # the library's default path
+    assert bvh.properties()["last_kernel"] == "trace_wide_kernel"
     ids = hits["prim_id"]
     hit = ids != INVALID
     assert 0.3 < hit.mean() <= 1.0
@@ -347,6 +349,7 @@ def test_full_size_properties(gpu_lib, oracle, kind):
     # a box face: the leaf holding the other triangle of a shared edge is culled by one ulp), and there it can
     # only report a closer hit, or the same distance with a lower id — and that hit must be a real one
     wide = bvh.intersect_rays(rays, flags=api.KERNEL_WIDE)
+    assert np.array_equal(wide.view(np.uint8), default.view(np.uint8))        # (the default IS this kernel)
     differs = np.nonzero((wide.view(np.uint8).reshape(m, 16) != hits.view(np.uint8).reshape(m, 16)).any(axis=1))[0]
     assert differs.size < 1e-5 * m, differs.size
     for i in differs:
@@ -376,6 +379,7 @@ def test_full_size_properties(gpu_lib, oracle, kind):
     oracle.set_triangles(tree, tris)
     want = oracle.trace(tree, rays[sample], flags=O_LOWEST)
     assert_hits_equal(hits_tuple(hits[sample]), want, f"{kind}-1M sample vs oracle")
+    assert_hits_conservative(default[sample], want, tris, rays[sample], oracle, f"{kind}-1M default path vs oracle")
     from oracle.pyoracle import Ref, ref_available
     if ref_available():
         ref = Ref()

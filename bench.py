@@ -441,25 +441,41 @@ def main():
             raise SystemExit(api.last_error())
 
     tracer, gather_desc = None, None
-    if world > 1 and args.gather != "nccl":
+    candidates = [] if world == 1 else (["peer", "direct"] if args.gather == "auto" else [] if args.gather == "nccl" else [args.gather])
+    for mode in candidates:                      # auto: staged bulk copies, then direct peer stores, then NCCL (below)
         try:
             from bvh_b200.multi_gpu import FusedGatherTracer
-            if args.gather == "direct":
-                api.set_option("gather_staging", 0)
-            tracer = FusedGatherTracer(bvh, rays, hit_words, flags=api.DEVICE_POINTERS | base_flags | kflag,
-                                       mode="peer" if args.gather == "direct" else args.gather)
-            how = ("one multimem.st per record through the NVSwitch multicast address" if tracer.mode == "multicast" else
-                   "one 16-byte NVLink peer store per record and rank" if args.gather == "direct" else
+            api.set_option("gather_staging", 0 if mode == "direct" else 1)
+            cand = FusedGatherTracer(bvh, rays, hit_words, flags=api.DEVICE_POINTERS | base_flags | kflag,
+                                     mode="multicast" if mode == "multicast" else "peer")
+            how = ("one multimem.st per record through the NVSwitch multicast address" if mode == "multicast" else
+                   "one 16-byte NVLink peer store per record and rank" if mode == "direct" else
                    "each warp stages the records of 32 consecutive rays in shared memory and sends the 512-byte block to every rank "
                    "with one cp.async.bulk (shared -> peer global over NVLink)")
+            # self-check before anything is timed: every rank must hold, for every shard, exactly the records its owner
+            # gets from a plain (ungathered) launch
+            truth = torch.empty((n_rays, hit_words), dtype=torch.int32, device=device)
+            trace(0, n_rays, truth)
+            cand.step()
+            cand.check()
+            torch.cuda.synchronize()
+            got = cand.global_hits().view(world, n_rays, hit_words).to(torch.int64).sum(dim=(1, 2))
+            owners = torch.empty(world, dtype=torch.int64, device=device)
+            dist.all_gather_into_tensor(owners, truth.to(torch.int64).sum().reshape(1))
+            good = torch.tensor([1 if torch.equal(got, owners) else 0], device=device)
+            dist.all_reduce(good, op=dist.ReduceOp.MIN)
+            del truth
+            if not bool(good.item()):
+                raise RuntimeError(f"fused gather ({mode}) delivered records that differ from the owners' plain launches")
+            tracer = cand
             gather_desc = (f"fused in the traversal kernel into all {world} ranks' symmetric-memory buffers (double-buffered): {how}; "
                            "one symmetric-memory barrier per step")
-        except Exception as exc:                 # no symmetric memory on this box: NCCL all-gather instead
+            break
+        except Exception as exc:
             if args.gather != "auto":
                 raise
             if rank == 0:
-                print(f"[bench] fused gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
-            tracer = None
+                print(f"[bench] fused gather mode {mode} unavailable ({type(exc).__name__}: {exc})", file=sys.stderr)
     if tracer is None:
         tracer = ShardedTracer(n_rays, hit_words, torch.int32, device, trace, chunks=args.chunks if world > 1 else 1)
         if world > 1:

@@ -382,16 +382,29 @@ def test_full_size_properties(gpu_lib, oracle, kind):
     assert_hits_conservative(default[sample], want, tris, rays[sample], oracle, f"{kind}-1M default path vs oracle")
     from oracle.pyoracle import Ref, ref_available
     if ref_available():
+        # ALL rays of the batch against the unmodified reference on its own High-quality tree (all host threads)
         ref = Ref()
         bb, cc = ref.tri_bboxes_centers(tris)
         rtree = ref.build(bb, cc, quality="high", threads=0)
         ref.set_triangles(rtree, tris)
-        want = ref.trace(rtree, rays[sample], flags=O_LOWEST, threads=0)
+        want = ref.trace(rtree, rays, flags=O_LOWEST, threads=0)
+        for name, got in (("exact binary traversal", hits), ("default path", default)):
+            g = hits_tuple(got)
+            differs = np.nonzero((g[0] != want[0]) | (g[1].view(np.uint32) != want[1].view(np.uint32)) |
+                                 (g[2].view(np.uint32) != want[2].view(np.uint32)) | (g[3].view(np.uint32) != want[3].view(np.uint32)))[0]
+            # Two different trees agree on every ray except where the reference's FAST slab test is not watertight
+            # (a hit point exactly on a box face is culled in one tree and not in the other): there one side reports
+            # a farther hit or a miss.  Both answers must then be real hits, and such rays must be a handful.
+            assert differs.size <= 1e-5 * m, f"{name}: {differs.size} of {m} rays differ from the reference's own tree"
+            for i in differs:
+                for ids_, t_, u_, v_ in ((g[0][i], g[1][i], g[2][i], g[3][i]), (want[0][i], want[1][i], want[2][i], want[3][i])):
+                    if ids_ == INVALID:
+                        continue
+                    one = oracle.brute_force(tris[int(ids_):int(ids_) + 1], rays[i:i + 1])
+                    assert one[0][0] == 0 and one[1][0] == t_ and one[2][0] == u_ and one[3][0] == v_, f"{name}: ray {i}: not a real hit"
+                assert g[1][i] != want[1][i] or g[0][i] != want[0][i]
         got = hits_tuple(hits[sample])
-        same = got[0] == want[0]
-        # the fast slab test is tree-dependent only for rays grazing box faces exactly; require exactness
-        assert same.all(), f"{(~same).sum()} ids differ from the reference's own tree"
-        assert_hits_equal(got, want, f"{kind}-1M sample vs reference tree")
+        assert_hits_equal(got, tuple(w[sample] for w in want), f"{kind}-1M sample vs reference tree")
 
 
 def test_incoherent_any_hit_full_size(gpu_lib, oracle):

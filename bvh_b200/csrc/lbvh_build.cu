@@ -697,6 +697,7 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     if (d_verts && device_alloc(reinterpret_cast<void**>(&out.tris), (size_t)n * sizeof(DevTri<T>), stream)) return -1;
 
     centre_bounds_kernel<T><<<grid, kBlock, 0, stream>>>(centre_src, n, mode, partials);
+    uint32_t* sort_status = nullptr;
     if (tunables().sort_onesweep.load() != 0) {
         const int passes = radix_passes(key_bits);
         uint32_t* state;
@@ -705,6 +706,7 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
         BVH_CUDA_TRY(cudaMemsetAsync(state, 0, words * sizeof(uint32_t), stream));
         morton_kernel<T, K><<<grid, kBlock, 0, stream>>>(centre_src, n, mode, partials, grid, keys_a, flags, alive, state + 64, passes);
         BVH_CUDA_TRY(radix_sort_onesweep<K>(keys_a, out.prim_ids, keys_b, vals_b, state, n, key_bits, stream));
+        sort_status = state + kOsStatusWord;
     } else {
         morton_kernel<T, K><<<grid, kBlock, 0, stream>>>(centre_src, n, mode, partials, grid, keys_a, flags, alive, nullptr, 0);
         BVH_CUDA_TRY(radix_sort_pairs<K>(keys_a, out.prim_ids, keys_b, vals_b, tile_hist, n, key_bits, stream));
@@ -773,11 +775,14 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     uint32_t host_info[4] = { 0, 0, 0, 0 }, host_treelets = 0;
     BVH_CUDA_TRY(cudaMemcpyAsync(host_info, info, sizeof(host_info), cudaMemcpyDeviceToHost, stream));
     if (with_wide) BVH_CUDA_TRY(cudaMemcpyAsync(host_wide, wide_counters, sizeof(host_wide), cudaMemcpyDeviceToHost, stream));
+    uint32_t host_sort_status = 0;
+    if (sort_status) BVH_CUDA_TRY(cudaMemcpyAsync(&host_sort_status, sort_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     if (treelets) BVH_CUDA_TRY(cudaMemcpyAsync(&host_treelets, treelet_words, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     BVH_CUDA_TRY(cudaStreamSynchronize(stream));
     // The depth travels through the hierarchy pass in 7 bits of the node's spare word (AuxPack).  It cannot get
     // there: distinct keys split within 63 levels, a run of equal keys is balanced by the index tie-break
     // (<= 28 more levels for 2^27 primitives).  A saturated value would under-size the traversal stacks: refuse.
+    if (host_sort_status != 0) { set_error("build: the radix sort's look-back timed out (a tile never published its counts)"); return -1; }
     if (host_info[0] >= 127u) { set_error("build: tree depth exceeds what the build pass can track (127 levels)"); return -1; }
     out.depth = host_info[0] + (treelets ? host_info[2] : 0u);
     out.treelets = host_treelets;

@@ -168,6 +168,7 @@ rs_scatter_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ va
 // three launches: 4 + 8 + 8 -> 8 + 8 bytes per key and pass.
 // Descriptor word: bits 31..30 = 0 not ready, 1 aggregate, 2 inclusive prefix; bits 29..0 = count.
 constexpr uint32_t kOsAggregate = 1u << 30, kOsInclusive = 2u << 30, kOsCountMask = (1u << 30) - 1u;
+constexpr uint32_t kOsMaxPolls = 1u << 24;      // look-back polls of one descriptor before a tile gives up (a hang becomes an error)
 
 __device__ __forceinline__ uint32_t os_load(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 __device__ __forceinline__ void os_store(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
@@ -176,7 +177,8 @@ template <typename K, bool kIota>
 __global__ void __launch_bounds__(kRsBlock)
 rs_onesweep_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    K* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, int shift,
-                   const uint32_t* __restrict__ digit_totals, uint32_t* __restrict__ desc, uint32_t* __restrict__ ticket) {
+                   const uint32_t* __restrict__ digit_totals, uint32_t* __restrict__ desc, uint32_t* __restrict__ ticket,
+                   uint32_t* __restrict__ status) {
     __shared__ uint32_t warp_hist[kRsWarps][kRsBins];     // 8 KB
     __shared__ uint32_t bin_base[kRsBins];
     __shared__ uint32_t scan_tmp[kRsWarps];
@@ -252,8 +254,9 @@ rs_onesweep_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
             os_store(mine, count | kOsAggregate);
             for (uint32_t p = tile; p-- > 0;) {
                 const uint32_t* theirs = desc + (size_t)p * kRsBins + tid;
-                uint32_t v;
-                do { v = os_load(theirs); } while ((v >> 30) == 0u);
+                uint32_t v, polls = 0;
+                do { v = os_load(theirs); } while ((v >> 30) == 0u && ++polls < kOsMaxPolls);
+                if ((v >> 30) == 0u) { atomicExch(status, 1u); break; }      // a predecessor never published: give up (the caller reports it)
                 before += v & kOsCountMask;
                 if ((v >> 30) == 2u) break;
             }
@@ -274,6 +277,7 @@ rs_onesweep_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
     }
 }
 
+constexpr int kOsStatusWord = 32;               // state[32]: set to 1 when a look-back gave up
 // Words of the one-sweep state for n keys and `passes` passes: [0, 64) tickets, then passes x 256 digit totals,
 // then passes x tiles x 256 descriptor words.  The caller zeroes it and has the digit totals filled in (digit d of
 // pass p at state[64 + 256 * p + d]) before radix_sort_onesweep runs.
@@ -296,9 +300,9 @@ inline cudaError_t radix_sort_onesweep(K* keys_a, uint32_t* vals_a, K* keys_b, u
     for (int pass = 0; pass < passes; ++pass) {
         uint32_t* d = desc + (size_t)pass * num_tiles * kRsBins;
         if (pass == 0)
-            rs_onesweep_kernel<K, true><<<num_tiles, kRsBlock, 0, stream>>>(kin, vin, kout, vout, n, pass * 8, totals + pass * kRsBins, d, tickets + pass);
+            rs_onesweep_kernel<K, true><<<num_tiles, kRsBlock, 0, stream>>>(kin, vin, kout, vout, n, pass * 8, totals + pass * kRsBins, d, tickets + pass, tickets + kOsStatusWord);
         else
-            rs_onesweep_kernel<K, false><<<num_tiles, kRsBlock, 0, stream>>>(kin, vin, kout, vout, n, pass * 8, totals + pass * kRsBins, d, tickets + pass);
+            rs_onesweep_kernel<K, false><<<num_tiles, kRsBlock, 0, stream>>>(kin, vin, kout, vout, n, pass * 8, totals + pass * kRsBins, d, tickets + pass, tickets + kOsStatusWord);
         K* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }

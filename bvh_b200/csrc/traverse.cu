@@ -882,6 +882,8 @@ int make_ray_order(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, uint32_t n,
     ray_key_kernel<T><<<want < cap ? want : cap, 256, 0, stream>>>(d_rays, n, bvh.nodes, keys_a, state + 64);
     BVH_CUDA_TRY(radix_sort_onesweep<uint32_t>(keys_a, vals_a, keys_b, vals_b, state, n, 30, stream));
     *order = vals_a;                                          // four passes: the result is back in buffer A
+    // (a timed-out look-back leaves a wrong but in-range order only if it also leaves duplicates; the kernels index
+    // rays[order[p]] with order values < n in either case because vals start as the identity permutation)
     return 0;
 }
 

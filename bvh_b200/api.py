@@ -109,6 +109,8 @@ def lib() -> C.CDLL:
         f("get_depth").argtypes = [P]
         f("get_property").restype = SZ
         f("get_property").argtypes = [P, C.c_int]
+        f("get_prim_ids").restype = P
+        f("get_prim_ids").argtypes = [P]
         for name in ("intersect_ray", "intersect_ray_any", "intersect_ray_robust", "intersect_ray_any_robust"):
             f(name).argtypes = [P, P, P]
         n = lambda name: getattr(L, f"bvh_node{s}_{name}")
@@ -338,8 +340,10 @@ class Bvh:
         nodes = np.frombuffer(buf, dtype=rec, count=n)
         bounds = nodes["bounds"].copy()
         index_values = nodes["index"].astype(np.uint64)
-        get_id = self._f("get_prim_id")
-        ids = np.fromiter((get_id(self.handle, i) for i in range(p)), dtype=np.uint64, count=p)
+        base_ids = self._f("get_prim_ids")(self.handle)
+        if not base_ids:
+            raise BvhError(last_error())
+        ids = np.frombuffer((C.c_char * (p * 8)).from_address(base_ids), dtype=np.uint64, count=p).copy()
         return bounds, index_values, ids
 
     def refit(self) -> None:

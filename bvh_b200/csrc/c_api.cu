@@ -860,6 +860,11 @@ BVH_EXPORT void bvh_thread_pool_destroy(struct bvh_thread_pool* pool) { delete p
         if (!h || ensure_device(*h)) return 0;                                                                     \
         return h->dev.depth;                                                                                       \
     }                                                                                                              \
+    BVH_EXPORT const size_t* bvh##S##_get_prim_ids(struct bvh##S* bvh) {                                           \
+        auto h = H(T, bvh);                                                                                        \
+        if (!h || download_mirror(*h)) return nullptr;                                                             \
+        return h->prim_ids.data();                                                                                 \
+    }                                                                                                              \
     BVH_EXPORT size_t bvh##S##_get_property(struct bvh##S* bvh, int property) {                                    \
         auto h = H(T, bvh);                                                                                        \
         if (!h || ensure_device(*h)) return (size_t)-1;                                                            \

@@ -729,7 +729,7 @@ template <> struct CApi<float> {
     static size_t node_count(Handle* h) { return bvh3f_get_node_count(h); }
     static size_t prim_count(Handle* h) { return bvh3f_get_prim_count(h); }
     static const void* node0(Handle* h) { return bvh3f_get_node(h, 0); }
-    static size_t prim_id(Handle* h, size_t i) { return bvh3f_get_prim_id(h, i); }
+    static const size_t* prim_ids(Handle* h) { return bvh3f_get_prim_ids(h); }
     static int intersect(Handle* h, const RayPod* r, size_t n, HitPod* o, unsigned fl) { return bvh3f_intersect_rays(h, r, n, o, fl); }
 };
 template <> struct CApi<double> {
@@ -741,7 +741,7 @@ template <> struct CApi<double> {
     static size_t node_count(Handle* h) { return bvh3d_get_node_count(h); }
     static size_t prim_count(Handle* h) { return bvh3d_get_prim_count(h); }
     static const void* node0(Handle* h) { return bvh3d_get_node(h, 0); }
-    static size_t prim_id(Handle* h, size_t i) { return bvh3d_get_prim_id(h, i); }
+    static const size_t* prim_ids(Handle* h) { return bvh3d_get_prim_ids(h); }
     static int intersect(Handle* h, const RayPod* r, size_t n, HitPod* o, unsigned fl) { return bvh3d_intersect_rays(h, r, n, o, fl); }
 };
 } // namespace detail
@@ -782,7 +782,7 @@ public:
         bvh.nodes.resize(Api::node_count(handle));                 // the handle's mirror IS an array of Node<T,3>
         std::memcpy(bvh.nodes.data(), Api::node0(handle), bvh.nodes.size() * sizeof(Node));
         bvh.prim_ids.resize(Api::prim_count(handle));
-        for (size_t i = 0; i < bvh.prim_ids.size(); ++i) bvh.prim_ids[i] = Api::prim_id(handle, i);
+        if (!bvh.prim_ids.empty()) std::memcpy(bvh.prim_ids.data(), Api::prim_ids(handle), bvh.prim_ids.size() * sizeof(size_t));
         Api::destroy(handle);
         return bvh;
     }

@@ -137,7 +137,10 @@ BVH_API int bvh_optimize_nodes(void* nodes, size_t node_count, int dim, int is_d
     /* Longest chain of inner nodes below the root (the traversal stack bound). */                      \
     BVH_API size_t bvh##S##_get_depth(struct bvh##S* bvh);                                              \
     /* enum bvh_property; (size_t)-1 for an unknown property or a failed upload of an edited mirror. */  \
-    BVH_API size_t bvh##S##_get_property(struct bvh##S* bvh, int property);
+    BVH_API size_t bvh##S##_get_property(struct bvh##S* bvh, int property);                             \
+    /* The whole BVH-order -> original primitive id array of the host mirror (bvhNN_get_prim_count entries; what   \
+       bvhNN_get_prim_id reads one element of), valid until the handle is destroyed or rebuilt; NULL on failure. */ \
+    BVH_API const size_t* bvh##S##_get_prim_ids(struct bvh##S* bvh);
 
 BVH_B200_DECLARE(float, 3f)
 BVH_B200_DECLARE(double, 3d)

@@ -13,7 +13,7 @@ LEGACY_PER_SUFFIX = ["build", "destroy", "save", "load", "get_node", "get_prim_i
                      "append_node", "remove_last_node", "refit", "optimize", "intersect_ray_any",
                      "intersect_ray_any_robust", "intersect_ray", "intersect_ray_robust"]
 NODE_PER_SUFFIX = ["is_leaf", "get_prim_count", "set_prim_count", "get_first_id", "set_first_id", "get_bbox", "set_bbox"]
-BATCHED_3D = ["build_triangles", "set_triangles", "refit_triangles", "intersect_rays", "intersect_rays_gather", "intersect_rays_stats", "sync", "get_depth", "get_property"]
+BATCHED_3D = ["build_triangles", "set_triangles", "refit_triangles", "intersect_rays", "intersect_rays_gather", "intersect_rays_stats", "sync", "get_depth", "get_property", "get_prim_ids"]
 RUNTIME = ["bvh_last_error", "bvh_cuda_device_count", "bvh_cuda_set_device", "bvh_cuda_set_stream", "bvh_cuda_reset_stream", "bvh_host_alloc",
            "bvh_host_free", "bvh_cuda_trim", "bvh_set_option", "bvh_optimize_nodes", "bvh_thread_pool_create", "bvh_thread_pool_destroy"]
 

@@ -42,7 +42,7 @@ Tunables& tunables() {
         }
         t.e2e_chunks = (int)env("BVH_B200_E2E_CHUNKS", 0);
         t.variant = (int)env("BVH_B200_VARIANT", 1);
-        t.use_wide = (int)env("BVH_B200_USE_WIDE", -1);
+        t.use_wide = (int)env("BVH_B200_USE_WIDE", 0);
         const long budget = env("BVH_B200_INNER_BUDGET", 12);
         t.inner_budget = budget <= 0 ? 0xFFFFFFFFu : (uint32_t)budget;
         const long wbudget = env("BVH_B200_WIDE_BUDGET", 4);
@@ -50,7 +50,7 @@ Tunables& tunables() {
         t.watchdog = (uint32_t)env("BVH_B200_WATCHDOG", 1l << 26);
         t.gather_staging = (int)env("BVH_B200_GATHER_STAGING", 1);
         t.sort_onesweep = (int)env("BVH_B200_SORT_ONESWEEP", 1);
-        t.speculate = (int)env("BVH_B200_SPECULATE", 0);
+        t.treelet_blocks = (int)env("BVH_B200_TREELET_BLOCKS", 3);
     });
     return t;
 }
@@ -677,7 +677,7 @@ BVH_EXPORT int bvh_set_option(const char* name, long value) {
     else if (n == "watchdog") t.watchdog = (uint32_t)value;
     else if (n == "gather_staging") t.gather_staging = (int)value;
     else if (n == "sort_onesweep") t.sort_onesweep = (int)value;
-    else if (n == "speculate") t.speculate = (int)value;
+    else if (n == "treelet_blocks") t.treelet_blocks = (int)value;
     else { set_error("set_option: unknown option " + n); return -1; }
     return 0;
 }

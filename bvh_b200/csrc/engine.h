@@ -43,11 +43,11 @@ struct Tunables {
     std::atomic<int> hierarchy { 128 };         // leaves per block of the hierarchy kernel (64 / 128 / 256), 0: global flags only
     std::atomic<int> e2e_chunks { 0 };          // chunks of the host-buffer pipeline, 0: auto
     std::atomic<int> variant { 1 };             // persistent kernel: 1 TMA-staged ray chunks, 0 streaming loads
-    std::atomic<int> use_wide { -1 };           // -1: auto (wide tree where its semantics allow), 0 / 1
+    std::atomic<int> use_wide { 0 };            // 1: derive the compressed wide tree with the build and trace with it where its semantics allow
     std::atomic<uint32_t> inner_budget { 12 };  // inner steps per lane per round
     std::atomic<uint32_t> wide_budget { 4 };    // same for the wide kernel
     std::atomic<uint32_t> watchdog { 1u << 26 };
-    std::atomic<int> speculate { 0 };           // wide kernel: speculative descent past the first leaf of a round
+    std::atomic<int> treelet_blocks { 3 };      // treelet kernel: resident blocks per SM its registers are limited for (2 / 3 / 4)
     std::atomic<int> sort_onesweep { 1 };       // build: 1 one-sweep radix sort (one kernel per pass), 0 histogram / scan / scatter per pass
     std::atomic<int> gather_staging { 1 };      // fused gather: 1 warp-aggregated bulk stores, 0 one store per record and rank
 };

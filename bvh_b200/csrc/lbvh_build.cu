@@ -15,7 +15,6 @@
 #include <cstdlib>
 #include <string>
 
-#include <cooperative_groups.h>
 #include <cuda/atomic>
 
 #include "build_core.cuh"
@@ -275,8 +274,11 @@ void launch_hierarchy(const BuildParams<T>& p, const K* keys, const uint32_t* va
 // warp's registers plus a 3.3 KB (float) slice of the block's shared memory.
 constexpr int kTreeletWarps = 8;
 
-template <typename T>
-__global__ void __launch_bounds__(kTreeletWarps * 32)
+// kMinBlocks: resident blocks per SM the register allocation is held to (float: 2 -> 109 registers, 3 -> 77, 4 -> 64
+// with a 32-byte spill; ncu of the 2-block build: 24 % of the warp slots active, stalls dominated by fixed-latency
+// dependencies, i.e. too few warps to hide them).
+template <typename T, int kMinBlocks>
+__global__ void __launch_bounds__(kTreeletWarps * 32, kMinBlocks)
 treelet_kernel(const Treelet* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t* __restrict__ cursor,
                DevNode<T>* __restrict__ nodes, uint32_t* __restrict__ prim_ids, DevTri<T>* __restrict__ tris,
                const T* __restrict__ leaf_src, const T* __restrict__ centre_src, int leaf_mode, uint32_t min_leaf,
@@ -551,62 +553,16 @@ __global__ void wide_init_kernel(uint2* frontier, uint32_t* counters) {
 // Builds (or rebuilds, after a refit) bvh.wide from the binary tree.  `levels` bounds the number of
 // collapse rounds (binary depth + 1 is always enough).  Leaves the number of wide levels in counters[63]
 // of the returned scratch, which the caller reads back together with its other results.
-// All levels in ONE cooperative launch: the grid walks the frontiers level by level with a grid-wide barrier in
-// between (the per-level launches of the first version cost ~10 us each, 0.28 ms per million triangles; a barrier
-// is ~2 us).  counters[1 + L] = size of frontier L is complete when the barrier after level L - 1 has been passed.
-__global__ void __launch_bounds__(kBlock)
-wide_collapse_all_kernel(const DevNode<float>* __restrict__ nodes, WideNode* __restrict__ wide,
-                         uint2* __restrict__ frontier_a, uint2* __restrict__ frontier_b, uint32_t* __restrict__ counters, int max_levels) {
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-    const uint32_t stride = gridDim.x * kBlock;
-    for (int level = 0; level < max_levels; ++level) {
-        const uint32_t count = *reinterpret_cast<volatile uint32_t*>(counters + 1 + level);
-        if (count == 0) break;                                          // (the same value for every thread of the grid)
-        const uint2* frontier_in = (level & 1) ? frontier_b : frontier_a;
-        uint2* frontier_out = (level & 1) ? frontier_a : frontier_b;
-        for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < count; i += stride) {
-            if (i == 0) atomicMax(&counters[63], (uint32_t)level + 1);
-            const uint2 item = frontier_in[i];
-            uint32_t slot[4];
-            const int used = wide_gather_children(nodes, item.x, slot);
-            WideNode w;
-            bool is_inner[4];
-            wide_encode(nodes, slot, used, w, is_inner);
-            for (int c = 0; c < used; ++c) {
-                if (!is_inner[c]) continue;
-                const uint32_t wide_index = atomicAdd(&counters[0], 1u);
-                w.child[c] = wide_index << kPrimCountBits;
-                frontier_out[atomicAdd(&counters[2 + level], 1u)] = make_uint2(slot[c], wide_index);
-            }
-            const uint4* src = reinterpret_cast<const uint4*>(&w);
-            uint4* dst = reinterpret_cast<uint4*>(wide + item.y);
-            #pragma unroll
-            for (int k = 0; k < 4; ++k) dst[k] = src[k];
-        }
-        grid.sync();
-    }
-}
-
 int build_wide(DeviceBvh<float>& bvh, uint32_t levels, uint32_t* d_counters, uint2* d_frontier_a, uint2* d_frontier_b,
                cudaStream_t stream) {
     const uint32_t n = bvh.prim_count;
     if (!bvh.wide && device_alloc(reinterpret_cast<void**>(&bvh.wide), (size_t)(n ? n : 1) * sizeof(WideNode), stream)) return -1;
     wide_init_kernel<<<1, 64, 0, stream>>>(d_frontier_a, d_counters);
     if (levels > (uint32_t)kWideMaxLevels) levels = kWideMaxLevels;
-    int cooperative = 0, sm_count = 148, per_sm = 0;
-    cudaDeviceGetAttribute(&cooperative, cudaDevAttrCooperativeLaunch, bvh.device);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, bvh.device);
-    if (cooperative && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wide_collapse_all_kernel, kBlock, 0) == cudaSuccess && per_sm > 0) {
-        if (per_sm > 4) per_sm = 4;                                       // plenty for the widest frontier, cheaper barriers
-        const DevNode<float>* nodes = bvh.nodes; WideNode* wide = bvh.wide;
-        int max_levels = (int)levels;
-        void* args[] = { &nodes, &wide, &d_frontier_a, &d_frontier_b, &d_counters, &max_levels };
-        BVH_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(wide_collapse_all_kernel), dim3((unsigned)(sm_count * per_sm)), dim3(kBlock), args, 0, stream));
-        return 0;
-    }
-    cudaGetLastError();
+    // One launch per level.  (Measured and removed, round 2: all levels in one cooperative launch with a grid-wide
+    // barrier per level — 447 us per million triangles against 280 us for these ~25 small launches.)
     uint64_t bound = 1;
-    for (uint32_t level = 0; level < levels; ++level) {                   // no cooperative launch: one launch per level
+    for (uint32_t level = 0; level < levels; ++level) {
         const uint64_t items = bound < n ? bound : n;                     // frontier L has at most min(4^L, n) items
         const unsigned blocks = (unsigned)((items + kBlock - 1) / kBlock);
         wide_collapse_kernel<<<blocks, kBlock, 0, stream>>>(bvh.nodes, bvh.wide, (level & 1) ? d_frontier_b : d_frontier_a,
@@ -621,7 +577,7 @@ inline int build_wide(DeviceBvh<double>&, uint32_t, uint32_t*, uint2*, uint2*, c
 // The wide tree is derived lazily, the first time a trace asks for it (trace_rays), unless the
 // environment asks for it at build time (experiments: BVH_B200_USE_WIDE=1 makes it the default path).
 bool wide_enabled() {
-    return tunables().use_wide.load() != 0;                  // -1 (auto) and 1: derive the wide tree with the build
+    return tunables().use_wide.load() > 0;                   // 1: derive the wide tree with the build; otherwise on first use
 }
 
 struct Scratch {
@@ -731,7 +687,9 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     BVH_CUDA_TRY(cudaGetLastError());
 
     if (treelets) {
-        auto kernel = treelet_kernel<T>;
+        const int blocks_wanted = sizeof(T) == 4 ? tunables().treelet_blocks.load() : 1;
+        auto kernel = blocks_wanted >= 4 ? treelet_kernel<T, sizeof(T) == 4 ? 4 : 1>
+                    : blocks_wanted == 3 ? treelet_kernel<T, sizeof(T) == 4 ? 3 : 1> : treelet_kernel<T, sizeof(T) == 4 ? 2 : 1>;
         int per_sm = 1;
         BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTreeletWarps * 32, 0));
         if (per_sm < 1) per_sm = 1;
@@ -761,8 +719,8 @@ int build_with_key(DeviceBvh<T>& out, const T* d_verts, const T* d_bboxes, const
     compact_scatter_kernel<T><<<(pairs + kBlock) / kBlock, kBlock, 0, stream>>>(sparse, out.nodes, alive, rank, pairs);
     BVH_CUDA_TRY(cudaGetLastError());
 
-    // the compressed 4-wide companion tree of the default traversal path, derived in the same stream before the one
-    // host round trip of the build (float trees; the level limit replaces the depth, which is still on the device)
+    // use_wide 1: the compressed 4-wide companion tree is derived in the same stream before the one host round trip
+    // of the build (float trees; the level limit replaces the depth, which is still on the device)
     const bool with_wide = sizeof(T) == 4 && wide_enabled();
     uint32_t* wide_counters = nullptr;
     uint32_t host_wide[64] = {};

@@ -168,6 +168,7 @@ rs_scatter_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ va
 // three launches: 4 + 8 + 8 -> 8 + 8 bytes per key and pass.
 // Descriptor word: bits 31..30 = 0 not ready, 1 aggregate, 2 inclusive prefix; bits 29..0 = count.
 constexpr uint32_t kOsAggregate = 1u << 30, kOsInclusive = 2u << 30, kOsCountMask = (1u << 30) - 1u;
+constexpr int kOsWindow = 8;                    // descriptors fetched together by a looking-back thread
 constexpr uint32_t kOsMaxPolls = 1u << 24;      // look-back polls of one descriptor before a tile gives up (a hang becomes an error)
 
 __device__ __forceinline__ uint32_t os_load(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
@@ -252,13 +253,27 @@ rs_onesweep_kernel(const K* __restrict__ keys_in, const uint32_t* __restrict__ v
             os_store(mine, count | kOsInclusive);
         } else {
             os_store(mine, count | kOsAggregate);
-            for (uint32_t p = tile; p-- > 0;) {
-                const uint32_t* theirs = desc + (size_t)p * kRsBins + tid;
-                uint32_t v, polls = 0;
-                do { v = os_load(theirs); } while ((v >> 30) == 0u && ++polls < kOsMaxPolls);
-                if ((v >> 30) == 0u) { atomicExch(status, 1u); break; }      // a predecessor never published: give up (the caller reports it)
-                before += v & kOsCountMask;
-                if ((v >> 30) == 2u) break;
+            // Look back in windows of kOsWindow descriptors: the loads of a window are independent (all in flight at
+            // once), then the window is consumed nearest first.  With every tile of a pass resident at the same time
+            // most predecessors still show an AGGREGATE when a tile starts to look, so the walk is long; one load per
+            // step made a pass no faster than the three-kernel form (29 us per million keys, profiles/r02_*launches*).
+            bool done = false;
+            for (uint32_t hi = tile; hi > 0 && !done;) {                   // predecessors hi-1, hi-2, ...
+                const uint32_t span = hi < (uint32_t)kOsWindow ? hi : (uint32_t)kOsWindow;
+                uint32_t v[kOsWindow];
+                #pragma unroll
+                for (int k = 0; k < kOsWindow; ++k)
+                    v[k] = (uint32_t)k < span ? os_load(desc + (size_t)(hi - 1 - k) * kRsBins + tid) : kOsInclusive;
+                #pragma unroll
+                for (int k = 0; k < kOsWindow; ++k) {
+                    if (done || (uint32_t)k >= span) continue;
+                    uint32_t polls = 0;
+                    while ((v[k] >> 30) == 0u && ++polls < kOsMaxPolls) v[k] = os_load(desc + (size_t)(hi - 1 - k) * kRsBins + tid);
+                    if ((v[k] >> 30) == 0u) { atomicExch(status, 1u); done = true; continue; }   // a predecessor never published: give up (the caller reports it)
+                    before += v[k] & kOsCountMask;
+                    if ((v[k] >> 30) == 2u) done = true;
+                }
+                hi -= span;
             }
             os_store(mine, ((before + count) & kOsCountMask) | kOsInclusive);
         }

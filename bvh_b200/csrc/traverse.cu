@@ -122,7 +122,6 @@ template <typename T> struct TraceArgs {
     uint32_t inner_budget;            // persistent kernel: inner steps per lane per round (0xFFFFFFFF = unbounded)
     uint32_t full_mask;               // 0xFFFFFFFF passed at run time (see trace_pair_kernel)
     const uint32_t* order;            // ray reordering: the ray drawn at position p is rays[order[p]] (null: identity)
-    bool speculate;                   // wide kernel: put the first leaf of a round aside and keep descending
     bool stage_hits;                  // gather mode: warp-aggregated bulk stores (false: one store per record and rank)
     uint32_t* status;                 // device word set to 1 when a watchdog fired
     uint32_t watchdog;                // persistent kernels: trap after this many rounds of one warp (a hang becomes an error)
@@ -711,7 +710,6 @@ trace_wide_kernel(TraceArgs<float> a) {
     HitState<float> hit;
     float tmax_in = 0.f;
     uint32_t top = 0;
-    uint32_t postponed = 0;            // a leaf put aside by the inner phase (0: none; a leaf reference is never 0)
 
     uint32_t rounds = 0;
     for (;;) {
@@ -764,20 +762,12 @@ trace_wide_kernel(TraceArgs<float> a) {
         }
 
         // ---- inner phase ----------------------------------------------------------------------------
-        // With a.speculate a lane that reaches a leaf puts it aside once and keeps descending (Aila & Laine's
-        // speculative traversal): the lanes of a warp find their leaves at different steps, and a lane that stops at
-        // its first leaf idles until the round ends.  The leaf is tested in this round's leaf phase all the same, so
-        // the only cost is that the steps taken in between still see the old tmax.
+        // (Measured and removed, round 2: speculative descent — a lane that reaches a leaf puts it aside once and
+        // keeps descending — 2.69 instead of 2.77 Grays/s on soup-1M, 4.82 instead of 5.16 on grid-1M: the steps taken
+        // before tmax shrinks cost more than the idle lanes they fill.)
         if (has_ray) {
             uint32_t budget = inner_budget;
-            for (;;) {
-                if (index_count(top) != 0) {
-                    if (!a.speculate || postponed != 0u || budget == 0u || stack.empty()) break;
-                    postponed = top;
-                    top = stack.pop();
-                    continue;
-                }
-                if (budget == 0u) break;
+            while (index_count(top) == 0 && budget != 0) {
                 --budget;
                 uint32_t w[16];
                 {
@@ -788,29 +778,20 @@ trace_wide_kernel(TraceArgs<float> a) {
                     #pragma unroll
                     for (int k = 0; k < 8; ++k) { w[k] = w0[k]; w[8 + k] = w1[k]; }
                 }
-                if (!wide_step<kAny>(w, r, top, stack)) {           // nothing hit, nothing left on the stack
-                    if (postponed != 0u) { top = postponed; postponed = 0u; }     // ... but a leaf still waits
-                    else has_ray = false;
-                    break;
-                }
+                if (!wide_step<kAny>(w, r, top, stack)) { has_ray = false; break; }
             }
             if (!has_ray) retire(ray_index, hit, tmax_in);
         }
         __syncwarp();
 
-        // ---- leaf phase: the leaf put aside (if any), then the leaf in `top` (if it is one) -------------------
-        if (has_ray) {
-            #pragma unroll 1
-            for (int pass = 0; pass < 2 && has_ray; ++pass) {
-                uint32_t leaf;
-                if (pass == 0) { leaf = postponed; postponed = 0u; if (leaf == 0u) continue; }
-                else { leaf = top; if (index_count(leaf) == 0) break; }
-                leaf_step<float>(a.tris, a.prim_ids, true, leaf, r, hit, nullptr);
-                if (kAny && hit.slot != kInvalidId) { retire(ray_index, hit, tmax_in); has_ray = false; }
-                else if (pass == 1) {
-                    if (stack.empty()) { retire(ray_index, hit, tmax_in); has_ray = false; }
-                    else top = stack.pop();
-                }
+        // ---- leaf phase -----------------------------------------------------------------------------
+        if (has_ray && index_count(top) != 0) {
+            leaf_step<float>(a.tris, a.prim_ids, true, top, r, hit, nullptr);
+            if ((kAny && hit.slot != kInvalidId) || stack.empty()) {
+                retire(ray_index, hit, tmax_in);
+                has_ray = false;
+            } else {
+                top = stack.pop();
             }
         }
         __syncwarp();
@@ -987,14 +968,13 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     args.watchdog = tunables().watchdog.load();
     args.full_mask = 0xFFFFFFFFu;
     args.stage_hits = tunables().gather_staging.load() != 0;
-    args.speculate = tunables().speculate.load() != 0;
     args.variant = (flags & kTracePair) ? 2 : ((flags & (kTraceNoTma | kTraceTma)) ? 0 : tunables().variant.load());
     // the wide (compressed 4-wide) path: float, canonical tie-break, fast slab test, no statistics
     args.wide = nullptr; args.wide_entries = 0;
     if constexpr (sizeof(T) == 4) {
         const bool explicit_binary = (flags & (kTracePair | kTraceNoTma | kTraceTma | kTraceSimple)) != 0;
         const bool order_sensitive = (flags & (kTraceLastVisited | kTraceRobust)) != 0 || d_ray_stats != nullptr;
-        const bool want_wide = !order_sensitive && ((flags & kTraceWide) || (!explicit_binary && (tunables().use_wide.load() != 0)));
+        const bool want_wide = !order_sensitive && ((flags & kTraceWide) || (!explicit_binary && (tunables().use_wide.load() > 0)));
         if (want_wide && !bvh.wide && !bvh.wide_unavailable) {      // derived on first use
             if (rebuild_wide(const_cast<DeviceBvh<T>&>(bvh), stream, true)) return -1;
         }

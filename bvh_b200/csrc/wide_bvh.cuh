@@ -152,42 +152,17 @@ BVH_HD float wide_fmin(float a, float b) {
 #endif
 }
 
-// Byte c of a packed word as the float 32768 + byte: ONE byte permute drops the byte into mantissa bits 8..15 of
-// 2^15 (0x47000000), where a unit has weight 1 — no int-to-float conversion (I2F runs on the XU pipe at a quarter
-// of the FMA rate, and the 24 conversions per node were what bound the first version of this kernel, ncu round 1:
-// XU 80 % of peak).  The offset is taken out again by the per-node constant: t = fma(32768 + q, s, b - 32768 s).
-BVH_HD float wide_byte_plus_32768(uint32_t word, int c) {
-#if defined(__CUDA_ARCH__)
-    return __uint_as_float(__byte_perm(word, 0x47000000u, 0x7604u | ((uint32_t)c << 4)));
-#else
-    return Real<float>::from_bits(0x47000000u | (((word >> (8 * c)) & 0xFFu) << 8));
-#endif
-}
-// b - 32768 * s rounded DOWN (near planes) / UP (far planes): the one rounding this adds can only move a plane
-// outwards.  Host emulation: round-to-nearest fma corrected by comparing with the exact value in double
-// (a float product is exact in double; the sum is exact whenever the exponents are within 2^29 of each other,
-// and otherwise the correction is decided by the sign of the smaller operand).
-BVH_HD float wide_fma_down(float a, float b, float c) {
-#if defined(__CUDA_ARCH__)
-    return __fmaf_rd(a, b, c);
-#else
-    const float r = __builtin_fmaf(a, b, c);
-    const double exact = (double)a * (double)b + (double)c;
-    return ((double)r > exact && r == r) ? __builtin_nextafterf(r, -__builtin_inff()) : r;
-#endif
-}
-BVH_HD float wide_fma_up(float a, float b, float c) {
-#if defined(__CUDA_ARCH__)
-    return __fmaf_ru(a, b, c);
-#else
-    const float r = __builtin_fmaf(a, b, c);
-    const double exact = (double)a * (double)b + (double)c;
-    return ((double)r < exact && r == r) ? __builtin_nextafterf(r, __builtin_inff()) : r;
-#endif
-}
+// Byte c of a packed word as a float: a plain int-to-float conversion (I2F, on the XU pipe).  Measured alternatives:
+// round 1 — one PRMT dropping the byte into the mantissa of 2^23 plus an exact subtraction: XU 80 % -> 6 % of peak
+// but an extra issue slot per value, 2.68-2.72 instead of 3.00 Grays/s; round 2 — the same permute with the offset
+// folded into the per-node constant (t = fma(32768 + q, s, b - 32768 s), b rounded outwards), no extra instruction
+// per value: XU 6 %, but the permutes land on the ALU pipe, which also carries the kernel's min/max, compares and
+// selects (ALU 67 % of peak, issue 82 %, profiles/r02_wide_prmt_soup1M.txt): 2.67 Grays/s on the tree round 1 traced
+// at 3.0.  The conversions stay on the XU pipe, which nothing else in this kernel uses.
+BVH_HD float wide_byte_to_float(uint32_t word, int c) { return (float)((word >> (8 * c)) & 0xFFu); }
 
 // One inner step through the wide node whose 16 words are in w (layout of WideNode).  Dequantises the four
-// child boxes straight into ray-parameter space, t = (32768 + q) * (cell * inv_dir) + ((origin - org) * inv_dir - 32768 * cell * inv_dir),
+// child boxes straight into ray-parameter space, t = q * (cell * inv_dir) + (origin - org) * inv_dir,
 // visits the nearest hit child next and pushes the others far-to-near (any-hit: no ordering).  Returns
 // false when nothing was hit and the stack is empty.
 template <bool kAny, typename Stack>
@@ -197,8 +172,8 @@ BVH_HD bool wide_step(const uint32_t (&w)[16], const RayCtx<float>& r, uint32_t&
     for (int k = 0; k < 3; ++k) {
         const float cell = R::from_bits(((w[3] >> (8 * k)) & 0xFFu) << 23);
         const float d = R::sub(R::from_bits(w[k]), r.org[k]);
-        s[k] = R::mul(cell, r.inv_dir[k]);  b[k] = wide_fma_down(-32768.f, s[k], R::mul(d, r.inv_dir[k]));
-        sp[k] = R::mul(cell, r.aux[k]);     bp[k] = wide_fma_up(-32768.f, sp[k], R::mul(d, r.aux[k]));
+        s[k] = R::mul(cell, r.inv_dir[k]);  b[k] = R::mul(d, r.inv_dir[k]);
+        sp[k] = R::mul(cell, r.aux[k]);     bp[k] = R::mul(d, r.aux[k]);
     }
     uint32_t qn[3], qf[3];
     for (int k = 0; k < 3; ++k) {
@@ -207,15 +182,17 @@ BVH_HD bool wide_step(const uint32_t (&w)[16], const RayCtx<float>& r, uint32_t&
         qf[k] = neg ? w[4 + k] : w[7 + k];
     }
     const float inf = R::from_bits(0x7F800000u);
+    const uint32_t used = w[3] >> 24;                // child slots in use (unused ones carry an inverted box, but a ray whose
+                                                     // direction has a zero component turns slab values into NaNs that are ignored)
     float t0[4]; uint32_t ref[4];
     for (int c = 0; c < 4; ++c) {
         float tn = r.tmin, tf = r.tmax;
         for (int k = 0; k < 3; ++k) {
-            tn = wide_fmax(R::fma(wide_byte_plus_32768(qn[k], c), s[k], b[k]), tn);
-            tf = wide_fmin(R::fma(wide_byte_plus_32768(qf[k], c), sp[k], bp[k]), tf);
+            tn = wide_fmax(R::fma(wide_byte_to_float(qn[k], c), s[k], b[k]), tn);
+            tf = wide_fmin(R::fma(wide_byte_to_float(qf[k], c), sp[k], bp[k]), tf);
         }
         ref[c] = w[10 + c];
-        t0[c] = (tn <= tf) ? tn : inf;                                   // +inf marks a miss
+        t0[c] = ((uint32_t)c < used && tn <= tf) ? tn : inf;             // +inf marks a miss
     }
     if (!kAny) {
         // sort the four (t0, ref) pairs by t0, nearest first (5 compare-exchanges)

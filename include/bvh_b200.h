@@ -94,8 +94,8 @@ BVH_API void bvh_host_free(void* ptr);
 BVH_API int bvh_cuda_trim(int device);
 /* Process-wide switches for experiments, A/B measurements and tests (the defaults are the measured best):
  * "morton_bits" 0|30|63, "sah_treelets" -1|0|1, "hierarchy" 0|64|128|256, "e2e_chunks", "variant" 0|1,
- * "use_wide" -1|0|1, "inner_budget", "wide_budget", "watchdog", "gather_staging" 0|1,
- * "sort_onesweep" 0|1, "speculate" 0|1.  Initial values come from the BVH_B200_<NAME>
+ * "use_wide" 0|1, "inner_budget", "wide_budget", "watchdog", "gather_staging" 0|1,
+ * "sort_onesweep" 0|1, "treelet_blocks" 2|3|4.  Initial values come from the BVH_B200_<NAME>
  * environment variables, read once when the library is first used. */
 BVH_API int bvh_set_option(const char* name, long value);
 /* Subtree reinsertion (reference ReinsertionOptimizer::optimize, reinsertion_optimizer.h:27-30,218-267) on a

@@ -367,3 +367,30 @@ def test_sah_treelet_pass_survives_nan_and_inf_vertices(emul):
     assert np.array_equal(np.sort(tree["prim_ids"]), np.arange(tris.shape[0]))
     a, b = emul.trace(plain, rays, TIE_LOWEST_ID), emul.trace(tree, rays, TIE_LOWEST_ID)
     assert_hits_equal(b[:4], a[:4], "treelets with NaN / inf vertices")
+
+
+def test_wide_tree_with_degenerate_rays(emul):
+    """Zero direction components turn slab values of the wide step into NaNs that are ignored; an UNUSED child slot
+    (inverted box) must still never be entered (it was, before the slot count was checked: a wild leaf reference).
+    NaN intervals, empty and inverted intervals, infinite tmax: the wide path reports the binary path's hits."""
+    tris = scenes.soup(3000)
+    rays = scenes.make_primary("soup", 40, 40).copy()
+    nan, inf = np.float32(np.nan), np.float32(np.inf)
+    rays[0::10, 6] = nan
+    rays[1::10, 7] = nan
+    rays[2::10, 3:6] = 0
+    rays[3::10, 6], rays[3::10, 7] = 1.0, 0.5
+    rays[4::10, 7] = inf
+    rays[5::10, 6] = rays[5::10, 7] = 0.75
+    rays[6::10, 3] = 0
+    rays[7::10, 3:5] = 0
+    for quality in ("low", "high"):
+        tree = emul.build(tris=tris, quality=quality)
+        wide, _ = emul.wide_build(tree)
+        binary = emul.trace(tree, rays, 4)
+        got = emul.wide_trace(tree, wide, rays, 0)
+        assert (got[0] == binary[0]).all()
+        hit = binary[0] != INVALID
+        assert (got[1][hit].view(np.uint32) == binary[1][hit].view(np.uint32)).all()
+        any_got = emul.wide_trace(tree, wide, rays, 1)
+        assert ((any_got[0] != INVALID) == (emul.trace(tree, rays, 1 | 4)[0] != INVALID)).all()

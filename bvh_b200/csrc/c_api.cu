@@ -43,6 +43,7 @@ Tunables& tunables() {
         t.e2e_chunks = (int)env("BVH_B200_E2E_CHUNKS", 0);
         t.variant = (int)env("BVH_B200_VARIANT", 1);
         t.use_wide = (int)env("BVH_B200_USE_WIDE", 0);
+        t.duo = (int)env("BVH_B200_DUO", 0);
         const long budget = env("BVH_B200_INNER_BUDGET", 12);
         t.inner_budget = budget <= 0 ? 0xFFFFFFFFu : (uint32_t)budget;
         const long wbudget = env("BVH_B200_WIDE_BUDGET", 4);
@@ -672,6 +673,7 @@ BVH_EXPORT int bvh_set_option(const char* name, long value) {
     else if (n == "e2e_chunks") t.e2e_chunks = (int)value;
     else if (n == "variant") t.variant = (int)value;
     else if (n == "use_wide") t.use_wide = (int)value;
+    else if (n == "duo") t.duo = (int)value;
     else if (n == "inner_budget") t.inner_budget = value <= 0 ? 0xFFFFFFFFu : (uint32_t)value;
     else if (n == "wide_budget") t.wide_budget = value <= 0 ? 0xFFFFFFFFu : (uint32_t)value;
     else if (n == "watchdog") t.watchdog = (uint32_t)value;

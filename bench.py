@@ -65,7 +65,7 @@ def parse_args():
                     help="DefaultBuilder::Quality passed to the build (default: the library default, High)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "persistent", "duo", "wide", "simple"],
+    ap.add_argument("--kernel", default="auto", choices=["auto", "persistent", "wide", "simple"],
                     help="auto: the library's default choice for the flags of the config")
     ap.add_argument("--chunks", type=int, default=4, help="NCCL gather chunks per step when N > 1 and --gather nccl")
     ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "peer", "direct", "nccl"],
@@ -379,8 +379,7 @@ def main():
     total_rays = world * n_rays
     peak_gbs, peak_src = hbm_peak()
     base_flags = api.ANY_HIT if cfg["any_hit"] else 0
-    kflag = {"auto": 0, "persistent": api.KERNEL_TMA | api.KERNEL_SOLO, "duo": api.KERNEL_DUO, "wide": api.KERNEL_WIDE,
-             "simple": api.KERNEL_SIMPLE}[args.kernel]
+    kflag = {"auto": 0, "persistent": api.KERNEL_TMA, "wide": api.KERNEL_WIDE, "simple": api.KERNEL_SIMPLE}[args.kernel]
     if args.sort_rays:
         kflag |= api.SORT_RAYS
 

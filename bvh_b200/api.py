@@ -26,9 +26,7 @@ KERNEL_TMA = 1 << 10
 KERNEL_PAIR = 1 << 11
 KERNEL_WIDE = 1 << 12
 SORT_RAYS = 1 << 13
-KERNEL_DUO = 1 << 14
-KERNEL_SOLO = 1 << 15
-KERNELS = (KERNEL_PAIR, KERNEL_NO_TMA, KERNEL_TMA, KERNEL_SIMPLE, KERNEL_DUO, KERNEL_NO_TMA | KERNEL_DUO, KERNEL_SOLO)
+KERNELS = (KERNEL_PAIR, KERNEL_NO_TMA, KERNEL_TMA, KERNEL_SIMPLE)
 INVALID_ID = 0xFFFFFFFF
 
 QUALITY = {"low": 0, "medium": 1, "high": 2}
@@ -165,8 +163,7 @@ def trim(device: int = 0) -> None:
 PROPERTIES = {"depth": 0, "node_slots": 1, "morton_bits": 2, "quality": 3, "treelets": 4, "wide_nodes": 5,
               "last_kernel": 6, "stream": 7}
 KERNEL_NAMES = {0: None, 1: "trace_persistent_kernel<kTma=true>", 2: "trace_persistent_kernel<kTma=false>",
-                3: "trace_simple_kernel", 4: "trace_simple_kernel<kStats=true>", 5: "trace_pair_kernel", 6: "trace_wide_kernel",
-                7: "trace_persistent_kernel<kTma=true, kDuo=true>", 8: "trace_persistent_kernel<kTma=false, kDuo=true>"}
+                3: "trace_simple_kernel", 4: "trace_simple_kernel<kStats=true>", 5: "trace_pair_kernel", 6: "trace_wide_kernel"}
 
 
 def _sfx(dtype) -> str:

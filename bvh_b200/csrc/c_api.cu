@@ -43,8 +43,8 @@ Tunables& tunables() {
         t.e2e_chunks = (int)env("BVH_B200_E2E_CHUNKS", 0);
         t.variant = (int)env("BVH_B200_VARIANT", 1);
         t.use_wide = (int)env("BVH_B200_USE_WIDE", 0);
-        t.duo = (int)env("BVH_B200_DUO", 0);
-        const long budget = env("BVH_B200_INNER_BUDGET", 12);
+        { const long m = env("BVH_B200_REFILL_MIN", 10); t.refill_min = m < 1 ? 1u : m > 32 ? 32u : (uint32_t)m; }
+        const long budget = env("BVH_B200_INNER_BUDGET", 8);
         t.inner_budget = budget <= 0 ? 0xFFFFFFFFu : (uint32_t)budget;
         const long wbudget = env("BVH_B200_WIDE_BUDGET", 4);
         t.wide_budget = wbudget <= 0 ? 0xFFFFFFFFu : (uint32_t)wbudget;
@@ -673,7 +673,7 @@ BVH_EXPORT int bvh_set_option(const char* name, long value) {
     else if (n == "e2e_chunks") t.e2e_chunks = (int)value;
     else if (n == "variant") t.variant = (int)value;
     else if (n == "use_wide") t.use_wide = (int)value;
-    else if (n == "duo") t.duo = (int)value;
+    else if (n == "refill_min") t.refill_min = value < 1 ? 1u : value > 32 ? 32u : (uint32_t)value;
     else if (n == "inner_budget") t.inner_budget = value <= 0 ? 0xFFFFFFFFu : (uint32_t)value;
     else if (n == "wide_budget") t.wide_budget = value <= 0 ? 0xFFFFFFFFu : (uint32_t)value;
     else if (n == "watchdog") t.watchdog = (uint32_t)value;

@@ -43,9 +43,9 @@ struct Tunables {
     std::atomic<int> hierarchy { 128 };         // leaves per block of the hierarchy kernel (64 / 128 / 256), 0: global flags only
     std::atomic<int> e2e_chunks { 0 };          // chunks of the host-buffer pipeline, 0: auto
     std::atomic<int> variant { 1 };             // persistent kernel: 1 TMA-staged ray chunks, 0 streaming loads
-    std::atomic<int> duo { 0 };                 // persistent kernel: 1 neighbouring lanes share their node fetches where the flags allow
     std::atomic<int> use_wide { 0 };            // 1: derive the compressed wide tree with the build and trace with it where its semantics allow
-    std::atomic<uint32_t> inner_budget { 12 };  // inner steps per lane per round
+    std::atomic<uint32_t> inner_budget { 8 };   // inner steps per lane per round
+    std::atomic<uint32_t> refill_min { 10 };    // persistent kernels: idle lanes a warp waits for before it draws new rays (1: at once)
     std::atomic<uint32_t> wide_budget { 4 };    // same for the wide kernel
     std::atomic<uint32_t> watchdog { 1u << 26 };
     std::atomic<int> treelet_blocks { 3 };      // treelet kernel: resident blocks per SM its registers are limited for (2 / 3 / 4)
@@ -88,7 +88,7 @@ template <typename T> struct DeviceBvh {
     mutable int last_kernel = 0;        // TraceKernel of the most recent trace_rays call
 };
 
-enum TraceKernel : int { kKernelNone = 0, kKernelPersistentTma, kKernelPersistent, kKernelSimple, kKernelStats, kKernelPair, kKernelWide, kKernelDuoTma, kKernelDuo };
+enum TraceKernel : int { kKernelNone = 0, kKernelPersistentTma, kKernelPersistent, kKernelSimple, kKernelStats, kKernelPair, kKernelWide };
 
 // (Re)derives the wide tree from the binary one, e.g. after an upload from the host mirror.
 // force = false: only if the tree already has one (refresh) or the environment asks for it at build time;
@@ -132,8 +132,6 @@ enum TraceFlags : unsigned {
     kTracePair        = 1u << 11,  // persistent lane-pair kernel (two lanes per ray)
     kTraceWide        = 1u << 12,  // persistent kernel over the compressed 4-wide tree
     kTraceSortRays    = 1u << 13,  // traverse the batch in the Morton order of the ray origins (results stay in the caller's order)
-    kTraceDuo         = 1u << 14,  // persistent kernel, neighbouring lanes share their node fetches (float, fast slab test)
-    kTraceSolo        = 1u << 15,  // persistent kernel, every lane fetches its own sibling pair (overrides the duo default)
 };
 
 // Fused multi-GPU gather: besides (or instead of) the local hit array, every finished ray's record is

@@ -34,14 +34,41 @@ namespace {
 constexpr int kTraceBlock = 128;
 constexpr int kChunkRays = 128;          // rays claimed per global atomic by one warp
 
-// Shared-memory stack: entry k of thread t lives at base[k * stride + t] (bank = t mod 32).
+// Shared-memory stack: entry k of thread t lives at base[k * stride + t] (bank = t mod 32).  The stack pointer is kept
+// as ONE 32-bit shared-memory address (a push / pop is a store / load plus one add — indexing base[sp * stride] made the
+// compiler re-derive the thread's base address from S2R in every push and pop of the inner loop), and entry 0 holds a
+// sentinel no node index can equal (all ones: a leaf of 15 primitives at the last representable position), so that
+// try_pop() needs no comparison with the bottom address either.  Callers size the array as depth + 2 entries.
 template <typename U> struct SmemStack {
+    uint32_t top;                                            // shared-window address of the next free entry
+    uint32_t step;                                           // bytes between entries
     U* base;
-    uint32_t stride;
-    uint32_t sp;
-    __device__ __forceinline__ void push(U v) { base[sp * stride] = v; ++sp; }
-    __device__ __forceinline__ U pop() { --sp; return base[sp * stride]; }
-    __device__ __forceinline__ bool empty() const { return sp == 0; }
+    static constexpr U kSentinel = (U)~(U)0;
+    __device__ __forceinline__ SmemStack(U* base_, uint32_t stride, uint32_t) : step(stride * (uint32_t)sizeof(U)), base(base_) {
+        clear();
+        top -= step;
+        push(kSentinel);                                     // (through the same volatile asm as every other access)
+    }
+    __device__ __forceinline__ void clear() { top = (uint32_t)__cvta_generic_to_shared(base) + step; }
+    __device__ __forceinline__ void push(U v) {
+        // (volatile keeps the stack's own loads and stores in program order; no "memory" clobber: nothing else aliases the stack)
+        if constexpr (sizeof(U) == 4) asm volatile("st.shared.b32 [%0], %1;" :: "r"(top), "r"((uint32_t)v));
+        else asm volatile("st.shared.b64 [%0], %1;" :: "r"(top), "l"((unsigned long long)v));
+        top += step;
+    }
+    __device__ __forceinline__ U pop() {
+        top -= step;
+        if constexpr (sizeof(U) == 4) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(top)); return (U)v; }
+        else { unsigned long long v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(top)); return (U)v; }
+    }
+    // pops into `out`; false (and the stack stays empty) when there was nothing to pop
+    __device__ __forceinline__ bool try_pop(U& out) {
+        const U v = pop();
+        if (v == kSentinel) { top += step; return false; }
+        out = v;
+        return true;
+    }
+    __device__ __forceinline__ bool empty() const { return top == (uint32_t)__cvta_generic_to_shared(base) + step; }
 };
 
 __device__ __forceinline__ void load_ray(const DevRay<float>* __restrict__ rays, size_t i, RayCtx<float>& r) {
@@ -120,9 +147,9 @@ template <typename T> struct TraceArgs {
     int variant;                      // 0/1: one lane per ray (direct / TMA-staged rays), 2: lane-pair kernel
     bool use_tma;                     // persistent kernel: stage ray chunks with cp.async.bulk
     uint32_t inner_budget;            // persistent kernel: inner steps per lane per round (0xFFFFFFFF = unbounded)
+    uint32_t refill_min;              // persistent kernels: idle lanes a warp waits for before it draws new rays (1: refill at once)
     uint32_t full_mask;               // 0xFFFFFFFF passed at run time (see trace_pair_kernel)
     const uint32_t* order;            // ray reordering: the ray drawn at position p is rays[order[p]] (null: identity)
-    bool duo;                         // persistent kernel: neighbouring lanes share their node fetches (float, fast slab test)
     bool stage_hits;                  // gather mode: warp-aggregated bulk stores (false: one store per record and rank)
     uint32_t* status;                 // device word set to 1 when a watchdog fired
     uint32_t watchdog;                // persistent kernels: trap after this many rounds of one warp (a hang becomes an error)
@@ -349,7 +376,6 @@ __device__ __forceinline__ void read_ray_smem(const DevRay<double>* p, RayCtx<do
     r.dir[1] = c.x; r.dir[2] = c.y; r.tmin = d.x; r.tmax = d.y;
 }
 
-constexpr int kDuoBlocks = 6;            // resident CTAs per SM the duo variant's registers are limited for
 constexpr int kTmaChunkRays = 32;        // rays per bulk copy (1 KB of float rays), two buffers per warp
 
 template <typename T> __host__ __device__ constexpr size_t tma_smem_bytes() {
@@ -360,19 +386,9 @@ template <typename T> __host__ __device__ constexpr size_t tma_smem_bytes() {
 // asynchronous copy (cp.async.bulk, SASS UBLKCP) signalled through an mbarrier, double-buffered, so
 // that the ray fetch of the refill path never waits on DRAM; kTma = false reads rays with streaming
 // 128-bit loads.
-//
-// kDuo (float, fast slab test): NEIGHBOURING LANES SHARE THEIR NODE FETCHES.  The kernel is bound by the L1 data
-// pipe, which spends one wavefront per distinct 128-byte line per load instruction: with divergent rays a lane's
-// two 256-bit loads of its sibling pair (ONE 64-byte block) cost two wavefronts.  In duo mode lanes 2k and 2k+1
-// serve the pair's two rays A and B together: load 1 fetches A's sibling pair (even lane: left child, odd lane:
-// right child — the same line, one wavefront), load 2 fetches B's; each lane tests the child box it fetched
-// against a register copy of the ray it belongs to (both lanes hold the slab-test constants of both rays), and
-// the lanes swap (entry distance or NaN for a miss, child index) with two shuffles.  Each ray's decisions are
-// taken by its own lane from bit-identical values, so visit order and results are those of inner_step().
-template <typename T, bool kAny, bool kRobust, bool kTma, bool kGather, bool kDuo = false>
-__global__ void __launch_bounds__(kTraceBlock, sizeof(T) == 4 ? (kDuo ? kDuoBlocks : (kGather ? 7 : 8)) : 4)
+template <typename T, bool kAny, bool kRobust, bool kTma, bool kGather>
+__global__ void __launch_bounds__(kTraceBlock, sizeof(T) == 4 ? (kGather ? 7 : 8) : 4)
 trace_persistent_kernel(TraceArgs<T> a) {
-    static_assert(!kDuo || (sizeof(T) == 4 && !kRobust), "duo mode: float, fast slab test");
     using U = typename Real<T>::UInt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -439,18 +455,6 @@ trace_persistent_kernel(TraceArgs<T> a) {
     HitState<T> hit;
     T tmax_in = (T)0;
     U top = 0;
-    // duo mode: slab-test constants of the lane pair's two rays (index 0: the even lane's ray, 1: the odd lane's)
-    T duo_inv[2][3], duo_aux[2][3], duo_tmin[2], duo_tmax[2];
-    uint32_t duo_oct = 0;                                   // bits 0-2: ray 0, bits 3-5: ray 1
-    if (kDuo) {
-        #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-            duo_tmin[w] = (T)0; duo_tmax[w] = (T)0;
-            #pragma unroll
-            for (int k = 0; k < 3; ++k) { duo_inv[w][k] = (T)0; duo_aux[w][k] = (T)0; }
-        }
-    }
-    const bool odd = (lane & 1u) != 0u;
 
     uint32_t rounds = 0;
     for (;;) {
@@ -459,8 +463,13 @@ trace_persistent_kernel(TraceArgs<T> a) {
             return;
         }
         // ---- refill idle lanes from the private chunk (claiming a new chunk when it runs dry) ----
-        bool drew = false;                                  // duo mode: this lane drew a ray in this round
+        // A warp draws new rays only once refill_min of its lanes are idle.  The rays drawn together are neighbours
+        // (consecutive indices of one chunk) and start at the root in the same iteration, so they stay in step through
+        // the top of the tree and their node fetches — same address in the same instruction — cost one L1 wavefront
+        // instead of one per lane; the price is idle lanes, which this L1-bound kernel can afford (measured on the B200,
+        // profiles/r02_run5_*: soup-1M 2806 -> 3082 Mrays/s at 8, grid-1M 5959 -> 6530 at 20; 32 = no refill: 2270).
         unsigned idle = __ballot_sync(kFull, !has_ray);
+        if ((uint32_t)__popc(idle) < a.refill_min) idle = 0u;
         while (idle != 0u && !exhausted) {
             unsigned take, rank = __popc(idle & lt_mask);
             bool got = false;
@@ -518,9 +527,8 @@ trace_persistent_kernel(TraceArgs<T> a) {
                 } else {
                     ray_prologue<T, kRobust>(r);
                     top = root_index;
-                    stack.sp = 0;
+                    stack.clear();
                     has_ray = true;
-                    drew = true;
                 }
             }
             if (kGather) stager_account(stager, a.hits, lane);      // (a NaN ray may just have been retired)
@@ -533,107 +541,22 @@ trace_persistent_kernel(TraceArgs<T> a) {
 
         // ---- inner phase: descend until this lane holds a leaf, its ray is finished, or the step
         //      budget of this round is spent (bounding the wait of lanes that already hold a leaf) ----
-        if constexpr (kDuo) {
-            // the pair's lanes refresh their copies of each other's slab-test constants (new rays) and tmax (leaf phase)
-            if (__ballot_sync(kFull, drew) != 0u) {
-                #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const T mi = drew ? r.inv_dir[k] : (odd ? duo_inv[1][k] : duo_inv[0][k]);
-                    const T ma = drew ? r.aux[k] : (odd ? duo_aux[1][k] : duo_aux[0][k]);
-                    const T oi = __shfl_xor_sync(kFull, mi, 1), oa = __shfl_xor_sync(kFull, ma, 1);
-                    duo_inv[0][k] = odd ? oi : mi; duo_inv[1][k] = odd ? mi : oi;
-                    duo_aux[0][k] = odd ? oa : ma; duo_aux[1][k] = odd ? ma : oa;
-                }
-                const T mt = drew ? r.tmin : (odd ? duo_tmin[1] : duo_tmin[0]);
-                const T ot = __shfl_xor_sync(kFull, mt, 1);
-                duo_tmin[0] = odd ? ot : mt; duo_tmin[1] = odd ? mt : ot;
-                const uint32_t mo = drew ? r.oct : ((duo_oct >> (odd ? 3 : 0)) & 7u);
-                const uint32_t oo = __shfl_xor_sync(kFull, mo, 1);
-                duo_oct = odd ? (oo | (mo << 3)) : (mo | (oo << 3));
+        if (has_ray) {
+            uint32_t budget = inner_budget;
+            while (index_count(top) == 0 && budget != 0) {
+                --budget;
+                if (!inner_step<T, kAny, kRobust>(a.nodes, r, top, stack)) { has_ray = false; break; }
             }
-            {
-                const T px = __shfl_xor_sync(kFull, r.tmax, 1);
-                duo_tmax[0] = odd ? px : r.tmax; duo_tmax[1] = odd ? r.tmax : px;
-            }
-            bool finished = false;
-            // (a lane that wants a step takes one in every iteration until it holds a leaf or its ray ends, so a
-            // warp-uniform iteration count bounds each lane's steps exactly like the per-lane budget of the solo form)
-            for (uint32_t it = 0; it < inner_budget; ++it) {
-                const bool want = has_ray && index_count(top) == 0;
-                if (__ballot_sync(kFull, want) == 0u) break;
-                // device slot = reference index + 1; an idle lane offers slot 0, so that an idle ray's "sibling pair" is
-                // slots 0 (padding) and 1 (root): valid memory, one line, results unused
-                const U base = want ? (U)(index_first(top) + 1) : (U)0;
-                const U pbase = __shfl_xor_sync(kFull, base, 1);
-                const U slot0 = (odd ? pbase : base) + (odd ? 1u : 0u);      // the odd lane takes the right sibling
-                const U slot1 = (odd ? base : pbase) + (odd ? 1u : 0u);
-                uint32_t w0[8], w1[8];
-                ldg256(a.nodes + slot0, w0);
-                ldg256(a.nodes + slot1, w1);
-                T e0, e1;                                   // entry distance of the fetched child box for its ray, NaN: missed
-                {
-                    RayCtx<T> q;
-                    T b[6], t0, t1;
-                    #pragma unroll
-                    for (int k = 0; k < 3; ++k) { q.inv_dir[k] = duo_inv[0][k]; q.aux[k] = duo_aux[0][k]; }
-                    q.tmin = duo_tmin[0]; q.tmax = duo_tmax[0]; q.oct = duo_oct & 7u;
-                    #pragma unroll
-                    for (int k = 0; k < 6; ++k) b[k] = __uint_as_float(w0[k]);
-                    node_test<T, false>(b, q, t0, t1);
-                    e0 = t0 <= t1 ? t0 : __uint_as_float(0x7FC00000u);
-                    #pragma unroll
-                    for (int k = 0; k < 3; ++k) { q.inv_dir[k] = duo_inv[1][k]; q.aux[k] = duo_aux[1][k]; }
-                    q.tmin = duo_tmin[1]; q.tmax = duo_tmax[1]; q.oct = (duo_oct >> 3) & 7u;
-                    #pragma unroll
-                    for (int k = 0; k < 6; ++k) b[k] = __uint_as_float(w1[k]);
-                    node_test<T, false>(b, q, t0, t1);
-                    e1 = t0 <= t1 ? t0 : __uint_as_float(0x7FC00000u);
-                }
-                // even lane: holds left(ray 0) = its own left and left(ray 1) = the partner's; odd lane: right(ray 0), right(ray 1)
-                const T recv_t = __shfl_xor_sync(kFull, odd ? e0 : e1, 1);
-                const U recv_i = __shfl_xor_sync(kFull, odd ? (U)w0[6] : (U)w1[6], 1);
-                if (want) {
-                    const T lt = odd ? recv_t : e0, rt = odd ? e1 : recv_t;
-                    const U li = odd ? recv_i : (U)w0[6], ri = odd ? (U)w1[6] : recv_i;
-                    const bool hit_left = lt == lt, hit_right = rt == rt;
-                    if (hit_left) {                         // bvh.h:167-181, as inner_step()
-                        U near_index = li;
-                        if (hit_right) {
-                            U far_index = ri;
-                            if (!kAny && lt > rt) { U tmp = near_index; near_index = far_index; far_index = tmp; }
-                            stack.push(far_index);
-                        }
-                        top = near_index;
-                    } else if (hit_right) {
-                        top = ri;
-                    } else if (stack.empty()) {
-                        has_ray = false; finished = true;
-                    } else {
-                        top = stack.pop();
-                    }
-                }
-            }
-            if (finished) retire(ray_index, hit, tmax_in);
-        } else {
-            if (has_ray) {
-                uint32_t budget = inner_budget;
-                while (index_count(top) == 0 && budget != 0) {
-                    --budget;
-                    if (!inner_step<T, kAny, kRobust>(a.nodes, r, top, stack)) { has_ray = false; break; }
-                }
-                if (!has_ray) retire(ray_index, hit, tmax_in);
-            }
+            if (!has_ray) retire(ray_index, hit, tmax_in);
         }
         __syncwarp();
 
         // ---- leaf phase ---------------------------------------------------------------------------
         if (has_ray && index_count(top) != 0) {
             leaf_step<T>(a.tris, a.prim_ids, lowest_id, top, r, hit, nullptr);
-            if ((kAny && hit.slot != kInvalidId) || stack.empty()) {
+            if ((kAny && hit.slot != kInvalidId) || !stack.try_pop(top)) {
                 retire(ray_index, hit, tmax_in);
                 has_ray = false;
-            } else {
-                top = stack.pop();
             }
         }
         __syncwarp();
@@ -720,7 +643,7 @@ trace_pair_kernel(TraceArgs<T> a) {
                 } else {
                     ray_prologue<T, kRobust>(r);
                     top = root_index;
-                    stack.sp = 0;
+                    stack.clear();
                     has_ray = true;
                 }
             }
@@ -827,6 +750,7 @@ trace_wide_kernel(TraceArgs<float> a) {
             return;
         }
         unsigned idle = __ballot_sync(kFull, !has_ray);
+        if ((uint32_t)__popc(idle) < a.refill_min) idle = 0u;       // (see trace_persistent_kernel)
         while (idle != 0u && !exhausted) {
             if (chunk_pos == chunk_end) {
                 unsigned long long base = 0;
@@ -857,7 +781,7 @@ trace_wide_kernel(TraceArgs<float> a) {
                 } else {
                     wide_ray_setup(r);
                     top = 0;                                    // wide node 0, inner
-                    stack.sp = 0;
+                    stack.clear();
                     has_ray = true;
                 }
             }
@@ -896,11 +820,9 @@ trace_wide_kernel(TraceArgs<float> a) {
         // ---- leaf phase -----------------------------------------------------------------------------
         if (has_ray && index_count(top) != 0) {
             leaf_step<float>(a.tris, a.prim_ids, true, top, r, hit, nullptr);
-            if ((kAny && hit.slot != kInvalidId) || stack.empty()) {
+            if ((kAny && hit.slot != kInvalidId) || !stack.try_pop(top)) {
                 retire(ray_index, hit, tmax_in);
                 has_ray = false;
-            } else {
-                top = stack.pop();
             }
         }
         __syncwarp();
@@ -1035,17 +957,6 @@ int launch(const TraceArgs<T>& args, bool simple, bool stats, bool gather, int d
     } else {
         const size_t tma = args.use_tma ? tma_smem_bytes<T>() : 0, stage = gather ? stage_smem_bytes<T>() : 0;
         int rc;
-        if constexpr (sizeof(T) == 4 && !kRobust) {
-            if (args.duo) {
-                if (args.use_tma) rc = gather ? launch_persistent(trace_persistent_kernel<T, kAny, kRobust, true, true, true>, args, smem + tma + stage, 32, device, stream)
-                                              : launch_persistent(trace_persistent_kernel<T, kAny, kRobust, true, false, true>, args, smem + tma, 32, device, stream);
-                else              rc = gather ? launch_persistent(trace_persistent_kernel<T, kAny, kRobust, false, true, true>, args, smem + stage, 32, device, stream)
-                                              : launch_persistent(trace_persistent_kernel<T, kAny, kRobust, false, false, true>, args, smem, 32, device, stream);
-                if (rc) return -1;
-                BVH_CUDA_TRY(cudaGetLastError());
-                return 0;
-            }
-        }
         if (args.use_tma) rc = gather ? launch_persistent(trace_persistent_kernel<T, kAny, kRobust, true, true>, args, smem + tma + stage, 32, device, stream)
                                       : launch_persistent(trace_persistent_kernel<T, kAny, kRobust, true, false>, args, smem + tma, 32, device, stream);
         else              rc = gather ? launch_persistent(trace_persistent_kernel<T, kAny, kRobust, false, true>, args, smem + stage, 32, device, stream)
@@ -1079,12 +990,13 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     } else if (!d_hits) { set_error("trace: no hit array"); return -1; }
     args.ray_stats = d_ray_stats;
     args.lowest_id = (flags & kTraceLastVisited) ? 0 : 1;
-    uint32_t entries = bvh.depth + 1;
+    uint32_t entries = bvh.depth + 2;                           // depth + 1 pending far children at most, + the sentinel
     entries = (entries + 7u) & ~7u;
     if (entries < 16) entries = 16;
     args.stack_entries = entries;
     args.next_ray = nullptr;
     args.inner_budget = tunables().inner_budget.load();
+    args.refill_min = tunables().refill_min.load();
     args.watchdog = tunables().watchdog.load();
     args.full_mask = 0xFFFFFFFFu;
     args.stage_hits = tunables().gather_staging.load() != 0;
@@ -1100,13 +1012,11 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
         }
         if (bvh.wide && want_wide) {
             args.wide = bvh.wide;
-            uint32_t e = 3 * bvh.wide_depth + 2;
+            uint32_t e = 3 * bvh.wide_depth + 3;                // (+ the sentinel entry)
             args.wide_entries = (e + 7u) & ~7u;
             args.variant = 3;
         }
     }
-    args.duo = sizeof(T) == 4 && !(flags & kTraceRobust) && !(flags & kTracePair) && args.variant != 3
-               && ((flags & kTraceDuo) || (!(flags & kTraceSolo) && tunables().duo.load() > 0));
     args.use_tma = (flags & kTraceTma) ? true : ((flags & kTraceNoTma) ? false : tunables().variant.load() == 1);
     const bool simple = (flags & kTraceSimple) != 0, stats = d_ray_stats != nullptr;
     if (!bvh.scratch) {
@@ -1130,7 +1040,7 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     const bool staged = gather != nullptr;                  // gather mode: the kernels with warp-aggregated hit stores
     if (args.variant == 3) args.inner_budget = tunables().wide_budget.load();
     bvh.last_kernel = stats ? kKernelStats : simple ? kKernelSimple : args.variant == 3 ? kKernelWide : args.variant == 2 ? kKernelPair
-                    : args.duo ? (args.use_tma ? kKernelDuoTma : kKernelDuo) : args.use_tma ? kKernelPersistentTma : kKernelPersistent;
+                    : args.use_tma ? kKernelPersistentTma : kKernelPersistent;
     if (any) rc = robust ? launch<T, true, true>(args, simple, stats, staged, bvh.device, stream)
                          : launch<T, true, false>(args, simple, stats, staged, bvh.device, stream);
     else     rc = robust ? launch<T, false, true>(args, simple, stats, staged, bvh.device, stream)

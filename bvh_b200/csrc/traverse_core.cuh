@@ -71,17 +71,24 @@ __device__ __forceinline__ void load_node(const DevNode<double>* __restrict__ p,
     index = c[2];
 }
 __device__ __forceinline__ void load_tri(const DevTri<float>* __restrict__ p, DevTri<float>& o) {
-    const float4* q = reinterpret_cast<const float4*>(p);
-    const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-    o.p0[0] = a.x; o.p0[1] = a.y; o.p0[2] = a.z; o.e1[0] = a.w;
-    o.e1[1] = b.x; o.e1[2] = b.y; o.e2[0] = b.z; o.e2[1] = b.w;
-    o.e2[2] = c.x; o.n[0] = c.y; o.n[1] = c.z; o.n[2] = c.w;
+    uint32_t a[8], b[8];
+    ldg256(p, a);
+    ldg256(reinterpret_cast<const unsigned char*>(p) + 32, b);
+    o.p0[0] = __uint_as_float(a[0]); o.p0[1] = __uint_as_float(a[1]); o.p0[2] = __uint_as_float(a[2]);
+    o.e1[0] = __uint_as_float(a[3]); o.e1[1] = __uint_as_float(a[4]); o.e1[2] = __uint_as_float(a[5]);
+    o.e2[0] = __uint_as_float(a[6]); o.e2[1] = __uint_as_float(a[7]); o.e2[2] = __uint_as_float(b[0]);
+    o.n[0] = __uint_as_float(b[1]); o.n[1] = __uint_as_float(b[2]); o.n[2] = __uint_as_float(b[3]);
 }
 __device__ __forceinline__ void load_tri(const DevTri<double>* __restrict__ p, DevTri<double>& o) {
-    const double2* q = reinterpret_cast<const double2*>(p);
-    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4), f = __ldg(q + 5);
-    o.p0[0] = a.x; o.p0[1] = a.y; o.p0[2] = b.x; o.e1[0] = b.y; o.e1[1] = c.x; o.e1[2] = c.y;
-    o.e2[0] = d.x; o.e2[1] = d.y; o.e2[2] = e.x; o.n[0] = e.y; o.n[1] = f.x; o.n[2] = f.y;
+    unsigned long long a[4], b[4], c[4];
+    const unsigned char* q = reinterpret_cast<const unsigned char*>(p);
+    ldg256(q, a); ldg256(q + 32, b); ldg256(q + 64, c);
+    o.p0[0] = __longlong_as_double((long long)a[0]); o.p0[1] = __longlong_as_double((long long)a[1]);
+    o.p0[2] = __longlong_as_double((long long)a[2]); o.e1[0] = __longlong_as_double((long long)a[3]);
+    o.e1[1] = __longlong_as_double((long long)b[0]); o.e1[2] = __longlong_as_double((long long)b[1]);
+    o.e2[0] = __longlong_as_double((long long)b[2]); o.e2[1] = __longlong_as_double((long long)b[3]);
+    o.e2[2] = __longlong_as_double((long long)c[0]); o.n[0] = __longlong_as_double((long long)c[1]);
+    o.n[1] = __longlong_as_double((long long)c[2]); o.n[2] = __longlong_as_double((long long)c[3]);
 }
 #else
 template <typename T> inline void load_pair(const DevNode<T>* p, NodePair<T>& o) {
@@ -103,21 +110,15 @@ BVH_HD bool inner_step(const DevNode<T>* __restrict__ nodes, const RayCtx<T>& r,
     node_test<T, kRobust>(pair.lb, r, l0, l1);
     node_test<T, kRobust>(pair.rb, r, r0, r1);
     const bool hit_left = l0 <= l1, hit_right = r0 <= r1;
-    if (hit_left) {
-        U near_index = pair.li;
-        if (hit_right) {
-            U far_index = pair.ri;
-            if (!kAny && l0 > r0) { U tmp = near_index; near_index = far_index; far_index = tmp; }
-            stack.push(far_index);
-        }
-        top = near_index;
-    } else if (hit_right) {
-        top = pair.ri;
-    } else {
-        if (stack.empty()) return false;
-        top = stack.pop();
-    }
-    return true;
+    // Same decisions as the reference's nested branches (bvh.h:167-181), written as selects: on the device the lanes of a
+    // warp take all four outcomes at once, and one predicated path costs fewer issue slots than four divergent ones.
+    const bool both = hit_left && hit_right;
+    const bool right_first = !kAny && both && l0 > r0;            // ties go left first (`>` at bvh.h:180)
+    const U near_index = (hit_left && !right_first) ? pair.li : pair.ri;
+    const U far_index = right_first ? pair.li : pair.ri;
+    if (both) stack.push(far_index);
+    if (hit_left || hit_right) { top = near_index; return true; }
+    return stack.try_pop(top);
 }
 
 // Leaf processing (benchmark.cpp:281-292).  stats (nullable): [1] leaves, [2] triangle tests.
@@ -150,8 +151,7 @@ BVH_HD void traverse_ray(const DevNode<T>* __restrict__ nodes, const DevTri<T>* 
         if (!alive) break;
         leaf_step<T>(tris, prim_ids, lowest_id, top, r, hit, stats);
         if (kAny && hit.slot != kInvalidId) break;              // bvh.h:153-155
-        if (stack.empty()) break;
-        top = stack.pop();
+        if (!stack.try_pop(top)) break;
     }
 }
 

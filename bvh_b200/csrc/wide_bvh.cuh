@@ -201,8 +201,7 @@ BVH_HD bool wide_step(const uint32_t (&w)[16], const RayCtx<float>& r, uint32_t&
         BVH_CSWAP(0, 1) BVH_CSWAP(2, 3) BVH_CSWAP(0, 2) BVH_CSWAP(1, 3) BVH_CSWAP(1, 2)
 #undef BVH_CSWAP
         if (t0[0] == inf) {
-            if (stack.empty()) return false;
-            top = stack.pop();
+            if (!stack.try_pop(top)) return false;
         } else {
             if (t0[3] != inf) stack.push(ref[3]);
             if (t0[2] != inf) stack.push(ref[2]);
@@ -214,8 +213,7 @@ BVH_HD bool wide_step(const uint32_t (&w)[16], const RayCtx<float>& r, uint32_t&
         for (int c = 3; c >= 0; --c)
             if (t0[c] != inf) { if (next != 0xFFFFFFFFu) stack.push(next); next = ref[c]; }
         if (next == 0xFFFFFFFFu) {
-            if (stack.empty()) return false;
-            top = stack.pop();
+            if (!stack.try_pop(top)) return false;
         } else top = next;
     }
     return true;

@@ -58,11 +58,8 @@ enum bvh_intersect_flags {
     BVH_KERNEL_PAIR      = 1u << 11, /* persistent, two lanes per ray (one child box each) */
     BVH_KERNEL_WIDE      = 1u << 12, /* persistent, compressed 4-wide tree derived from the binary one (float; canonical
                                         tie-break and fast slab test only — otherwise the binary kernels are used) */
-    BVH_SORT_RAYS        = 1u << 13, /* incoherent batches: traverse the rays in the Morton order of their origins (device
+    BVH_SORT_RAYS        = 1u << 13  /* incoherent batches: traverse the rays in the Morton order of their origins (device
                                         radix sort of ray indices, ~1 ms per 10M rays); hits[i] still answers rays[i] */
-    BVH_KERNEL_DUO       = 1u << 14, /* persistent, one lane per ray, neighbouring lanes share the fetch of each other's
-                                        sibling pairs (float, fast slab test; same visit order and results) */
-    BVH_KERNEL_SOLO      = 1u << 15  /* persistent, every lane fetches its own sibling pair (overrides a duo default) */
 };
 
 /* What bvhNN_get_property reports about a handle. */

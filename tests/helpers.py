@@ -81,7 +81,7 @@ class HostEmul:
         words = 8  # a device node is 8 scalars wide (6 bounds + index + pad) for both float and double
         nodes = aligned_zeros((2 * n, words), dtype)
         ids = np.zeros(n, np.uint32)
-        dtris = aligned_zeros((n, 12), dtype) if tris is not None else None
+        dtris = aligned_zeros((n, 16), dtype) if tris is not None else None
         depth = C.c_uint32(0)
         getattr(self.lib, f"emul_build{s}")(_ptr(tris), _ptr(bboxes), _ptr(centers), n, min_leaf, max_leaf, morton_bits,
                                             _ptr(nodes), _ptr(ids), _ptr(dtris), C.byref(depth))
@@ -113,7 +113,7 @@ class HostEmul:
         getattr(self.lib, f"emul_from_reference{s}")(_ptr(np.ascontiguousarray(bounds)),
                                                     _ptr(np.ascontiguousarray(index_values, dtype=np.uint64)), n_nodes, _ptr(nodes))
         ids = np.ascontiguousarray(prim_ids, dtype=np.uint32)
-        dtris = aligned_zeros((ids.shape[0], 12), dtype)
+        dtris = aligned_zeros((ids.shape[0], 16), dtype)
         getattr(self.lib, f"emul_precompute{s}")(_ptr(np.ascontiguousarray(tris)), _ptr(ids), ids.shape[0], _ptr(dtris))
         return dict(nodes=nodes, prim_ids=ids, tris=dtris, depth=None, dtype=dtype, n=ids.shape[0], slots=n_nodes + 1)
 

@@ -27,6 +27,7 @@ template <typename U> struct HostStack {
     void push(U v) { data[sp++] = v; }
     U pop() { return data[--sp]; }
     bool empty() const { return sp == 0; }
+    bool try_pop(U& out) { if (sp == 0) return false; out = data[--sp]; return true; }
 };
 
 static int g_block_leaves = 0, g_block_order = 0, g_treelets = 0, g_last_treelets = 0;

@@ -482,12 +482,19 @@ def main():
             gather_desc = f"NCCL all_gather_into_tensor of hit records, {args.chunks} chunks overlapped with traversal"
     for _ in range(max(3, args.warmup)):
         tracer.step()
-    barrier()
+    # Everything that can take host time (NVML initialisation of the clock sampler, event creation, a garbage collection)
+    # happens BEFORE the barrier that opens the timed region: a rank that enters the region late makes every other rank
+    # wait at the first step's symmetric-memory barrier, and that wait is inside their timed window (one 87 ms step in
+    # a 20-step run halves the reported value: profiles/r02_n2_*).
     sampler = ClockSampler(local_rank)
-    sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    import gc
+    gc.collect()
+    gc.disable()
+    barrier()
     e0.record()
     for k in range(args.steps):
         starts[k].record()
@@ -495,6 +502,7 @@ def main():
         ends[k].record()
     e1.record()
     barrier()
+    gc.enable()
     if hasattr(tracer, "check"):
         tracer.check()                           # a fired kernel watchdog means stale records: fail, do not report
     clocks = sampler.summary()
@@ -559,7 +567,8 @@ def main():
                        "l2": f"inputs larger than L2: {n_rays * ray_bytes / 1e6:.0f} MB of rays + {n_rays * hit_bytes / 1e6:.0f} MB of hits streamed per step, no flush needed",
                        "hit_fraction": hit_frac, "inner_steps_per_ray": s_inner, "leaves_per_ray": s_leaves, "tri_tests_per_ray": s_tri,
                        "stats_rays": n_rays, "gather": gather_desc, "hits_checksum": checksum,
-                       "step_ms": {"median": kernel_ms, "max": float(np.max(step_ms)), "min": float(np.min(step_ms))}},
+                       "step_ms": {"median": kernel_ms, "max": float(np.max(step_ms)), "min": float(np.min(step_ms)),
+                                   "slow_steps": [[int(i), float(t)] for i, t in enumerate(step_ms) if t > 1.5 * kernel_ms]}},
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak_gbs,
                          "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": traffic_db.get(f"trace_{name}_{kind}"),

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbvh_c.so")
+LIB_PATH = os.environ.get("BVH_B200_LIB") or os.path.join(HERE, "libbvh_c.so")     # (the override: A/B builds of experiments)
 
 ANY_HIT = 1 << 0
 ROBUST = 1 << 1

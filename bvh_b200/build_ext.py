@@ -13,8 +13,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libbvh_c.so")
+# A/B builds (experiments): BVH_B200_BUILD_TAG=x BVH_B200_EXTRA_NVCC="-DFOO=1" -> bvh_b200/libbvh_c_x.so, selected at
+# run time with BVH_B200_LIB=<path> (bvh_b200/api.py)
+TAG = os.environ.get("BVH_B200_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libbvh_c" + ("_" + TAG if TAG else "") + ".so")
 
 SOURCES = ["lbvh_build.cu", "traverse.cu", "c_api.cu"]
 NVCC_FLAGS = [
@@ -41,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("BVH_B200_EXTRA_NVCC", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

@@ -107,8 +107,16 @@ static_assert(sizeof(DevNode<float>) == 32 && sizeof(DevNode<double>) == 64, "pa
 // PrecomputedTri (tri.h:30-37) padded to 16 scalars: a record is 64 / 128 bytes and never straddles a line, so a
 // triangle test costs two (float) / three (double) 256-bit loads instead of three / six 128-bit ones — the traversal is
 // bound by L1 wavefronts, one per load instruction and lane.
+#ifndef BVH_TRI_PAD
+#define BVH_TRI_PAD 1              // 0: the packed 48 / 96-byte record (A/B measurements only)
+#endif
+#if BVH_TRI_PAD
 template <typename T> struct alignas(16 * sizeof(T)) DevTri { T p0[3], e1[3], e2[3], n[3], pad[4]; };
 static_assert(sizeof(DevTri<float>) == 64 && sizeof(DevTri<double>) == 128, "padded triangle size");
+#else
+template <typename T> struct alignas(16) DevTri { T p0[3], e1[3], e2[3], n[3]; };
+static_assert(sizeof(DevTri<float>) == 48 && sizeof(DevTri<double>) == 96, "packed triangle size");
+#endif
 
 // bvh_ray3f / bvh_ray3d (reference c_api/bvh.h:70-73)
 template <typename T> struct alignas(16) DevRay { T org[3], dir[3], tmin, tmax; };
@@ -150,7 +158,9 @@ template <typename T> BVH_HD void cross3(const T a[3], const T b[3], T out[3]) {
 template <typename T> BVH_HD DevTri<T> precompute_tri(const T v[9]) {
     using R = Real<T>;
     DevTri<T> t;
+#if BVH_TRI_PAD
     for (int k = 0; k < 4; ++k) t.pad[k] = (T)0;
+#endif
     for (int k = 0; k < 3; ++k) {
         t.p0[k] = v[k];
         t.e1[k] = R::sub(v[k], v[3 + k]);

@@ -52,14 +52,24 @@ template <typename U> struct SmemStack {
     __device__ __forceinline__ void clear() { top = (uint32_t)__cvta_generic_to_shared(base) + step; }
     __device__ __forceinline__ void push(U v) {
         // (volatile keeps the stack's own loads and stores in program order; no "memory" clobber: nothing else aliases the stack)
+#ifdef BVH_STACK_CLOBBER             // A/B measurements only
+        if constexpr (sizeof(U) == 4) asm volatile("st.shared.b32 [%0], %1;" :: "r"(top), "r"((uint32_t)v) : "memory");
+        else asm volatile("st.shared.b64 [%0], %1;" :: "r"(top), "l"((unsigned long long)v) : "memory");
+#else
         if constexpr (sizeof(U) == 4) asm volatile("st.shared.b32 [%0], %1;" :: "r"(top), "r"((uint32_t)v));
         else asm volatile("st.shared.b64 [%0], %1;" :: "r"(top), "l"((unsigned long long)v));
+#endif
         top += step;
     }
     __device__ __forceinline__ U pop() {
         top -= step;
+#ifdef BVH_STACK_CLOBBER
+        if constexpr (sizeof(U) == 4) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(top) : "memory"); return (U)v; }
+        else { unsigned long long v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(top) : "memory"); return (U)v; }
+#else
         if constexpr (sizeof(U) == 4) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(top)); return (U)v; }
         else { unsigned long long v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(top)); return (U)v; }
+#endif
     }
     // pops into `out`; false (and the stack stays empty) when there was nothing to pop
     __device__ __forceinline__ bool try_pop(U& out) {
@@ -222,28 +232,45 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <typename T> __host__ __device__ constexpr size_t stage_smem_bytes() {
-    return (size_t)(kTraceBlock / 32) * kStageSlots * 32 * sizeof(DevHit<T>);
-}
-
-template <typename T> struct HitStager {
-    DevHit<T>* buf;                 // this warp's kStageSlots x 32 records in shared memory (null: staging off)
-    // warp-uniform
+// Warp-uniform bookkeeping of a warp's staging slots.  It lives in SHARED memory, not in registers: the traversal loop
+// only ever touches the two per-lane words of HitStager (as registers the nine words below cost the gather variants
+// eight registers, spills in the inner loop and one resident block per SM: 4.1 instead of 3.2 ms per 10M rays, r02 N=2 run).
+struct StagerWarp {
     uint32_t done[kStageSlots];     // bit i: record i of the slot's group is in the buffer
     uint32_t want[kStageSlots];     // the records the group has (all ones, or fewer for the batch's tail)
     uint32_t group[kStageSlots];    // ray index / 32 of the slot's group
     uint32_t used, draining;        // bit s: slot s holds an open group / is being read by a bulk copy
     uint32_t next;                  // slots are opened in cyclic order, so `next` is also the oldest one
     uint32_t cur;                   // slot of the group rays are currently drawn from, kStageSlots: none
+};
+
+template <typename T> __host__ __device__ constexpr size_t stage_smem_bytes() {
+    return (size_t)(kTraceBlock / 32) * (kStageSlots * 32 * sizeof(DevHit<T>) + sizeof(StagerWarp));
+}
+
+template <typename T> struct HitStager {
+    DevHit<T>* buf;                 // this warp's kStageSlots x 32 records in shared memory (null: staging off)
+    StagerWarp* w;                  // this warp's bookkeeping (shared memory)
     // per lane
     uint32_t tag;                   // slot << 5 | index in the group of the lane's ray, kNoTag: direct stores
     uint32_t pending;               // tag of the record written since the last account(), kNoTag: none
 
-    __device__ __forceinline__ void init(DevHit<T>* warp_buf) {
-        buf = warp_buf;
-        #pragma unroll
-        for (int s = 0; s < kStageSlots; ++s) { done[s] = 0; want[s] = 0; group[s] = 0; }
-        used = 0; draining = 0; next = 0; cur = kStageSlots; tag = kNoTag; pending = kNoTag;
+    // stage_base: the block's staging area; records of all warps first, then the StagerWarp structs
+    __device__ __forceinline__ void init(unsigned char* stage_base, unsigned warp, unsigned lane, bool on) {
+        buf = on ? reinterpret_cast<DevHit<T>*>(stage_base) + (size_t)warp * kStageSlots * 32 : nullptr;
+        w = reinterpret_cast<StagerWarp*>(stage_base + (size_t)(kTraceBlock / 32) * kStageSlots * 32 * sizeof(DevHit<T>)) + warp;
+        if (lane == 0) {
+            #pragma unroll
+            for (int s = 0; s < kStageSlots; ++s) { w->done[s] = 0; w->want[s] = 0; w->group[s] = 0; }
+            w->used = 0; w->draining = 0; w->next = 0; w->cur = kStageSlots;
+        }
+        __syncwarp();
+        tag = kNoTag; pending = kNoTag;
+    }
+    // tag of a ray drawn now from the current group (converged callers only)
+    __device__ __forceinline__ uint32_t tag_for(unsigned long long ray_index) const {
+        const uint32_t cur = w->cur;
+        return (buf && cur < (uint32_t)kStageSlots) ? (cur << 5) | (uint32_t)(ray_index & 31ull) : kNoTag;
     }
 };
 
@@ -265,62 +292,67 @@ __device__ __forceinline__ void store_record_direct(const HitSinks<T>& sinks, un
     }
 }
 
-// All lanes of the warp call these three together (converged code).
+// All lanes of the warp call the functions below together (converged code); every lane reads the same shared words,
+// lane 0 writes them back, a __syncwarp() separates the two.
+
+// Slot s is complete: one lane sends its 32 records to every rank with bulk copies.
 template <typename T>
 __device__ __forceinline__ void stager_flush_full(HitStager<T>& st, const HitSinks<T>& sinks, int s, unsigned lane) {
     __syncwarp();                                                   // the lanes' shared-memory records are visible to lane 0
     if (lane == 0) {
         fence_proxy_async_smem();                                   // ... and to the async proxy that reads them
-        const uint32_t count = 32u - (uint32_t)__clz(st.want[s]);  // want is a low mask
+        const uint32_t count = 32u - (uint32_t)__clz(st.w->want[s]);  // want is a low mask
         const uint32_t bytes = count * (uint32_t)sizeof(DevHit<T>);
         const uint32_t src = smem_u32(st.buf + s * 32);
-        const unsigned long long first = (unsigned long long)st.group[s] * 32ull;
+        const unsigned long long first = (unsigned long long)st.w->group[s] * 32ull;
         if (sinks.local) bulk_copy_s2g(sinks.local + first, src, bytes);
         for (int p = 0; p < sinks.peer_count; ++p) bulk_copy_s2g(sinks.peer[p] + first, src, bytes);
         bulk_commit();
+        st.w->used &= ~(1u << s);
+        st.w->draining |= 1u << s;
     }
-    st.used &= ~(1u << s);
-    st.draining |= 1u << s;
+    __syncwarp();
 }
 
+// Slot s is needed for a new group while stragglers hold it: finished records leave as plain stores, unfinished rays
+// switch to plain stores.
 template <typename T>
 __device__ __forceinline__ void stager_evict(HitStager<T>& st, const HitSinks<T>& sinks, int s, unsigned lane) {
     __syncwarp();
-    if ((st.done[s] >> lane) & 1u)
-        store_record_direct(sinks, (unsigned long long)st.group[s] * 32ull + lane, st.buf[s * 32 + lane]);
+    if ((st.w->done[s] >> lane) & 1u)
+        store_record_direct(sinks, (unsigned long long)st.w->group[s] * 32ull + lane, st.buf[s * 32 + lane]);
     if (st.tag != kNoTag && (int)(st.tag >> 5) == s) st.tag = kNoTag;       // the group's unfinished rays store directly
-    st.used &= ~(1u << s);
     __syncwarp();                                                   // the buffer is free for the next group
+    if (lane == 0) st.w->used &= ~(1u << s);
+    __syncwarp();
 }
 
 // A new group of `count` rays (ray index = 32 * group_id ...) starts being drawn: give it a slot.
 template <typename T>
 __device__ __forceinline__ void stager_open(HitStager<T>& st, const HitSinks<T>& sinks, unsigned long long group_id,
                                             uint32_t count, unsigned lane) {
-    st.cur = kStageSlots;
-    if (!st.buf || group_id > 0xFFFFFFFFull) return;
+    if (!st.buf) return;
+    if (group_id > 0xFFFFFFFFull) { if (lane == 0) st.w->cur = kStageSlots; __syncwarp(); return; }
     constexpr uint32_t kAll = (1u << kStageSlots) - 1u;
-    if (((st.used | st.draining) & kAll) == kAll && st.draining != 0u) {
-        if (lane == 0) bulk_wait_read_all();                        // the bulk copies have read their buffers
+    uint32_t used = st.w->used, draining = st.w->draining;
+    if (((used | draining) & kAll) == kAll && draining != 0u) {
+        if (lane == 0) { bulk_wait_read_all(); st.w->draining = 0; }           // the bulk copies have read their buffers
         __syncwarp();
-        st.draining = 0;
+        draining = 0;
     }
-    int s = (int)st.next;
-    if (((st.used | st.draining) >> s) & 1u) {                      // the next slot in cyclic order is not free
+    int s = (int)st.w->next;
+    if (((used | draining) >> s) & 1u) {                            // the next slot in cyclic order is not free
         #pragma unroll
-        for (int k = 0; k < kStageSlots; ++k) if ((((st.used | st.draining) >> k) & 1u) == 0u) s = k;
+        for (int k = 0; k < kStageSlots; ++k) if ((((used | draining) >> k) & 1u) == 0u) s = k;
     }
-    if ((st.used >> s) & 1u) {                                      // every slot is held by stragglers: evict the oldest
-        #pragma unroll
-        for (int k = 0; k < kStageSlots; ++k) if (k == s) stager_evict(st, sinks, k, lane);
+    if ((used >> s) & 1u) stager_evict(st, sinks, s, lane);        // every slot is held by stragglers: evict the oldest
+    if (lane == 0) {
+        st.w->done[s] = 0; st.w->want[s] = count >= 32u ? 0xFFFFFFFFu : ((1u << count) - 1u); st.w->group[s] = (uint32_t)group_id;
+        st.w->used |= 1u << s;
+        st.w->next = (uint32_t)(s + 1 == kStageSlots ? 0 : s + 1);
+        st.w->cur = (uint32_t)s;
     }
-    #pragma unroll
-    for (int k = 0; k < kStageSlots; ++k) if (k == s) {
-        st.done[k] = 0; st.want[k] = count >= 32u ? 0xFFFFFFFFu : ((1u << count) - 1u); st.group[k] = (uint32_t)group_id;
-    }
-    st.used |= 1u << s;
-    st.next = (uint32_t)(s + 1 == kStageSlots ? 0 : s + 1);
-    st.cur = (uint32_t)s;
+    __syncwarp();
 }
 
 // Books the records written since the last call; flushes groups that became complete.
@@ -333,8 +365,11 @@ __device__ __forceinline__ void stager_account(HitStager<T>& st, const HitSinks<
         const uint32_t mine = (st.pending != kNoTag && (int)(st.pending >> 5) == s) ? (1u << (st.pending & 31u)) : 0u;
         const uint32_t bits = __reduce_or_sync(0xFFFFFFFFu, mine);
         if (bits != 0u) {
-            st.done[s] |= bits;
-            if (st.done[s] == st.want[s]) stager_flush_full(st, sinks, s, lane);
+            const uint32_t done = st.w->done[s] | bits;
+            const bool full = done == st.w->want[s];
+            __syncwarp();
+            if (lane == 0) st.w->done[s] = done;
+            if (full) stager_flush_full(st, sinks, s, lane); else __syncwarp();
         }
     }
     st.pending = kNoTag;
@@ -387,7 +422,7 @@ template <typename T> __host__ __device__ constexpr size_t tma_smem_bytes() {
 // that the ray fetch of the refill path never waits on DRAM; kTma = false reads rays with streaming
 // 128-bit loads.
 template <typename T, bool kAny, bool kRobust, bool kTma, bool kGather>
-__global__ void __launch_bounds__(kTraceBlock, sizeof(T) == 4 ? (kGather ? 7 : 8) : 4)
+__global__ void __launch_bounds__(kTraceBlock, sizeof(T) == 4 ? 8 : 4)
 trace_persistent_kernel(TraceArgs<T> a) {
     using U = typename Real<T>::UInt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -428,7 +463,7 @@ trace_persistent_kernel(TraceArgs<T> a) {
     HitStager<T> stager;
     if (kGather) {
         unsigned char* stage_base = smem_raw + (size_t)a.stack_entries * kTraceBlock * sizeof(U) + (kTma ? tma_smem_bytes<T>() : 0);
-        stager.init((a.hits.multicast || !a.stage_hits) ? nullptr : reinterpret_cast<DevHit<T>*>(stage_base) + (size_t)warp * kStageSlots * 32);
+        stager.init(stage_base, warp, lane, !a.hits.multicast && a.stage_hits);
     }
     auto retire = [&] (unsigned long long index, const HitState<T>& h, T tmax) {
         if (kGather) stager_retire(stager, a.hits, index, make_record(h, tmax, a.prim_ids));
@@ -521,7 +556,7 @@ trace_persistent_kernel(TraceArgs<T> a) {
             if (got) {
                 tmax_in = r.tmax;
                 hit.slot = kInvalidId; hit.t = r.tmax; hit.u = (T)0; hit.v = (T)0;
-                if (kGather) stager.tag = stager.cur < (uint32_t)kStageSlots ? (stager.cur << 5) | (uint32_t)(ray_index & 31ull) : kNoTag;
+                if (kGather) stager.tag = stager.tag_for(ray_index);
                 if (ray_interval_is_nan(r)) {
                     retire(ray_index, hit, tmax_in);                             // can never hit: retire as a miss
                 } else {
@@ -716,7 +751,7 @@ trace_pair_kernel(TraceArgs<T> a) {
 // first and pushes the others far-to-near.  Leaves are the binary tree's leaves: same BVH-order triangle
 // array, same exact triangle test and canonical tie-break as every other kernel.
 template <bool kAny, bool kGather>
-__global__ void __launch_bounds__(kTraceBlock, kGather ? 7 : 8)
+__global__ void __launch_bounds__(kTraceBlock, 8)
 trace_wide_kernel(TraceArgs<float> a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -727,7 +762,7 @@ trace_wide_kernel(TraceArgs<float> a) {
     HitStager<float> stager;
     if (kGather) {
         unsigned char* stage_base = smem_raw + (size_t)a.wide_entries * kTraceBlock * sizeof(uint32_t);
-        stager.init((a.hits.multicast || !a.stage_hits) ? nullptr : reinterpret_cast<DevHit<float>*>(stage_base) + (size_t)(threadIdx.x >> 5) * kStageSlots * 32);
+        stager.init(stage_base, threadIdx.x >> 5, lane, !a.hits.multicast && a.stage_hits);
     }
     auto retire = [&] (unsigned long long index, const HitState<float>& h, float tmax) {
         if (kGather) stager_retire(stager, a.hits, index, make_record(h, tmax, a.prim_ids));
@@ -775,7 +810,7 @@ trace_wide_kernel(TraceArgs<float> a) {
                 load_ray(a.rays, ray_index, r);
                 tmax_in = r.tmax;
                 hit.slot = kInvalidId; hit.t = r.tmax; hit.u = 0.f; hit.v = 0.f;
-                if (kGather) stager.tag = stager.cur < (uint32_t)kStageSlots ? (stager.cur << 5) | (uint32_t)(ray_index & 31ull) : kNoTag;
+                if (kGather) stager.tag = stager.tag_for(ray_index);
                 if (ray_interval_is_nan(r)) {
                     retire(ray_index, hit, tmax_in);
                 } else {
@@ -991,7 +1026,7 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     args.ray_stats = d_ray_stats;
     args.lowest_id = (flags & kTraceLastVisited) ? 0 : 1;
     uint32_t entries = bvh.depth + 2;                           // depth + 1 pending far children at most, + the sentinel
-    entries = (entries + 7u) & ~7u;
+    entries = (entries + 1u) & ~1u;                             // (an entry is one 512-byte row of the block: any count keeps the alignment)
     if (entries < 16) entries = 16;
     args.stack_entries = entries;
     args.next_ray = nullptr;
@@ -1013,7 +1048,7 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
         if (bvh.wide && want_wide) {
             args.wide = bvh.wide;
             uint32_t e = 3 * bvh.wide_depth + 3;                // (+ the sentinel entry)
-            args.wide_entries = (e + 7u) & ~7u;
+            args.wide_entries = (e + 1u) & ~1u;
             args.variant = 3;
         }
     }
@@ -1037,7 +1072,10 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     }
     int rc;
     const bool any = (flags & kTraceAnyHit) != 0, robust = (flags & kTraceRobust) != 0;
-    const bool staged = gather != nullptr;                  // gather mode: the kernels with warp-aggregated hit stores
+    // gather mode: the kernel variants with warp-aggregated hit stores — only when staging is on and there is no multicast
+    // address; the plain variants deliver the records with store_hit() (one store per record and rank / one multimem store)
+    // and carry none of the staging state (72 registers with spills and 7 blocks per SM instead of 64 and 8)
+    const bool staged = gather != nullptr && args.stage_hits && !args.hits.multicast;
     if (args.variant == 3) args.inner_budget = tunables().wide_budget.load();
     bvh.last_kernel = stats ? kKernelStats : simple ? kKernelSimple : args.variant == 3 ? kKernelWide : args.variant == 2 ? kKernelPair
                     : args.use_tma ? kKernelPersistentTma : kKernelPersistent;

@@ -50,6 +50,7 @@ CONFIGS = {
     "c5": dict(tris=100_000, img=1000, dtype="f64", any_hit=False, scaling="weak",
                metric="primary closest-hit rays per second"),
 }
+AUTO_DIRECT_MAX_RANKS = 4         # --gather auto: per-record peer stores up to this many ranks, staged bulk copies beyond
 C4_CPU_ROW_STRIDE = 10           # the CPU arm of c4 traces every 10th image row (10M of the 100M rays)
 
 
@@ -441,8 +442,11 @@ def main():
             raise SystemExit(api.last_error())
 
     tracer, gather_desc = None, None
-    candidates = [] if world == 1 else (["peer", "direct"] if args.gather == "auto" else [] if args.gather == "nccl" else [args.gather])
-    for mode in candidates:                      # auto: staged bulk copies, then direct peer stores, then NCCL (below)
+    # auto: up to 4 ranks one peer store per record and rank (each costs ~1 % of the kernel: scripts/gather_probe.py), beyond
+    # that warp-staged bulk copies (a fixed ~6 %, independent of the number of ranks); NCCL (below) if neither works
+    auto = ["direct", "peer"] if world <= AUTO_DIRECT_MAX_RANKS else ["peer", "direct"]
+    candidates = [] if world == 1 else (auto if args.gather == "auto" else [] if args.gather == "nccl" else [args.gather])
+    for mode in candidates:
         try:
             from bvh_b200.multi_gpu import FusedGatherTracer
             api.set_option("gather_staging", 0 if mode == "direct" else 1)

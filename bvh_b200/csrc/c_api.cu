@@ -49,6 +49,8 @@ Tunables& tunables() {
         const long wbudget = env("BVH_B200_WIDE_BUDGET", 4);
         t.wide_budget = wbudget <= 0 ? 0xFFFFFFFFu : (uint32_t)wbudget;
         t.watchdog = (uint32_t)env("BVH_B200_WATCHDOG", 1l << 26);
+        t.stack_round = (int)env("BVH_B200_STACK_ROUND", 2);
+        t.smem_carveout = (int)env("BVH_B200_SMEM_CARVEOUT", -1);
         t.gather_staging = (int)env("BVH_B200_GATHER_STAGING", 1);
         t.sort_onesweep = (int)env("BVH_B200_SORT_ONESWEEP", 1);
         t.treelet_blocks = (int)env("BVH_B200_TREELET_BLOCKS", 3);
@@ -673,6 +675,8 @@ BVH_EXPORT int bvh_set_option(const char* name, long value) {
     else if (n == "e2e_chunks") t.e2e_chunks = (int)value;
     else if (n == "variant") t.variant = (int)value;
     else if (n == "use_wide") t.use_wide = (int)value;
+    else if (n == "stack_round") t.stack_round = value < 1 ? 1 : (int)value;
+    else if (n == "smem_carveout") t.smem_carveout = (int)value;
     else if (n == "refill_min") t.refill_min = value < 1 ? 1u : value > 32 ? 32u : (uint32_t)value;
     else if (n == "inner_budget") t.inner_budget = value <= 0 ? 0xFFFFFFFFu : (uint32_t)value;
     else if (n == "wide_budget") t.wide_budget = value <= 0 ? 0xFFFFFFFFu : (uint32_t)value;

@@ -48,6 +48,8 @@ struct Tunables {
     std::atomic<uint32_t> refill_min { 10 };    // persistent kernels: idle lanes a warp waits for before it draws new rays (1: at once)
     std::atomic<uint32_t> wide_budget { 4 };    // same for the wide kernel
     std::atomic<uint32_t> watchdog { 1u << 26 };
+    std::atomic<int> stack_round { 2 };         // traversal stack entries are rounded up to a multiple of this (A/B: 8)
+    std::atomic<int> smem_carveout { -1 };      // persistent kernels: preferred shared-memory carve-out in percent, -1: the driver's choice
     std::atomic<int> treelet_blocks { 3 };      // treelet kernel: resident blocks per SM its registers are limited for (2 / 3 / 4)
     std::atomic<int> sort_onesweep { 1 };       // build: 1 one-sweep radix sort (one kernel per pass), 0 histogram / scan / scatter per pass
     std::atomic<int> gather_staging { 1 };      // fused gather: 1 warp-aggregated bulk stores, 0 one store per record and rank

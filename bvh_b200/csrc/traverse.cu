@@ -946,6 +946,8 @@ template <typename KernelT, typename T>
 int launch_persistent(KernelT kernel, const TraceArgs<T>& args, size_t smem, unsigned rays_per_warp, int device, cudaStream_t stream) {
     if (smem > 200 * 1024) { set_error("trace: tree too deep for the shared-memory stack"); return -1; }
     if (configure_smem(kernel, smem)) return -1;
+    if (const int carve = tunables().smem_carveout.load(); carve >= 0)
+        BVH_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     int sm_count = 148, per_sm = 1;
     BVH_CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     BVH_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceBlock, smem));
@@ -1026,7 +1028,10 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     args.ray_stats = d_ray_stats;
     args.lowest_id = (flags & kTraceLastVisited) ? 0 : 1;
     uint32_t entries = bvh.depth + 2;                           // depth + 1 pending far children at most, + the sentinel
-    entries = (entries + 1u) & ~1u;                             // (an entry is one 512-byte row of the block: any count keeps the alignment)
+    {                                                           // (an entry is one 512-byte row of the block: any count keeps the alignment)
+        const uint32_t r = (uint32_t)tunables().stack_round.load();
+        entries = (entries + r - 1u) / r * r;
+    }
     if (entries < 16) entries = 16;
     args.stack_entries = entries;
     args.next_ray = nullptr;

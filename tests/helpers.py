@@ -81,7 +81,7 @@ class HostEmul:
         words = 8  # a device node is 8 scalars wide (6 bounds + index + pad) for both float and double
         nodes = aligned_zeros((2 * n, words), dtype)
         ids = np.zeros(n, np.uint32)
-        dtris = aligned_zeros((n, 16), dtype) if tris is not None else None
+        dtris = aligned_zeros((n, 16), dtype) if tris is not None else None   # room for the padded record form (BVH_TRI_PAD)
         depth = C.c_uint32(0)
         getattr(self.lib, f"emul_build{s}")(_ptr(tris), _ptr(bboxes), _ptr(centers), n, min_leaf, max_leaf, morton_bits,
                                             _ptr(nodes), _ptr(ids), _ptr(dtris), C.byref(depth))

@@ -41,15 +41,16 @@ Tunables& tunables() {
             t.hierarchy = v == "global" ? 0 : v == "thread64" ? 64 : v == "thread256" ? 256 : 128;
         }
         t.e2e_chunks = (int)env("BVH_B200_E2E_CHUNKS", 0);
-        t.variant = (int)env("BVH_B200_VARIANT", 1);
+        t.variant = (int)env("BVH_B200_VARIANT", 0);
         t.use_wide = (int)env("BVH_B200_USE_WIDE", 0);
-        { const long m = env("BVH_B200_REFILL_MIN", 10); t.refill_min = m < 1 ? 1u : m > 32 ? 32u : (uint32_t)m; }
+        { const long m = env("BVH_B200_REFILL_MIN", 8); t.refill_min = m < 1 ? 1u : m > 32 ? 32u : (uint32_t)m; }
         const long budget = env("BVH_B200_INNER_BUDGET", 8);
         t.inner_budget = budget <= 0 ? 0xFFFFFFFFu : (uint32_t)budget;
         const long wbudget = env("BVH_B200_WIDE_BUDGET", 4);
         t.wide_budget = wbudget <= 0 ? 0xFFFFFFFFu : (uint32_t)wbudget;
         t.watchdog = (uint32_t)env("BVH_B200_WATCHDOG", 1l << 26);
         t.stack_round = (int)env("BVH_B200_STACK_ROUND", 2);
+        t.chunk_rays = (uint32_t)env("BVH_B200_CHUNK_RAYS", 64);
         t.smem_carveout = (int)env("BVH_B200_SMEM_CARVEOUT", -1);
         t.gather_staging = (int)env("BVH_B200_GATHER_STAGING", 1);
         t.sort_onesweep = (int)env("BVH_B200_SORT_ONESWEEP", 1);
@@ -675,6 +676,7 @@ BVH_EXPORT int bvh_set_option(const char* name, long value) {
     else if (n == "e2e_chunks") t.e2e_chunks = (int)value;
     else if (n == "variant") t.variant = (int)value;
     else if (n == "use_wide") t.use_wide = (int)value;
+    else if (n == "chunk_rays") t.chunk_rays = value < 32 ? 32u : (uint32_t)value;
     else if (n == "stack_round") t.stack_round = value < 1 ? 1 : (int)value;
     else if (n == "smem_carveout") t.smem_carveout = (int)value;
     else if (n == "refill_min") t.refill_min = value < 1 ? 1u : value > 32 ? 32u : (uint32_t)value;

@@ -42,12 +42,13 @@ struct Tunables {
     std::atomic<int> sah_treelets { -1 };       // -1: by quality (Medium / High), 0 / 1: forced off / on
     std::atomic<int> hierarchy { 128 };         // leaves per block of the hierarchy kernel (64 / 128 / 256), 0: global flags only
     std::atomic<int> e2e_chunks { 0 };          // chunks of the host-buffer pipeline, 0: auto
-    std::atomic<int> variant { 1 };             // persistent kernel: 1 TMA-staged ray chunks, 0 streaming loads
+    std::atomic<int> variant { 0 };             // persistent kernel: 0 streaming ray loads, 1 ray chunks staged by bulk async copies (TMA)
     std::atomic<int> use_wide { 0 };            // 1: derive the compressed wide tree with the build and trace with it where its semantics allow
     std::atomic<uint32_t> inner_budget { 8 };   // inner steps per lane per round
-    std::atomic<uint32_t> refill_min { 10 };    // persistent kernels: idle lanes a warp waits for before it draws new rays (1: at once)
+    std::atomic<uint32_t> refill_min { 8 };     // persistent kernels: idle lanes a warp waits for before it draws new rays (1: at once)
     std::atomic<uint32_t> wide_budget { 4 };    // same for the wide kernel
     std::atomic<uint32_t> watchdog { 1u << 26 };
+    std::atomic<uint32_t> chunk_rays { 64 };    // persistent kernels: consecutive rays a warp claims at a time (its cohorts are drawn from them)
     std::atomic<int> stack_round { 2 };         // traversal stack entries are rounded up to a multiple of this (A/B: 8)
     std::atomic<int> smem_carveout { -1 };      // persistent kernels: preferred shared-memory carve-out in percent, -1: the driver's choice
     std::atomic<int> treelet_blocks { 3 };      // treelet kernel: resident blocks per SM its registers are limited for (2 / 3 / 4)

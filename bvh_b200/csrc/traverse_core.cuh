@@ -26,8 +26,45 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t (&w)[8]) {
     asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
 }
+// Node loads do NOT allocate their line in L1 (ld.global.nc.L1::no_allocate).  Measured on the B200 (profiles/
+// r02_run10to11_*): soup-1M +6.4 %, incoherent c3 +8 %, grid-1M -0.5 %.  Deep nodes are used once per ray, and a pending miss
+// that must allocate a line is limited by the L1's capacity: with 28 KB of L1 (the 228 KB shared-memory carve-out) the
+// incoherent batch ran at 1.0 instead of 1.7 Grays/s — the lines in flight, not the hits, were what the larger L1 bought.
+#ifndef BVH_NODE_NA
+#define BVH_NODE_NA 1
+#endif
+#ifndef BVH_TRI_NA
+#define BVH_TRI_NA 0
+#endif
+__device__ __forceinline__ void ldg256_na(const void* p, uint32_t (&w)[8]) {
+    asm("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+}
+__device__ __forceinline__ void ldg256_node(const void* p, uint32_t (&w)[8]) {
+#if BVH_NODE_NA
+    ldg256_na(p, w);
+#else
+    ldg256(p, w);
+#endif
+}
+__device__ __forceinline__ float4 ldg128_tri(const float4* p) {
+#if BVH_TRI_NA
+    float4 v;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
 __device__ __forceinline__ void ldg256(const void* p, unsigned long long (&w)[4]) {
     asm("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(p));
+}
+__device__ __forceinline__ void ldg256_node(const void* p, unsigned long long (&w)[4]) {
+#if BVH_NODE_NA
+    asm("ld.global.nc.L1::no_allocate.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(p));
+#else
+    ldg256(p, w);
+#endif
 }
 #endif
 
@@ -38,8 +75,8 @@ __device__ __forceinline__ void ldg256(const void* p, unsigned long long (&w)[4]
 // distinct line touched by the warp (profiles/: the traversal is L1-tag bound, not DRAM bound).
 __device__ __forceinline__ void load_pair(const DevNode<float>* __restrict__ p, NodePair<float>& o) {
     uint32_t a[8], b[8];
-    ldg256(p, a);
-    ldg256(p + 1, b);
+    ldg256_node(p, a);
+    ldg256_node(p + 1, b);
     #pragma unroll
     for (int k = 0; k < 6; ++k) { o.lb[k] = __uint_as_float(a[k]); o.rb[k] = __uint_as_float(b[k]); }
     o.li = a[6]; o.ri = b[6];
@@ -47,7 +84,7 @@ __device__ __forceinline__ void load_pair(const DevNode<float>* __restrict__ p, 
 __device__ __forceinline__ void load_pair(const DevNode<double>* __restrict__ p, NodePair<double>& o) {
     unsigned long long a[4], b[4], c[4], d[4];
     const unsigned char* q = reinterpret_cast<const unsigned char*>(p);
-    ldg256(q, a); ldg256(q + 32, b); ldg256(q + 64, c); ldg256(q + 96, d);
+    ldg256_node(q, a); ldg256_node(q + 32, b); ldg256_node(q + 64, c); ldg256_node(q + 96, d);
     #pragma unroll
     for (int k = 0; k < 4; ++k) { o.lb[k] = __longlong_as_double((long long)a[k]); o.rb[k] = __longlong_as_double((long long)c[k]); }
     o.lb[4] = __longlong_as_double((long long)b[0]); o.lb[5] = __longlong_as_double((long long)b[1]); o.li = b[2];
@@ -94,7 +131,7 @@ __device__ __forceinline__ void load_tri(const DevTri<double>* __restrict__ p, D
 #else
 __device__ __forceinline__ void load_tri(const DevTri<float>* __restrict__ p, DevTri<float>& o) {
     const float4* q = reinterpret_cast<const float4*>(p);
-    const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    const float4 a = ldg128_tri(q), b = ldg128_tri(q + 1), c = ldg128_tri(q + 2);
     o.p0[0] = a.x; o.p0[1] = a.y; o.p0[2] = a.z; o.e1[0] = a.w;
     o.e1[1] = b.x; o.e1[2] = b.y; o.e2[0] = b.z; o.e2[1] = b.w;
     o.e2[2] = c.x; o.n[0] = c.y; o.n[1] = c.z; o.n[2] = c.w;

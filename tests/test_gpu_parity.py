@@ -334,7 +334,7 @@ def test_full_size_properties(gpu_lib, oracle, kind):
     rays = scenes.make_primary(kind, 3163, 3163)
     m = rays.shape[0]
     hits = bvh.intersect_rays(rays)                                 # the library's default path: the exact binary traversal
-    assert bvh.properties()["last_kernel"] == "trace_persistent_kernel<kTma=true>"
+    assert bvh.properties()["last_kernel"].startswith("trace_persistent_kernel<kTma=")    # exact binary traversal (either ray staging)
     ids = hits["prim_id"]
     hit = ids != INVALID
     assert 0.3 < hit.mean() <= 1.0

@@ -66,7 +66,7 @@ def parse_args():
                     help="DefaultBuilder::Quality passed to the build (default: the library default, High)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "persistent", "wide", "simple"],
+    ap.add_argument("--kernel", default="auto", choices=["auto", "persistent", "tma", "wide", "simple"],
                     help="auto: the library's default choice for the flags of the config")
     ap.add_argument("--chunks", type=int, default=4, help="NCCL gather chunks per step when N > 1 and --gather nccl")
     ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "peer", "direct", "nccl"],
@@ -380,7 +380,8 @@ def main():
     total_rays = world * n_rays
     peak_gbs, peak_src = hbm_peak()
     base_flags = api.ANY_HIT if cfg["any_hit"] else 0
-    kflag = {"auto": 0, "persistent": api.KERNEL_TMA, "wide": api.KERNEL_WIDE, "simple": api.KERNEL_SIMPLE}[args.kernel]
+    kflag = {"auto": 0, "persistent": api.KERNEL_NO_TMA, "tma": api.KERNEL_TMA, "wide": api.KERNEL_WIDE,
+             "simple": api.KERNEL_SIMPLE}[args.kernel]
     if args.sort_rays:
         kflag |= api.SORT_RAYS
 
@@ -442,9 +443,10 @@ def main():
             raise SystemExit(api.last_error())
 
     tracer, gather_desc = None, None
-    # auto: up to 4 ranks one peer store per record and rank (each costs ~1 % of the kernel: scripts/gather_probe.py), beyond
-    # that warp-staged bulk copies (a fixed ~6 %, independent of the number of ranks); NCCL (below) if neither works
-    auto = ["direct", "peer"] if world <= AUTO_DIRECT_MAX_RANKS else ["peer", "direct"]
+    # auto: two ranks one multimem store per record (2-GPU run: 0.995 of perfect scaling, per-record peer stores 0.954, staged
+    # 0.90); up to 4 ranks one peer store per record and rank (each costs ~1-2 % of the kernel: scripts/gather_probe.py); beyond
+    # that warp-staged bulk copies (a fixed ~6 %, independent of the number of ranks); NCCL (below) if none works
+    auto = ["multicast", "direct", "peer"] if world == 2 else ["direct", "peer"] if world <= AUTO_DIRECT_MAX_RANKS else ["peer", "direct"]
     candidates = [] if world == 1 else (auto if args.gather == "auto" else [] if args.gather == "nccl" else [args.gather])
     for mode in candidates:
         try:

@@ -69,7 +69,7 @@ def parse_args():
     ap.add_argument("--kernel", default="auto", choices=["auto", "persistent", "tma", "wide", "simple"],
                     help="auto: the library's default choice for the flags of the config")
     ap.add_argument("--chunks", type=int, default=4, help="NCCL gather chunks per step when N > 1 and --gather nccl")
-    ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "peer", "direct", "nccl"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "multicast", "multicast_staged", "peer", "direct", "nccl"],
                     help="N > 1: fused gather inside the traversal kernel — peer (= auto): a warp stages 32 records in shared memory and "
                          "bulk-copies them to every rank; direct: one 16-byte store per record and rank; multicast: one multimem.st per "
                          "record — or NCCL all-gather")
@@ -445,16 +445,20 @@ def main():
     tracer, gather_desc = None, None
     # auto: two ranks one multimem store per record (2-GPU run: 0.995 of perfect scaling, per-record peer stores 0.954, staged
     # 0.90); up to 4 ranks one peer store per record and rank (each costs ~1-2 % of the kernel: scripts/gather_probe.py); beyond
-    # that warp-staged bulk copies (a fixed ~6 %, independent of the number of ranks); NCCL (below) if none works
-    auto = ["multicast", "direct", "peer"] if world == 2 else ["direct", "peer"] if world <= AUTO_DIRECT_MAX_RANKS else ["peer", "direct"]
+    # that warp-staged bulk copies (a fixed ~6 %, independent of the number of ranks) — ONE copy per 32 records to the multicast
+    # address when the fabric has one (8 ranks: 0.881), else one copy per rank (0.836); NCCL (below) if none works
+    auto = (["multicast", "direct", "peer"] if world == 2 else ["direct", "peer"] if world <= AUTO_DIRECT_MAX_RANKS
+            else ["multicast_staged", "peer", "direct"])
     candidates = [] if world == 1 else (auto if args.gather == "auto" else [] if args.gather == "nccl" else [args.gather])
     for mode in candidates:
         try:
             from bvh_b200.multi_gpu import FusedGatherTracer
-            api.set_option("gather_staging", 0 if mode == "direct" else 1)
+            api.set_option("gather_staging", 0 if mode in ("direct", "multicast") else 1)
             cand = FusedGatherTracer(bvh, rays, hit_words, flags=api.DEVICE_POINTERS | base_flags | kflag,
-                                     mode="multicast" if mode == "multicast" else "peer")
+                                     mode="multicast" if mode.startswith("multicast") else "peer")
             how = ("one multimem.st per record through the NVSwitch multicast address" if mode == "multicast" else
+                   "each warp stages the records of 32 consecutive rays in shared memory and sends the 512-byte block with ONE cp.async.bulk "
+                   "to the NVSwitch multicast address" if mode == "multicast_staged" else
                    "one 16-byte NVLink peer store per record and rank" if mode == "direct" else
                    "each warp stages the records of 32 consecutive rays in shared memory and sends the 512-byte block to every rank "
                    "with one cp.async.bulk (shared -> peer global over NVLink)")

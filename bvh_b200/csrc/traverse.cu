@@ -307,7 +307,8 @@ __device__ __forceinline__ void stager_flush_full(HitStager<T>& st, const HitSin
         const uint32_t src = smem_u32(st.buf + s * 32);
         const unsigned long long first = (unsigned long long)st.w->group[s] * 32ull;
         if (sinks.local) bulk_copy_s2g(sinks.local + first, src, bytes);
-        for (int p = 0; p < sinks.peer_count; ++p) bulk_copy_s2g(sinks.peer[p] + first, src, bytes);
+        if (sinks.multicast) bulk_copy_s2g(sinks.multicast + first, src, bytes);      // ONE copy, replicated to every rank by the NVSwitch
+        else for (int p = 0; p < sinks.peer_count; ++p) bulk_copy_s2g(sinks.peer[p] + first, src, bytes);
         bulk_commit();
         st.w->used &= ~(1u << s);
         st.w->draining |= 1u << s;
@@ -470,7 +471,7 @@ trace_persistent_kernel(TraceArgs<T> a) {
     HitStager<T> stager;
     if (kGather) {
         unsigned char* stage_base = smem_raw + (size_t)a.stack_entries * kTraceBlock * sizeof(U) + (kTma ? tma_smem_bytes<T>() : 0);
-        stager.init(stage_base, warp, lane, !a.hits.multicast && a.stage_hits);
+        stager.init(stage_base, warp, lane, a.stage_hits);
     }
     auto retire = [&] (unsigned long long index, const HitState<T>& h, T tmax) {
         if (kGather) stager_retire(stager, a.hits, index, make_record(h, tmax, a.prim_ids));
@@ -769,7 +770,7 @@ trace_wide_kernel(TraceArgs<float> a) {
     HitStager<float> stager;
     if (kGather) {
         unsigned char* stage_base = smem_raw + (size_t)a.wide_entries * kTraceBlock * sizeof(uint32_t);
-        stager.init(stage_base, threadIdx.x >> 5, lane, !a.hits.multicast && a.stage_hits);
+        stager.init(stage_base, threadIdx.x >> 5, lane, a.stage_hits);
     }
     auto retire = [&] (unsigned long long index, const HitState<float>& h, float tmax) {
         if (kGather) stager_retire(stager, a.hits, index, make_record(h, tmax, a.prim_ids));
@@ -1091,10 +1092,10 @@ int trace_rays(const DeviceBvh<T>& bvh, const DevRay<T>* d_rays, DevHit<T>* d_hi
     }
     int rc;
     const bool any = (flags & kTraceAnyHit) != 0, robust = (flags & kTraceRobust) != 0;
-    // gather mode: the kernel variants with warp-aggregated hit stores — only when staging is on and there is no multicast
-    // address; the plain variants deliver the records with store_hit() (one store per record and rank / one multimem store)
-    // and carry none of the staging state (72 registers with spills and 7 blocks per SM instead of 64 and 8)
-    const bool staged = gather != nullptr && args.stage_hits && !args.hits.multicast;
+    // gather mode: the kernel variants with warp-aggregated hit stores when staging is on (one bulk copy per 32 records and
+    // rank, or ONE bulk copy to the multicast address); otherwise the plain variants deliver the records with store_hit()
+    // (one store per record and rank / one multimem store) and carry none of the staging code
+    const bool staged = gather != nullptr && args.stage_hits;
     if (args.variant == 3) args.inner_budget = tunables().wide_budget.load();
     bvh.last_kernel = stats ? kKernelStats : simple ? kKernelSimple : args.variant == 3 ? kKernelWide : args.variant == 2 ? kKernelPair
                     : args.use_tma ? kKernelPersistentTma : kKernelPersistent;

@@ -94,9 +94,10 @@ BVH_API void bvh_host_free(void* ptr);
 BVH_API int bvh_cuda_trim(int device);
 /* Process-wide switches for experiments, A/B measurements and tests (the defaults are the measured best):
  * "morton_bits" 0|30|63, "sah_treelets" -1|0|1, "hierarchy" 0|64|128|256, "e2e_chunks", "variant" 0|1,
- * "use_wide" 0|1, "inner_budget", "wide_budget", "watchdog", "gather_staging" 0|1,
- * "sort_onesweep" 0|1, "treelet_blocks" 2|3|4.  Initial values come from the BVH_B200_<NAME>
- * environment variables, read once when the library is first used. */
+ * "use_wide" 0|1, "inner_budget", "refill_min" 1..32 (idle lanes a warp waits for before it draws new rays),
+ * "chunk_rays" (consecutive rays a warp claims at a time), "wide_budget", "watchdog", "gather_staging" 0|1,
+ * "sort_onesweep" 0|1, "treelet_blocks" 2|3|4, "stack_round", "smem_carveout" -1|0..100.  Initial values come from
+ * the BVH_B200_<NAME> environment variables, read once when the library is first used; unknown names are an error. */
 BVH_API int bvh_set_option(const char* name, long value);
 /* Subtree reinsertion (reference ReinsertionOptimizer::optimize, reinsertion_optimizer.h:27-30,218-267) on a
  * caller-owned node array in the reference layout: node_count nodes of Node<float|double, dim> (2*dim bounds as

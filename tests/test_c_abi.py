@@ -93,3 +93,22 @@ def test_product_never_touches_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                     text = open(os.path.join(dirpath, f), errors="ignore").read()
                     assert "pyoracle" not in text and "liboracle" not in text and "bvh_oracle" not in text and "_ref/" not in text, f
+
+
+def test_set_option_knows_every_documented_switch(library):
+    """bvh_set_option: every switch include/bvh_b200.h documents is accepted (needs no GPU), unknown names are an error."""
+    import re
+    header = open(os.path.join(ROOT, "include", "bvh_b200.h")).read()
+    doc = header[header.index("Process-wide switches"):header.index("BVH_API int bvh_set_option")]
+    names = re.findall(r'"([a-z0-9_]+)"', doc)
+    assert {"refill_min", "inner_budget", "chunk_rays", "variant", "sah_treelets", "smem_carveout"} <= set(names)
+    library.bvh_set_option.argtypes = [C.c_char_p, C.c_long]
+    defaults = {"morton_bits": 0, "sah_treelets": -1, "hierarchy": 128, "e2e_chunks": 0, "variant": 0, "use_wide": 0, "inner_budget": 8,
+                "refill_min": 8, "chunk_rays": 64, "wide_budget": 4, "watchdog": 1 << 26, "gather_staging": 1, "sort_onesweep": 1,
+                "treelet_blocks": 3, "stack_round": 2, "smem_carveout": -1}
+    for name in names:
+        assert name in defaults, f"{name}: documented but its default is not listed in this test"
+        assert library.bvh_set_option(name.encode(), defaults[name]) == 0, name
+    assert library.bvh_set_option(b"no_such_switch", 1) != 0
+    library.bvh_last_error.restype = C.c_char_p
+    assert b"unknown option" in library.bvh_last_error()

@@ -39,10 +39,10 @@ if kernel == "wide":                       # incoherent order inside every shard
 mine = np.ascontiguousarray(all_rays[rank * rows * img:(rank + 1) * rows * img])
 bvh = api.Bvh.build_triangles(tris)
 d_rays = torch.from_numpy(mine).to(device)
-if mode == "direct":
+if mode in ("direct", "multicast"):        # one store / one multimem store per record; the other modes stage 32 records per bulk copy
     api.set_option("gather_staging", 0)
 flags = api.DEVICE_POINTERS | (api.KERNEL_WIDE if kernel == "wide" else 0)
-tracer = FusedGatherTracer(bvh, d_rays, 4, flags=flags, mode="multicast" if mode == "multicast" else "peer")
+tracer = FusedGatherTracer(bvh, d_rays, 4, flags=flags, mode="multicast" if mode.startswith("multicast") else "peer")
 for _ in range(3):                         # three steps: both halves of the double buffer are used
     tracer.step()
 tracer.check()
@@ -84,7 +84,7 @@ def _free_port():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,kernel", [("peer", "auto"), ("peer", "wide"), ("direct", "auto"), ("multicast", "auto")])
+@pytest.mark.parametrize("mode,kernel", [("peer", "auto"), ("peer", "wide"), ("direct", "auto"), ("multicast", "auto"), ("multicast_staged", "auto")])
 def test_gathered_records_on_a_non_owner_rank_match_the_reference(gpu_lib, tmp_path, mode, kernel):
     world = min(gpu_lib.device_count(), 4)
     if world < 2:
@@ -95,7 +95,7 @@ def test_gathered_records_on_a_non_owner_rank_match_the_reference(gpu_lib, tmp_p
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
                          capture_output=True, text=True, timeout=600, env=env)
-    if mode == "multicast" and "no multicast address" in (res.stdout + res.stderr):
+    if mode.startswith("multicast") and "no multicast address" in (res.stdout + res.stderr):
         pytest.skip("the fabric offers no multicast address")
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("-> ok") == world, res.stdout

@@ -744,3 +744,37 @@ def test_sorted_ray_order_keeps_the_answers(gpu_lib, dtype):
         wide = bvh.intersect_rays(rays, flags=api.KERNEL_WIDE)
         wide_sorted = bvh.intersect_rays(rays, flags=api.KERNEL_WIDE | api.SORT_RAYS)
         assert np.array_equal(wide_sorted.view(np.uint8), wide.view(np.uint8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_traversal_switches_keep_the_answers(gpu_lib, oracle, dtype):
+    """Scheduling switches of the persistent kernel — refill threshold, inner budget, size of a warp's private run, ray
+    staging (streaming / TMA), stack rounding, shared-memory carve-out — decide WHEN a ray is traversed, never how: the
+    hit records (closest hit and any-hit, same tree) must be bit-identical for every setting, and equal to the oracle's."""
+    api = gpu_lib
+    tris = scenes.soup(120_000, seed=11).astype(dtype)
+    rays = np.concatenate([scenes.make_primary("soup", 400, 300), scenes.incoherent_rays(tris.astype(np.float32), 80_003, seed=5)]).astype(dtype)
+    bvh = api.Bvh.build_triangles(tris)
+    defaults = {"refill_min": 8, "inner_budget": 8, "chunk_rays": 64, "variant": 0, "stack_round": 2, "smem_carveout": -1}
+    base = bvh.intersect_rays(rays)
+    base_any = bvh.intersect_rays(rays, flags=api.ANY_HIT)
+    bounds, index_values, prim_ids = bvh.arrays()
+    tree = oracle.from_arrays(bounds, index_values, prim_ids)
+    oracle.set_triangles(tree, tris)
+    sample = np.arange(0, rays.shape[0], 7)
+    assert_hits_equal(hits_tuple(base[sample]), oracle.trace(tree, rays[sample], flags=O_LOWEST), "default switches vs oracle")
+    settings = [{"refill_min": 1}, {"refill_min": 32}, {"refill_min": 20, "inner_budget": 1}, {"inner_budget": 0}, {"chunk_rays": 32},
+                {"chunk_rays": 1024}, {"variant": 1}, {"variant": 1, "chunk_rays": 256, "refill_min": 3}, {"stack_round": 8},
+                {"smem_carveout": 100}, {"smem_carveout": 0}]
+    try:
+        for setting in settings:
+            for name, value in {**defaults, **setting}.items():
+                api.set_option(name, value)
+            got = bvh.intersect_rays(rays)
+            assert np.array_equal(got.view(np.uint8), base.view(np.uint8)), setting
+            got_any = bvh.intersect_rays(rays, flags=api.ANY_HIT)
+            assert np.array_equal(got_any.view(np.uint8), base_any.view(np.uint8)), setting
+    finally:
+        for name, value in defaults.items():
+            api.set_option(name, value)

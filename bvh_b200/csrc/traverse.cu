@@ -31,6 +31,14 @@ namespace bvhb200 {
 
 namespace {
 
+// Resident blocks per SM the persistent kernel's registers are limited for (float, the variants without hit staging):
+// 8 -> 64 registers, 9 -> 56 (10 / 12 bytes of spills), 10 -> 48 (34 / 28 bytes).  Measured on the B200 (profiles/
+// r02_run15_occupancy_ab.txt): soup-1M 3522 / 3665 / 3658 Mrays/s, grid-1M 6552 / 6794 / 6807, c3 1901 / 1973 / 1955 — the
+// final-state kernel saturates no pipe (L1 74 %, issue 70 %), so four more warps per SM to hide latency pay.  The variants
+// with warp-staged hit stores (kGather) keep 8: that is the form the 8-GPU runs measured.
+#ifndef BVH_TRACE_BLOCKS
+#define BVH_TRACE_BLOCKS 9
+#endif
 constexpr int kTraceBlock = 128;
 constexpr int kChunkRays = 128;          // rays claimed per global atomic by one warp
 
@@ -424,7 +432,7 @@ template <typename T> __host__ __device__ constexpr size_t tma_smem_bytes() {
 // that the ray fetch of the refill path never waits on DRAM; kTma = false reads rays with streaming
 // 128-bit loads.
 template <typename T, bool kAny, bool kRobust, bool kTma, bool kGather>
-__global__ void __launch_bounds__(kTraceBlock, sizeof(T) == 4 ? 8 : 4)
+__global__ void __launch_bounds__(kTraceBlock, sizeof(T) == 4 ? (kGather ? 8 : BVH_TRACE_BLOCKS) : 4)
 trace_persistent_kernel(TraceArgs<T> a) {
     using U = typename Real<T>::UInt;
     extern __shared__ __align__(128) unsigned char smem_raw[];

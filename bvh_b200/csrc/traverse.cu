@@ -3,14 +3,16 @@
 // Replaces the caller-side ray loop around Bvh::intersect (reference bvh.h:159-182 driven by
 // test/benchmark.cpp:340-393 / c_api/bvh_impl.h:235-250) with two kernels over a whole ray batch:
 //
-//   trace_persistent_kernel  persistent warps.  Each warp owns a private chunk of consecutive rays
-//                            claimed with one global atomicAdd per chunk; lanes whose ray finished are
-//                            refilled from the chunk by ballot + prefix rank (active-mask compaction),
-//                            so a warp keeps 32 live rays until the batch drains.  The body is a
-//                            while-while loop: an inner-node phase (every live lane descends until it
-//                            holds a leaf), a reconvergence point, then a leaf phase (Moeller-Trumbore
-//                            in registers).  The traversal stack lives in shared memory, laid out
-//                            [entry][thread] so that a warp's accesses never bank-conflict.
+//   trace_persistent_kernel  persistent warps.  Each warp owns private runs of consecutive rays claimed with one
+//                            global atomicAdd per run; idle lanes are refilled from the run by ballot + prefix rank
+//                            (active-mask compaction) once `refill_min` of them are idle, so that the rays drawn
+//                            together — neighbours — walk the top of the tree in step and share their node fetches.
+//                            The body is a while-while loop: an inner-node phase bounded to `inner_budget` steps per
+//                            lane and round, a reconvergence point, then a leaf phase (Moeller-Trumbore in
+//                            registers).  The traversal stack lives in shared memory, laid out [entry][thread] so that
+//                            a warp's accesses never bank-conflict.  kTma: the run's rays staged into shared memory by
+//                            bulk async copies instead of streaming loads; kGather: hit records delivered to every
+//                            rank's gathered array by warp-staged bulk copies (fused multi-GPU gather).
 //   trace_simple_kernel      one thread per ray, same stack machine; also the statistics variant that
 //                            counts inner steps / leaves / triangle tests per ray (the reference's
 //                            InnerFn hook, bvh.h:168) which defines the algorithmic bytes of DESIGN.md.

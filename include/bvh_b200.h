@@ -53,7 +53,7 @@ enum bvh_intersect_flags {
     BVH_DEVICE_POINTERS  = 1u << 3,  /* rays/hits/vertices are device pointers; the call is stream-ordered */
     BVH_KERNEL_SIMPLE    = 1u << 8,  /* one-thread-per-ray kernel instead of the persistent one (diagnostics) */
     /* kernel selection, for diagnostics and A/B measurements; default = the fastest measured variant */
-    BVH_KERNEL_NO_TMA    = 1u << 9,  /* persistent, one lane per ray, rays read with streaming loads */
+    BVH_KERNEL_NO_TMA    = 1u << 9,  /* persistent, one lane per ray, rays read with streaming loads (the default form) */
     BVH_KERNEL_TMA       = 1u << 10, /* persistent, one lane per ray, ray chunks staged with cp.async.bulk (TMA) */
     BVH_KERNEL_PAIR      = 1u << 11, /* persistent, two lanes per ray (one child box each) */
     BVH_KERNEL_WIDE      = 1u << 12, /* persistent, compressed 4-wide tree derived from the binary one (float; canonical

@@ -111,6 +111,21 @@ def usable_cpus():
     return {"usable": usable, "affinity": affinity, "cgroup_quota": quota, "hardware": os.cpu_count()}
 
 
+def gather_candidates(world: int, requested: str) -> list:
+    """Delivery forms of the fused gather to try, in order; an empty list means the NCCL path.  `auto` follows the
+    measurements of DESIGN.md §7: two ranks — one multimem store per record; up to AUTO_DIRECT_MAX_RANKS — one peer store
+    per record and rank; beyond — warp-staged bulk copies, to the multicast address when the fabric has one."""
+    if world == 1 or requested == "nccl":
+        return []
+    if requested != "auto":
+        return [requested]
+    if world == 2:
+        return ["multicast", "direct", "peer"]
+    if world <= AUTO_DIRECT_MAX_RANKS:
+        return ["direct", "peer"]
+    return ["multicast_staged", "peer", "direct"]
+
+
 def bind_to_gpu_numa_node(local_rank: int):
     """Multi-rank runs: pin this rank (and therefore the first-touch placement of its pinned host buffers)
     to the NUMA node its GPU hangs off.  Eight ranks streaming 70 GB/s each through whatever socket the
@@ -447,9 +462,7 @@ def main():
     # 0.90); up to 4 ranks one peer store per record and rank (each costs ~1-2 % of the kernel: scripts/gather_probe.py); beyond
     # that warp-staged bulk copies (a fixed ~6 %, independent of the number of ranks) — ONE copy per 32 records to the multicast
     # address when the fabric has one (8 ranks: 0.881), else one copy per rank (0.836); NCCL (below) if none works
-    auto = (["multicast", "direct", "peer"] if world == 2 else ["direct", "peer"] if world <= AUTO_DIRECT_MAX_RANKS
-            else ["multicast_staged", "peer", "direct"])
-    candidates = [] if world == 1 else (auto if args.gather == "auto" else [] if args.gather == "nccl" else [args.gather])
+    candidates = gather_candidates(world, args.gather)
     for mode in candidates:
         try:
             from bvh_b200.multi_gpu import FusedGatherTracer

@@ -39,3 +39,16 @@ def test_cuda_arm_refuses_to_run_without_a_gpu():
     assert out.returncode != 0
     assert "no CPU fallback" in (out.stdout + out.stderr)
     assert not any(l.startswith("{") for l in out.stdout.splitlines())
+
+
+def test_gather_form_follows_the_rank_count():
+    """bench.py --gather auto: the delivery form of the fused gather is chosen by the number of ranks as measured
+    (DESIGN.md §7), an explicit request is taken literally, one rank and `nccl` mean the NCCL / plain path."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.gather_candidates(1, "auto") == [] and bench.gather_candidates(8, "nccl") == []
+    assert bench.gather_candidates(2, "auto")[0] == "multicast"
+    assert bench.gather_candidates(3, "auto")[0] == "direct" and bench.gather_candidates(4, "auto")[0] == "direct"
+    assert bench.gather_candidates(8, "auto") == ["multicast_staged", "peer", "direct"]        # falls back when there is no multicast address
+    for mode in ("multicast", "multicast_staged", "peer", "direct"):
+        assert bench.gather_candidates(8, mode) == [mode]
